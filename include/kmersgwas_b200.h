@@ -1,0 +1,153 @@
+/* kmersgwas_b200.h -- C ABI of the B200 (sm_100a) association hot path of kmersGWAS.
+ *
+ * This is the drop-in boundary.  The reference has no plugin/FFI layer: its
+ * boundary is the public C++ surface of MultipleKmersDataBases / BestAssociationsHeap called from
+ * the two CLIs.  The host-side C++ mirror of that surface lives in kmersgwas_b200/host/ (same class
+ * and method names) and calls ONLY the functions below; a reference maintainer would bind exactly
+ * these from the reference classes (INTEGRATION.md shows the patch).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no STL / torch types, no exceptions cross this boundary;
+ *   - every function returns kg_status (0 = ok); kg_last_error(ctx) gives the message
+ *     (kg_last_error(NULL) for failures of kg_ctx_create);
+ *   - one kg_ctx per GPU, driven by one host thread at a time; different contexts are fully
+ *     concurrent; device work is issued on the context's stream and is asynchronous until a
+ *     *_fetch / kg_sync call;
+ *   - "rows" arguments are RAW .table rows exactly as on disk
+ *     (/root/reference/src/kmers_merge_multiple_databaes.cpp:60-73): per row one u64 k-mer followed
+ *     by W_file = ceil(N_file/64) u64 presence words, no padding, little endian.  The pointer may
+ *     be host memory (pageable or pinned; copied through the context's pinned staging ring) or
+ *     device memory of the context's GPU (used in place);
+ *   - there is NO CPU fallback: without a CUDA device kg_ctx_create fails with KG_ERR_CUDA.
+ */
+#ifndef KMERSGWAS_B200_H
+#define KMERSGWAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KG_ABI_VERSION 1
+
+typedef int kg_status;
+enum {
+	KG_OK = 0,
+	KG_ERR_INVALID = 1,       /* bad argument / shape */
+	KG_ERR_CUDA = 2,          /* CUDA runtime error (message has the cudaError string) */
+	KG_ERR_NOMEM = 3,         /* host or device allocation failed */
+	KG_ERR_HITS_OVERFLOW = 4, /* more hits than the hit buffer holds: resubmit the tile in smaller pieces */
+	KG_ERR_STATE = 5          /* call sequence error (e.g. fetch without submit) */
+};
+
+typedef struct kg_ctx kg_ctx;
+
+/* Table / column geometry.  Replaces the members MultipleKmersDataBases derives in its ctor and in
+ * create_map_from_all_DBs (/root/reference/src/kmers_multiple_databases.cpp:39-94, 297-311). */
+typedef struct kg_shape {
+	uint64_t n_file;          /* accessions (columns) in the .table file          (m_accessions_db_file) */
+	uint64_t n_used;          /* accessions used = memory columns, phenotype order (m_accessions)        */
+	const uint32_t *map_word; /* [n_used] file word index of memory column i       (m_map_word_index)    */
+	const uint32_t *map_bit;  /* [n_used] bit index inside that word               (m_map_bit_index)     */
+} kg_shape;
+
+/* One admitted association: what add_kmers_to_heap hands to BestAssociationsHeap::add_association
+ * (/root/reference/src/kmers_multiple_databases.cpp:281-283). */
+typedef struct kg_hit {
+	uint64_t row;    /* caller's row id: first_row_id + index of the row inside the submitted tile */
+	uint64_t kmer;   /* k-mer word of the row */
+	double score;    /* bit-identical to calculate_kmer_score (:327-363) */
+	uint32_t pheno;  /* phenotype column index */
+	uint32_t pad_;
+} kg_hit;
+
+/* Options for kg_set_option */
+enum {
+	KG_OPT_SCAN_ENGINE = 1, /* 0 = auto, 1 = exact fp32-order kernel on every row, 2 = int8 tensor filter + exact refine */
+	KG_OPT_HIT_CAPACITY = 2, /* number of kg_hit the device hit buffer holds (default 1<<22); set before first submit */
+	KG_OPT_KINSHIP_ENGINE = 3 /* 0 = auto, 1 = popcount kernel, 2 = int8 tensor-core Gram */
+};
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int kg_abi_version(void);
+/* device: CUDA ordinal.  stream: a cudaStream_t (as void*) to issue all work on, or NULL to let the
+ * context create its own non-blocking stream. */
+kg_status kg_ctx_create(int device, const kg_shape *shape, void *stream, kg_ctx **out);
+void kg_ctx_destroy(kg_ctx *ctx);
+const char *kg_last_error(const kg_ctx *ctx);
+kg_status kg_set_option(kg_ctx *ctx, int option, int64_t value);
+kg_status kg_sync(kg_ctx *ctx);
+
+/* ---- association scan ------------------------------------------------------------------------
+ * Replaces, per batch, the P calls of MultipleKmersDataBases::add_kmers_to_heap
+ * (/root/reference/src/associate_kmers.cpp:134-141; kmers_multiple_databases.cpp:275-295, 327-363)
+ * and the MAC filter of load_kmers (:117-121). */
+
+/* y: [n_pheno][n_used] float32, UN-permuted, memory (phenotype-file) order -- the vectors the
+ * reference passes to add_kmers_to_heap.  min_count: the effective minor allele count
+ * (associate_kmers.cpp:99-102).  May be called again to change phenotypes. */
+kg_status kg_scan_set_phenotypes(kg_ctx *ctx, const float *y, uint32_t n_pheno, uint64_t min_count);
+
+/* thresholds[p]: only (row, p) with score > thresholds[p] are reported; a negative threshold reports
+ * every row passing the MAC filter (heap not yet full).  The caller passes the current
+ * BestAssociationsHeap::lowest_score of each phenotype's heap
+ * (/root/reference/src/best_associations_heap.cpp:43-59: strict '>'); because that value never
+ * decreases, stale (lower) thresholds are always safe. */
+kg_status kg_scan_set_thresholds(kg_ctx *ctx, const double *thresholds, uint32_t n_pheno);
+
+/* Score one tile of raw rows against all phenotypes; asynchronous.  Hits are appended to the
+ * context's hit buffer.  first_row_id: id given to the tile's first row (kg_hit.row). */
+kg_status kg_scan_submit(kg_ctx *ctx, const uint64_t *rows, uint64_t n_rows, uint64_t first_row_id);
+
+/* Wait for all submitted tiles; copy out up to cap hits, sorted by (pheno, row).  *n_hits = number
+ * available (call again with a larger buffer if > cap; hits stay until kg_scan_clear_hits).
+ * rows_seen / rows_kept (either may be NULL): totals since kg_scan_set_phenotypes -- rows_kept is the
+ * reference's number_of_insertion() (.tested_kmers, associate_kmers.cpp:203-205). */
+kg_status kg_scan_fetch(kg_ctx *ctx, kg_hit *out, size_t cap, size_t *n_hits,
+                        uint64_t *rows_seen, uint64_t *rows_kept);
+kg_status kg_scan_clear_hits(kg_ctx *ctx);
+
+/* Testing / --k_mers_scores aid: exact scores of EVERY row of one tile.
+ * keep[r] = row passes the MAC filter; scores[p * n_rows + r] valid where keep[r].  Host outputs. */
+kg_status kg_scan_scores_dense(kg_ctx *ctx, const uint64_t *rows, uint64_t n_rows,
+                               uint8_t *keep, double *scores);
+
+/* ---- kinship ----------------------------------------------------------------------------------
+ * Replaces MultipleKmersDataBases::update_emma_kinshhip_calculation
+ * (/root/reference/src/kmers_multiple_databases.cpp:418-438) over the rows load_kmers keeps. */
+
+/* Start (or restart) accumulation.  accum_dev: optional caller-owned DEVICE buffer of
+ * kg_kinship_accum_len(ctx) u64 (e.g. a torch int64 tensor, so that the caller can all-reduce it
+ * with NCCL between kg_kinship_submit and kg_kinship_fetch); NULL = context-owned.
+ * The buffer is zeroed. Layout: [n_used*n_used] Gram counts G[i][j] = #kept rows with both bits
+ * set (lower triangle j<=i; the diagonal G[i][i] is the column count c[i]), then [1] kept rows M.
+ * Every entry is a plain sum over rows, so shards add: all-reduce(sum) the whole buffer. */
+kg_status kg_kinship_begin(kg_ctx *ctx, uint64_t min_count, uint64_t *accum_dev);
+size_t kg_kinship_accum_len(const kg_ctx *ctx);
+kg_status kg_kinship_submit(kg_ctx *ctx, const uint64_t *rows, uint64_t n_rows);
+/* Wait; convert the (possibly all-reduced) accumulator into the reference's matrix:
+ * ibs[i*n_used + j] = M - c[i] - c[j] + 2 G[i][j] for j < i (other entries 0), *kept_rows = M. */
+kg_status kg_kinship_fetch(kg_ctx *ctx, uint64_t *ibs, uint64_t *kept_rows);
+
+/* ---- pinned host memory ----------------------------------------------------------------------
+ * Page-locked buffers for the host-side tile reader (so that it needs no CUDA headers); tiles handed
+ * to *_submit from such buffers are copied with one asynchronous DMA instead of the staging ring.
+ * Host rows passed to *_submit must stay valid and unchanged until the next *_fetch / kg_sync. */
+kg_status kg_host_alloc(kg_ctx *ctx, size_t bytes, void **out);
+void kg_host_free(kg_ctx *ctx, void *p);
+
+/* ---- synthetic tiles (bench / tests) -----------------------------------------------------------
+ * Fill DEVICE memory with n_rows raw rows of the counter-based generator documented in
+ * oracle/oracle.c (kgo_synth_rows): bit-identical on host and device. */
+kg_status kg_synth_rows_device(kg_ctx *ctx, uint64_t seed, uint64_t first_row, uint64_t n_rows,
+                               uint64_t *rows_dev);
+
+/* Number of kernels this library launched since the context was created (bench "gpu_launches"). */
+uint64_t kg_launch_count(const kg_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMERSGWAS_B200_H */

@@ -1,0 +1,203 @@
+"""ctypes binding of include/kmersgwas_b200.h (lib/libkmersgwas_b200.so).
+
+This is plumbing for tests and bench.py; the product host code is the C++ mirror of the reference
+classes in kmersgwas_b200/host/.  There is no CPU fallback: if the CUDA library is missing or no
+device is present, calls fail loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import build as _build
+
+KG_OK = 0
+KG_ERR_HITS_OVERFLOW = 4
+OPT_SCAN_ENGINE, OPT_HIT_CAPACITY, OPT_KINSHIP_ENGINE = 1, 2, 3
+
+HIT_DTYPE = np.dtype([("row", "<u8"), ("kmer", "<u8"), ("score", "<f8"), ("pheno", "<u4"), ("pad", "<u4")])
+
+# every symbol include/kmersgwas_b200.h declares
+ABI_SYMBOLS = [
+    "kg_abi_version", "kg_ctx_create", "kg_ctx_destroy", "kg_last_error", "kg_set_option", "kg_sync",
+    "kg_scan_set_phenotypes", "kg_scan_set_thresholds", "kg_scan_submit", "kg_scan_fetch",
+    "kg_scan_clear_hits", "kg_scan_scores_dense", "kg_kinship_begin", "kg_kinship_accum_len",
+    "kg_kinship_submit", "kg_kinship_fetch", "kg_host_alloc", "kg_host_free", "kg_synth_rows_device",
+    "kg_launch_count",
+]
+
+
+class KgShape(C.Structure):
+    _fields_ = [("n_file", C.c_uint64), ("n_used", C.c_uint64),
+                ("map_word", C.POINTER(C.c_uint32)), ("map_bit", C.POINTER(C.c_uint32))]
+
+
+class KgError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"kg status {status}: {msg}")
+        self.status = status
+
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return _build.cuda_lib_path()
+
+
+def load():
+    """Load the CUDA library (it must have been built in-tree: python -m kmersgwas_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not p.exists():
+        raise RuntimeError(f"{p} is missing: run `python -m kmersgwas_b200.build` (no CPU fallback exists)")
+    lib = C.CDLL(str(p))
+    vp, u64, u32p, u64p = C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    lib.kg_abi_version.restype = C.c_int
+    lib.kg_ctx_create.argtypes = [C.c_int, C.POINTER(KgShape), vp, C.POINTER(vp)]
+    lib.kg_ctx_destroy.argtypes = [vp]
+    lib.kg_ctx_destroy.restype = None
+    lib.kg_last_error.argtypes = [vp]
+    lib.kg_last_error.restype = C.c_char_p
+    lib.kg_set_option.argtypes = [vp, C.c_int, C.c_int64]
+    lib.kg_sync.argtypes = [vp]
+    lib.kg_scan_set_phenotypes.argtypes = [vp, C.POINTER(C.c_float), C.c_uint32, u64]
+    lib.kg_scan_set_thresholds.argtypes = [vp, C.POINTER(C.c_double), C.c_uint32]
+    lib.kg_scan_submit.argtypes = [vp, vp, u64, u64]
+    lib.kg_scan_fetch.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t), u64p, u64p]
+    lib.kg_scan_clear_hits.argtypes = [vp]
+    lib.kg_scan_scores_dense.argtypes = [vp, vp, u64, C.POINTER(C.c_uint8), C.POINTER(C.c_double)]
+    lib.kg_kinship_begin.argtypes = [vp, u64, vp]
+    lib.kg_kinship_accum_len.argtypes = [vp]
+    lib.kg_kinship_accum_len.restype = C.c_size_t
+    lib.kg_kinship_submit.argtypes = [vp, vp, u64]
+    lib.kg_kinship_fetch.argtypes = [vp, u64p, u64p]
+    lib.kg_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    lib.kg_host_free.argtypes = [vp, vp]
+    lib.kg_host_free.restype = None
+    lib.kg_synth_rows_device.argtypes = [vp, u64, u64, u64, vp]
+    lib.kg_launch_count.argtypes = [vp]
+    lib.kg_launch_count.restype = u64
+    _lib = lib
+    return lib
+
+
+def _rows_ptr(rows):
+    """rows: numpy uint64 array (host) or an int device/host address."""
+    if isinstance(rows, np.ndarray):
+        assert rows.dtype == np.uint64 and rows.flags.c_contiguous
+        return rows.ctypes.data
+    return int(rows)
+
+
+class Context:
+    """One kg_ctx (one GPU).  Thin, 1:1 with the C ABI."""
+
+    def __init__(self, n_file: int, map_word, map_bit, device: int = 0, stream: int | None = None):
+        self._lib = load()
+        self._mw = np.ascontiguousarray(map_word, dtype=np.uint32)
+        self._mb = np.ascontiguousarray(map_bit, dtype=np.uint32)
+        self.n_file = int(n_file)
+        self.n_used = len(self._mw)
+        self.w_file = (self.n_file + 63) // 64
+        shape = KgShape(self.n_file, self.n_used, self._mw.ctypes.data_as(C.POINTER(C.c_uint32)),
+                        self._mb.ctypes.data_as(C.POINTER(C.c_uint32)))
+        h = C.c_void_p()
+        st = self._lib.kg_ctx_create(device, C.byref(shape), C.c_void_p(stream or 0), C.byref(h))
+        if st != KG_OK:
+            raise KgError(st, self._lib.kg_last_error(None).decode())
+        self._h = h
+        self.n_pheno = 0
+
+    @classmethod
+    def identity(cls, n_file: int, **kw):
+        idx = np.arange(n_file)
+        return cls(n_file, idx // 64, idx % 64, **kw)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.kg_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, st):
+        if st != KG_OK:
+            raise KgError(st, self._lib.kg_last_error(self._h).decode())
+
+    def set_option(self, opt: int, value: int):
+        self._chk(self._lib.kg_set_option(self._h, opt, value))
+
+    def sync(self):
+        self._chk(self._lib.kg_sync(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(self._lib.kg_launch_count(self._h))
+
+    # ---- scan
+    def set_phenotypes(self, y: np.ndarray, min_count: int):
+        y = np.ascontiguousarray(y, dtype=np.float32)
+        assert y.ndim == 2 and y.shape[1] == self.n_used
+        self.n_pheno = y.shape[0]
+        self._chk(self._lib.kg_scan_set_phenotypes(self._h, y.ctypes.data_as(C.POINTER(C.c_float)),
+                                                   self.n_pheno, int(min_count)))
+
+    def set_thresholds(self, thr):
+        thr = np.ascontiguousarray(thr, dtype=np.float64)
+        assert thr.shape == (self.n_pheno,)
+        self._chk(self._lib.kg_scan_set_thresholds(self._h, thr.ctypes.data_as(C.POINTER(C.c_double)), self.n_pheno))
+
+    def scan_submit(self, rows, n_rows: int, first_row_id: int = 0):
+        self._keepalive = rows
+        self._chk(self._lib.kg_scan_submit(self._h, _rows_ptr(rows), int(n_rows), int(first_row_id)))
+
+    def scan_fetch(self, clear: bool = True):
+        """-> (hits structured array sorted by (pheno,row), rows_seen, rows_kept)"""
+        n = C.c_size_t(0)
+        seen, kept = C.c_uint64(0), C.c_uint64(0)
+        self._chk(self._lib.kg_scan_fetch(self._h, None, 0, C.byref(n), C.byref(seen), C.byref(kept)))
+        hits = np.zeros(n.value, dtype=HIT_DTYPE)
+        if n.value:
+            self._chk(self._lib.kg_scan_fetch(self._h, hits.ctypes.data, n.value, C.byref(n), None, None))
+        if clear:
+            self._chk(self._lib.kg_scan_clear_hits(self._h))
+        return hits, int(seen.value), int(kept.value)
+
+    def scores_dense(self, rows, n_rows: int):
+        keep = np.zeros(n_rows, dtype=np.uint8)
+        scores = np.zeros((self.n_pheno, n_rows), dtype=np.float64)
+        self._chk(self._lib.kg_scan_scores_dense(self._h, _rows_ptr(rows), int(n_rows),
+                                                 keep.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                 scores.ctypes.data_as(C.POINTER(C.c_double))))
+        return keep.astype(bool), scores
+
+    # ---- kinship
+    def kinship_accum_len(self) -> int:
+        return int(self._lib.kg_kinship_accum_len(self._h))
+
+    def kinship_begin(self, min_count: int, accum_dev: int | None = None):
+        self._chk(self._lib.kg_kinship_begin(self._h, int(min_count), C.c_void_p(accum_dev or 0)))
+
+    def kinship_submit(self, rows, n_rows: int):
+        self._keepalive = rows
+        self._chk(self._lib.kg_kinship_submit(self._h, _rows_ptr(rows), int(n_rows)))
+
+    def kinship_fetch(self, want_matrix: bool = True):
+        m = C.c_uint64(0)
+        ibs = np.zeros((self.n_used, self.n_used), dtype=np.uint64) if want_matrix else None
+        p = ibs.ctypes.data_as(C.POINTER(C.c_uint64)) if want_matrix else None
+        self._chk(self._lib.kg_kinship_fetch(self._h, p, C.byref(m)))
+        return ibs, int(m.value)
+
+    # ---- synthetic
+    def synth_rows_device(self, seed: int, first_row: int, n_rows: int, rows_dev: int):
+        self._chk(self._lib.kg_synth_rows_device(self._h, int(seed), int(first_row), int(n_rows), C.c_void_p(rows_dev)))

@@ -1,0 +1,702 @@
+// kg_abi.cu -- implementation of include/kmersgwas_b200.h (the C ABI) on top of the sm_100a kernels.
+// No CPU fallback: every entry point needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kg_common.cuh"
+#include "kg_kinship_popc.cuh"
+#include "kg_scan_exact.cuh"
+#include "kg_synth.cuh"
+#include "kg_tc_state.cuh"
+
+// ------------------------------------------------------------------------------------- context
+struct kg_ctx {
+	int device = 0;
+	int sm_count = KG_SM_COUNT_DEFAULT;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	cudaStream_t copy_stream = nullptr;
+	std::string err;
+	uint64_t launches = 0;
+
+	// geometry
+	uint64_t n_file = 0, n_used = 0;
+	uint32_t w_file = 0, w_mem = 0, nb = 0;
+	bool identity = false;
+	std::vector<uint32_t> map_word, map_bit;
+	uint32_t *d_map_mem = nullptr;   // [n_used] (word<<6)|bit of memory column i
+	uint32_t *d_map_lane = nullptr;  // [nb*128] same, in lane order (4b+L)*32+t ; 0xFFFFFFFF = pad
+	uint64_t *d_file_mask = nullptr; // [w_file]
+	uint64_t *d_mem_mask = nullptr;  // [w_mem]
+	uint32_t *d_mask32 = nullptr;    // [nb*4]
+
+	// phenotypes
+	uint32_t n_pheno = 0, p_alloc = 0, pt = 8;
+	uint64_t min_count = 0;
+	float *d_y_lane = nullptr;
+	float *d_sums = nullptr;
+	double *d_thr = nullptr;
+	std::vector<float> h_y;      // [P][n_used] as given (tensor filter quantises from it)
+	std::vector<float> h_sums;
+	std::vector<double> h_thr;
+
+	// hits / counters
+	kg_hit *d_hits = nullptr;
+	uint64_t hit_capacity = 1ull << 22;
+	unsigned long long *d_counters = nullptr;  // [0] hits  [1] kept  [2] pairs [3] spare
+	std::vector<kg_hit> h_hits;
+	bool hits_sorted = true;
+	uint64_t rows_seen = 0, rows_seen_committed = 0, kept_committed = 0;
+	bool pending = false;
+
+	// tile upload
+	uint64_t *d_tile[2] = {nullptr, nullptr};
+	size_t tile_cap[2] = {0, 0};
+	cudaEvent_t slot_free[2] = {nullptr, nullptr}, slot_ready[2] = {nullptr, nullptr};
+	int next_slot = 0, cur_slot = -1;
+	void *h_stage[2] = {nullptr, nullptr};
+	cudaEvent_t stage_free[2] = {nullptr, nullptr};
+	static constexpr size_t kStageBytes = 16u << 20;
+
+	// squeeze scratch
+	uint64_t *d_squeezed = nullptr;
+	size_t squeezed_cap = 0;
+
+	// kinship
+	unsigned long long *d_accum = nullptr;
+	bool own_accum = false, kin_active = false;
+	uint64_t kin_min_count = 0;
+	uint32_t *d_keep_bits = nullptr;
+	size_t keep_bits_cap = 0;
+	unsigned long long *d_ibs = nullptr;
+
+	// tensor-core engine state (kg_tc.cuh)
+	KgTcState tc;
+
+	int scan_engine = 0, kin_engine = 0;
+};
+
+static std::string g_create_error;
+
+#define KG_FAIL(ctx, code, ...)                                   \
+	do {                                                          \
+		char buf_[512];                                           \
+		snprintf(buf_, sizeof buf_, __VA_ARGS__);                 \
+		(ctx)->err = buf_;                                        \
+		return (code);                                            \
+	} while (0)
+
+#define KG_CUDA(ctx, expr)                                                                   \
+	do {                                                                                     \
+		cudaError_t e_ = (expr);                                                             \
+		if (e_ != cudaSuccess) {                                                             \
+			char buf_[512];                                                                  \
+			snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+			         __FILE__, __LINE__);                                                    \
+			(ctx)->err = buf_;                                                               \
+			return KG_ERR_CUDA;                                                              \
+		}                                                                                    \
+	} while (0)
+
+#define KG_LAUNCH_CHECK(ctx)            \
+	do {                                \
+		(ctx)->launches++;              \
+		KG_CUDA(ctx, cudaGetLastError()); \
+	} while (0)
+
+// tensor-core engine (needs kg_ctx and the macros above)
+#include "kg_tc.cuh"
+
+template <typename T>
+static cudaError_t dev_alloc_copy(T **dst, const std::vector<T> &src) {
+	cudaError_t e = cudaMalloc((void **)dst, std::max<size_t>(src.size(), 1) * sizeof(T));
+	if (e != cudaSuccess) return e;
+	if (!src.empty()) e = cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+	return e;
+}
+
+extern "C" int kg_abi_version(void) { return KG_ABI_VERSION; }
+
+extern "C" const char *kg_last_error(const kg_ctx *ctx) {
+	return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" uint64_t kg_launch_count(const kg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static kg_status ctx_init(kg_ctx *c, int device, const kg_shape *shape, void *stream) {
+	if (!shape || !shape->map_word || !shape->map_bit || shape->n_used == 0 || shape->n_file == 0)
+		KG_FAIL(c, KG_ERR_INVALID, "kg_ctx_create: empty shape");
+	if (shape->n_used > 65000) KG_FAIL(c, KG_ERR_INVALID, "kg_ctx_create: n_used > 65000 not supported");
+	int n_dev = 0;
+	cudaError_t e = cudaGetDeviceCount(&n_dev);
+	if (e != cudaSuccess || n_dev == 0)
+		KG_FAIL(c, KG_ERR_CUDA, "kg_ctx_create: no CUDA device (%s); this library has no CPU fallback",
+		        cudaGetErrorString(e));
+	if (device < 0 || device >= n_dev) KG_FAIL(c, KG_ERR_INVALID, "kg_ctx_create: bad device %d", device);
+	KG_CUDA(c, cudaSetDevice(device));
+	c->device = device;
+	cudaDeviceProp prop;
+	KG_CUDA(c, cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10)
+		KG_FAIL(c, KG_ERR_CUDA, "kg_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
+		        device, prop.major, prop.minor);
+	c->sm_count = prop.multiProcessorCount;
+	if (stream) {
+		c->stream = (cudaStream_t)stream;
+	} else {
+		KG_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+		c->own_stream = true;
+	}
+	KG_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; i++) {
+		KG_CUDA(c, cudaEventCreateWithFlags(&c->slot_free[i], cudaEventDisableTiming));
+		KG_CUDA(c, cudaEventCreateWithFlags(&c->slot_ready[i], cudaEventDisableTiming));
+		KG_CUDA(c, cudaEventCreateWithFlags(&c->stage_free[i], cudaEventDisableTiming));
+	}
+
+	c->n_file = shape->n_file;
+	c->n_used = shape->n_used;
+	c->w_file = (uint32_t)((c->n_file + 63) / 64);
+	c->w_mem = (uint32_t)(2 * ((c->n_used + 127) / 128));  // kmers_multiple_databases.cpp:51
+	c->nb = c->w_mem / 2;
+	c->map_word.assign(shape->map_word, shape->map_word + c->n_used);
+	c->map_bit.assign(shape->map_bit, shape->map_bit + c->n_used);
+	c->identity = (c->n_used == c->n_file);
+	std::vector<uint64_t> file_mask(c->w_file, 0), mem_mask(c->w_mem, 0);
+	std::vector<uint32_t> map_mem(c->n_used), map_lane((size_t)c->nb * 128, 0xFFFFFFFFu), mask32((size_t)c->nb * 4, 0);
+	for (uint64_t i = 0; i < c->n_used; i++) {
+		const uint32_t w = c->map_word[i], b = c->map_bit[i];
+		if (w >= c->w_file || b >= 64 || (uint64_t)w * 64 + b >= c->n_file)
+			KG_FAIL(c, KG_ERR_INVALID, "kg_ctx_create: column map entry %llu out of range", (unsigned long long)i);
+		if (file_mask[w] & (1ull << b))
+			KG_FAIL(c, KG_ERR_INVALID, "kg_ctx_create: file column used twice (entry %llu)", (unsigned long long)i);
+		file_mask[w] |= 1ull << b;  // :308 m_map_mask
+		mem_mask[i >> 6] |= 1ull << (i & 63);
+		map_mem[i] = (w << 6) | b;
+		if ((uint64_t)w * 64 + b != i) c->identity = false;
+		// lane order: sample i = 128 blk + 32 L + (31 - t)
+		const uint32_t blk = (uint32_t)(i / 128), L = (uint32_t)((i % 128) / 32), t = 31 - (uint32_t)(i % 32);
+		map_lane[(size_t)(blk * 4 + L) * 32 + t] = map_mem[i];
+		mask32[blk * 4 + L] |= 1u << (i % 32);
+	}
+	KG_CUDA(c, dev_alloc_copy(&c->d_map_mem, map_mem));
+	KG_CUDA(c, dev_alloc_copy(&c->d_map_lane, map_lane));
+	KG_CUDA(c, dev_alloc_copy(&c->d_file_mask, file_mask));
+	KG_CUDA(c, dev_alloc_copy(&c->d_mem_mask, mem_mask));
+	KG_CUDA(c, dev_alloc_copy(&c->d_mask32, mask32));
+	KG_CUDA(c, cudaMalloc((void **)&c->d_counters, 8 * sizeof(unsigned long long)));
+	KG_CUDA(c, cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long)));
+	return KG_OK;
+}
+
+extern "C" kg_status kg_ctx_create(int device, const kg_shape *shape, void *stream, kg_ctx **out) {
+	if (!out) return KG_ERR_INVALID;
+	*out = nullptr;
+	kg_ctx *c = new (std::nothrow) kg_ctx();
+	if (!c) { g_create_error = "out of host memory"; return KG_ERR_NOMEM; }
+	kg_status st = ctx_init(c, device, shape, stream);
+	if (st != KG_OK) {
+		g_create_error = c->err;
+		kg_ctx_destroy(c);
+		return st;
+	}
+	*out = c;
+	return KG_OK;
+}
+
+extern "C" void kg_ctx_destroy(kg_ctx *c) {
+	if (!c) return;
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+	cudaFree(c->d_map_mem); cudaFree(c->d_map_lane); cudaFree(c->d_file_mask); cudaFree(c->d_mem_mask);
+	cudaFree(c->d_mask32); cudaFree(c->d_y_lane); cudaFree(c->d_sums); cudaFree(c->d_thr);
+	cudaFree(c->d_hits); cudaFree(c->d_counters); cudaFree(c->d_squeezed); cudaFree(c->d_keep_bits);
+	cudaFree(c->d_ibs);
+	if (c->own_accum) cudaFree(c->d_accum);
+	kg_tc_free(&c->tc);
+	for (int i = 0; i < 2; i++) {
+		cudaFree(c->d_tile[i]);
+		if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
+		if (c->slot_free[i]) cudaEventDestroy(c->slot_free[i]);
+		if (c->slot_ready[i]) cudaEventDestroy(c->slot_ready[i]);
+		if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
+	}
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+extern "C" kg_status kg_set_option(kg_ctx *c, int option, int64_t value) {
+	if (!c) return KG_ERR_INVALID;
+	switch (option) {
+	case KG_OPT_SCAN_ENGINE:
+		if (value < 0 || value > 2) KG_FAIL(c, KG_ERR_INVALID, "scan engine must be 0, 1 or 2");
+		c->scan_engine = (int)value;
+		return KG_OK;
+	case KG_OPT_HIT_CAPACITY:
+		if (value < 1) KG_FAIL(c, KG_ERR_INVALID, "hit capacity must be >= 1");
+		if (c->d_hits) KG_FAIL(c, KG_ERR_STATE, "hit capacity must be set before the first submit");
+		c->hit_capacity = (uint64_t)value;
+		return KG_OK;
+	case KG_OPT_KINSHIP_ENGINE:
+		if (value < 0 || value > 2) KG_FAIL(c, KG_ERR_INVALID, "kinship engine must be 0, 1 or 2");
+		c->kin_engine = (int)value;
+		return KG_OK;
+	default:
+		KG_FAIL(c, KG_ERR_INVALID, "unknown option %d", option);
+	}
+}
+
+extern "C" kg_status kg_sync(kg_ctx *c) {
+	if (!c) return KG_ERR_INVALID;
+	KG_CUDA(c, cudaSetDevice(c->device));
+	KG_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+	KG_CUDA(c, cudaStreamSynchronize(c->stream));
+	return KG_OK;
+}
+
+extern "C" kg_status kg_host_alloc(kg_ctx *c, size_t bytes, void **out) {
+	if (!c || !out) return KG_ERR_INVALID;
+	KG_CUDA(c, cudaSetDevice(c->device));
+	cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e));
+	return KG_OK;
+}
+
+extern "C" void kg_host_free(kg_ctx *c, void *p) {
+	(void)c;
+	if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------------------------- tile upload
+// Returns a device pointer holding the tile.  Device pointers are used in place; host pointers are
+// copied on copy_stream into one of two device slots (so the copy of tile i+1 overlaps the kernels
+// of tile i) and the compute stream is made to wait for the copy.
+static kg_status acquire_tile(kg_ctx *c, const uint64_t *rows, uint64_t n_rows, const uint64_t **dev) {
+	c->cur_slot = -1;
+	const size_t bytes = (size_t)n_rows * (c->w_file + 1) * 8;
+	cudaPointerAttributes attr;
+	cudaError_t e = cudaPointerGetAttributes(&attr, rows);
+	if (e != cudaSuccess) { cudaGetLastError(); attr.type = cudaMemoryTypeUnregistered; }
+	if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) {
+		if (attr.type == cudaMemoryTypeDevice && attr.device != c->device)
+			KG_FAIL(c, KG_ERR_INVALID, "tile is on device %d, context on %d", attr.device, c->device);
+		*dev = rows;
+		return KG_OK;
+	}
+	const int s = c->next_slot;
+	c->next_slot ^= 1;
+	if (c->tile_cap[s] < bytes) {
+		KG_CUDA(c, cudaEventSynchronize(c->slot_free[s]));
+		if (c->d_tile[s]) KG_CUDA(c, cudaFree(c->d_tile[s]));
+		c->d_tile[s] = nullptr;
+		c->tile_cap[s] = 0;
+		const size_t cap = std::max<size_t>(bytes, 1u << 20);
+		cudaError_t me = cudaMalloc((void **)&c->d_tile[s], cap);
+		if (me != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc(%zu) for tile: %s", cap, cudaGetErrorString(me));
+		c->tile_cap[s] = cap;
+	}
+	KG_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->slot_free[s], 0));
+	if (attr.type == cudaMemoryTypeHost) {
+		KG_CUDA(c, cudaMemcpyAsync(c->d_tile[s], rows, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+	} else {
+		// pageable memory: bounce through two pinned staging buffers
+		const char *src = reinterpret_cast<const char *>(rows);
+		size_t off = 0;
+		int k = 0;
+		while (off < bytes) {
+			if (!c->h_stage[k]) {
+				cudaError_t he = cudaMallocHost(&c->h_stage[k], kg_ctx::kStageBytes);
+				if (he != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMallocHost staging: %s", cudaGetErrorString(he));
+			}
+			const size_t n = std::min(kg_ctx::kStageBytes, bytes - off);
+			KG_CUDA(c, cudaEventSynchronize(c->stage_free[k]));
+			memcpy(c->h_stage[k], src + off, n);
+			KG_CUDA(c, cudaMemcpyAsync(reinterpret_cast<char *>(c->d_tile[s]) + off, c->h_stage[k], n,
+			                           cudaMemcpyHostToDevice, c->copy_stream));
+			KG_CUDA(c, cudaEventRecord(c->stage_free[k], c->copy_stream));
+			off += n;
+			k ^= 1;
+		}
+	}
+	KG_CUDA(c, cudaEventRecord(c->slot_ready[s], c->copy_stream));
+	KG_CUDA(c, cudaStreamWaitEvent(c->stream, c->slot_ready[s], 0));
+	c->cur_slot = s;
+	*dev = c->d_tile[s];
+	return KG_OK;
+}
+
+static kg_status release_tile(kg_ctx *c) {
+	if (c->cur_slot >= 0) KG_CUDA(c, cudaEventRecord(c->slot_free[c->cur_slot], c->stream));
+	c->cur_slot = -1;
+	return KG_OK;
+}
+
+// Memory-order view of a device tile: the raw tile itself when the column map is the identity,
+// else a squeezed copy (load_kmers :125-132) in the context's scratch buffer.
+static kg_status memory_view(kg_ctx *c, const uint64_t *dev, uint64_t n_rows, KgRowView *view) {
+	if (c->identity) {
+		*view = KgRowView{dev, n_rows, c->w_file + 1, c->w_file};
+		return KG_OK;
+	}
+	const size_t need = (size_t)n_rows * (c->w_mem + 1) * 8;
+	if (c->squeezed_cap < need) {
+		KG_CUDA(c, cudaStreamSynchronize(c->stream));
+		if (c->d_squeezed) KG_CUDA(c, cudaFree(c->d_squeezed));
+		c->d_squeezed = nullptr;
+		c->squeezed_cap = 0;
+		cudaError_t me = cudaMalloc((void **)&c->d_squeezed, need);
+		if (me != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc(%zu) squeeze scratch: %s", need, cudaGetErrorString(me));
+		c->squeezed_cap = need;
+	}
+	KgRowView raw{dev, n_rows, c->w_file + 1, c->w_file};
+	const uint64_t total = n_rows * (uint64_t)(c->w_mem + 1);
+	const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->sm_count * 16);
+	kg_squeeze_kernel<<<std::max(grid, 1u), 256, 0, c->stream>>>(raw, c->d_map_mem, (uint32_t)c->n_used, c->w_mem,
+	                                                             c->d_squeezed);
+	KG_LAUNCH_CHECK(c);
+	*view = KgRowView{c->d_squeezed, n_rows, c->w_mem + 1, c->w_mem};
+	return KG_OK;
+}
+
+// ------------------------------------------------------------------------------------- scan
+extern "C" kg_status kg_scan_set_phenotypes(kg_ctx *c, const float *y, uint32_t n_pheno, uint64_t min_count) {
+	if (!c || !y || n_pheno == 0) { if (c) c->err = "kg_scan_set_phenotypes: bad arguments"; return KG_ERR_INVALID; }
+	KG_CUDA(c, cudaSetDevice(c->device));
+	KG_CUDA(c, cudaStreamSynchronize(c->stream));
+	c->n_pheno = n_pheno;
+	c->min_count = min_count;
+	c->pt = n_pheno > 4 ? 8 : (n_pheno > 2 ? 4 : n_pheno);
+	// shared memory of the y tile must fit: shrink PT for very wide tables
+	while (c->pt > 1 && (size_t)c->nb * 4 * (32 * c->pt + 4) * 4 > 200u * 1024) c->pt /= 2;
+	if ((size_t)c->nb * 4 * (32 * c->pt + 4) * 4 > 200u * 1024)
+		KG_FAIL(c, KG_ERR_INVALID, "n_used = %llu too wide for the exact kernel", (unsigned long long)c->n_used);
+	c->p_alloc = (n_pheno + 7) / 8 * 8;
+	const size_t lane_len = (size_t)c->nb * 128;
+	std::vector<float> y_lane((size_t)c->p_alloc * lane_len, 0.0f);
+	c->h_sums.assign(c->p_alloc, 0.0f);
+	c->h_y.assign(y, y + (size_t)n_pheno * c->n_used);
+	for (uint32_t p = 0; p < n_pheno; p++) {
+		const float *yp = y + (size_t)p * c->n_used;
+		float *yl = y_lane.data() + (size_t)p * lane_len;
+		for (uint64_t i = 0; i < c->n_used; i++) {
+			const uint32_t blk = (uint32_t)(i / 128), L = (uint32_t)((i % 128) / 32), t = 31 - (uint32_t)(i % 32);
+			yl[(size_t)(blk * 4 + L) * 32 + t] = yp[i];
+		}
+		// update_scores_and_sum (:288-295): sequential fp32 sum over the PERMUTED padded vector,
+		// permuted index = 128 blk + 4 t + L  (kmer_general.cpp:155-167)
+		volatile float sum = 0.0f;
+		for (uint32_t blk = 0; blk < c->nb; blk++)
+			for (uint32_t t = 0; t < 32; t++)
+				for (uint32_t L = 0; L < 4; L++) sum = sum + yl[(size_t)(blk * 4 + L) * 32 + t];
+		c->h_sums[p] = sum;
+	}
+	cudaFree(c->d_y_lane); cudaFree(c->d_sums); cudaFree(c->d_thr);
+	c->d_y_lane = nullptr; c->d_sums = nullptr; c->d_thr = nullptr;
+	KG_CUDA(c, dev_alloc_copy(&c->d_y_lane, y_lane));
+	KG_CUDA(c, dev_alloc_copy(&c->d_sums, c->h_sums));
+	c->h_thr.assign(c->p_alloc, -1.0);
+	KG_CUDA(c, dev_alloc_copy(&c->d_thr, c->h_thr));
+	if (!c->d_hits) {
+		cudaError_t me = cudaMalloc((void **)&c->d_hits, c->hit_capacity * sizeof(kg_hit));
+		if (me != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc hit buffer: %s", cudaGetErrorString(me));
+	}
+	KG_CUDA(c, cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long)));
+	c->h_hits.clear();
+	c->rows_seen = c->rows_seen_committed = c->kept_committed = 0;
+	c->pending = false;
+	kg_status st = kg_tc_prepare_scan(c);
+	return st;
+}
+
+extern "C" kg_status kg_scan_set_thresholds(kg_ctx *c, const double *thr, uint32_t n_pheno) {
+	if (!c || !thr) return KG_ERR_INVALID;
+	if (n_pheno != c->n_pheno || !c->d_thr) KG_FAIL(c, KG_ERR_STATE, "kg_scan_set_thresholds: phenotypes not set / count mismatch");
+	KG_CUDA(c, cudaSetDevice(c->device));
+	for (uint32_t p = 0; p < n_pheno; p++) c->h_thr[p] = thr[p];
+	// stream-ordered so tiles already queued keep the thresholds they were submitted with
+	KG_CUDA(c, cudaMemcpyAsync(c->d_thr, c->h_thr.data(), (size_t)c->p_alloc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	KG_CUDA(c, cudaStreamSynchronize(c->stream));
+	return kg_tc_update_thresholds(c);
+}
+
+template <int R, int PT, int MODE>
+static kg_status launch_exact(kg_ctx *c, const KgScanParams &prm) {
+	constexpr int GS = kg_ys_group_stride<PT>();
+	const size_t smem = (size_t)c->nb * 4 * GS * sizeof(float);
+	auto kern = kg_scan_exact_kernel<R, PT, MODE>;
+	KG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int occ = 1;
+	KG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+	if (occ < 1) occ = 1;
+	const uint32_t p_tiles = (c->n_pheno + PT - 1) / PT;
+	const uint64_t n_chunks = (prm.view.n_rows + (64 * R) - 1) / (64 * R);
+	uint64_t gx = ((uint64_t)c->sm_count * occ + p_tiles - 1) / p_tiles;
+	gx = std::max<uint64_t>(1, std::min(gx, n_chunks));
+	dim3 grid((unsigned)gx, p_tiles);
+	kern<<<grid, 256, smem, c->stream>>>(prm);
+	KG_LAUNCH_CHECK(c);
+	return KG_OK;
+}
+
+template <int MODE>
+static kg_status launch_exact_pt(kg_ctx *c, const KgScanParams &prm) {
+	switch (c->pt) {
+	case 8: return launch_exact<8, 8, MODE>(c, prm);
+	case 4: return launch_exact<8, 4, MODE>(c, prm);
+	case 2: return launch_exact<8, 2, MODE>(c, prm);
+	default: return launch_exact<8, 1, MODE>(c, prm);
+	}
+}
+
+static KgScanParams scan_params(kg_ctx *c, const KgRowView &view, uint64_t first_row_id) {
+	KgScanParams prm;
+	memset(&prm, 0, sizeof prm);
+	prm.view = view;
+	prm.nb = c->nb;
+	prm.n_used = (uint32_t)c->n_used;
+	prm.n_pheno = c->n_pheno;
+	prm.min_count = (uint32_t)std::min<uint64_t>(c->min_count, 0xFFFFFFFFull);
+	prm.y_lane = c->d_y_lane;
+	prm.sums = c->d_sums;
+	prm.mask32 = c->d_mask32;
+	prm.thr = c->d_thr;
+	prm.hits = c->d_hits;
+	prm.hit_count = c->d_counters + 0;
+	prm.hit_capacity = c->hit_capacity;
+	prm.kept_count = c->d_counters + 1;
+	prm.first_row_id = first_row_id;
+	return prm;
+}
+
+extern "C" kg_status kg_scan_submit(kg_ctx *c, const uint64_t *rows, uint64_t n_rows, uint64_t first_row_id) {
+	if (!c) return KG_ERR_INVALID;
+	if (!c->d_y_lane) KG_FAIL(c, KG_ERR_STATE, "kg_scan_submit: call kg_scan_set_phenotypes first");
+	if (n_rows == 0) return KG_OK;
+	if (!rows) KG_FAIL(c, KG_ERR_INVALID, "kg_scan_submit: null rows");
+	if (n_rows >= (1ull << 31)) KG_FAIL(c, KG_ERR_INVALID, "kg_scan_submit: tile of %llu rows too large (max 2^31-1)", (unsigned long long)n_rows);
+	KG_CUDA(c, cudaSetDevice(c->device));
+	const uint64_t *dev = nullptr;
+	kg_status st = acquire_tile(c, rows, n_rows, &dev);
+	if (st != KG_OK) return st;
+	bool use_tc = false;
+	if (c->scan_engine == 2) use_tc = true;
+	else if (c->scan_engine == 0) use_tc = kg_tc_scan_profitable(c);
+	if (use_tc && !kg_tc_scan_available(c))
+		KG_FAIL(c, KG_ERR_INVALID, "tensor filter engine unavailable for this shape: %s", c->tc.why_unavailable.c_str());
+	if (use_tc) {
+		st = kg_tc_scan_tile(c, dev, n_rows, first_row_id);
+		if (st != KG_OK) return st;
+	} else {
+		KgRowView view;
+		st = memory_view(c, dev, n_rows, &view);
+		if (st != KG_OK) return st;
+		KgScanParams prm = scan_params(c, view, first_row_id);
+		st = launch_exact_pt<0>(c, prm);
+		if (st != KG_OK) return st;
+	}
+	c->rows_seen += n_rows;
+	c->pending = true;
+	return release_tile(c);
+}
+
+extern "C" kg_status kg_scan_fetch(kg_ctx *c, kg_hit *out, size_t cap, size_t *n_hits, uint64_t *rows_seen,
+                                   uint64_t *rows_kept) {
+	if (!c) return KG_ERR_INVALID;
+	if (!c->d_y_lane) KG_FAIL(c, KG_ERR_STATE, "kg_scan_fetch: call kg_scan_set_phenotypes first");
+	KG_CUDA(c, cudaSetDevice(c->device));
+	KG_CUDA(c, cudaStreamSynchronize(c->stream));
+	unsigned long long cnt[4];
+	KG_CUDA(c, cudaMemcpy(cnt, c->d_counters, sizeof cnt, cudaMemcpyDeviceToHost));
+	if (cnt[0] > c->hit_capacity || cnt[2] > c->tc.pair_capacity) {
+		// roll back to the last committed state; the caller resubmits in smaller pieces
+		unsigned long long reset[4] = {0, c->kept_committed, 0, 0};
+		KG_CUDA(c, cudaMemcpy(c->d_counters, reset, sizeof reset, cudaMemcpyHostToDevice));
+		c->rows_seen = c->rows_seen_committed;
+		c->pending = false;
+		KG_FAIL(c, KG_ERR_HITS_OVERFLOW, "%llu hits / %llu candidate pairs exceed the buffers (%llu / %llu): resubmit smaller tiles",
+		        cnt[0], cnt[2], (unsigned long long)c->hit_capacity, (unsigned long long)c->tc.pair_capacity);
+	}
+	if (cnt[0] > 0) {
+		const size_t old = c->h_hits.size();
+		c->h_hits.resize(old + cnt[0]);
+		KG_CUDA(c, cudaMemcpy(c->h_hits.data() + old, c->d_hits, cnt[0] * sizeof(kg_hit), cudaMemcpyDeviceToHost));
+		KG_CUDA(c, cudaMemset(c->d_counters, 0, sizeof(unsigned long long)));
+		c->hits_sorted = false;
+	}
+	KG_CUDA(c, cudaMemset(c->d_counters + 2, 0, sizeof(unsigned long long)));
+	c->kept_committed = cnt[1];
+	c->rows_seen_committed = c->rows_seen;
+	c->pending = false;
+	if (!c->hits_sorted) {
+		std::sort(c->h_hits.begin(), c->h_hits.end(), [](const kg_hit &a, const kg_hit &b) {
+			return a.pheno != b.pheno ? a.pheno < b.pheno : a.row < b.row;
+		});
+		c->hits_sorted = true;
+	}
+	if (n_hits) *n_hits = c->h_hits.size();
+	if (out && cap) memcpy(out, c->h_hits.data(), std::min(cap, c->h_hits.size()) * sizeof(kg_hit));
+	if (rows_seen) *rows_seen = c->rows_seen;
+	if (rows_kept) *rows_kept = c->kept_committed;
+	return KG_OK;
+}
+
+extern "C" kg_status kg_scan_clear_hits(kg_ctx *c) {
+	if (!c) return KG_ERR_INVALID;
+	c->h_hits.clear();
+	c->hits_sorted = true;
+	return KG_OK;
+}
+
+extern "C" kg_status kg_scan_scores_dense(kg_ctx *c, const uint64_t *rows, uint64_t n_rows, uint8_t *keep,
+                                          double *scores) {
+	if (!c) return KG_ERR_INVALID;
+	if (!c->d_y_lane) KG_FAIL(c, KG_ERR_STATE, "kg_scan_scores_dense: call kg_scan_set_phenotypes first");
+	if (n_rows == 0) return KG_OK;
+	if (!rows || !keep || !scores) KG_FAIL(c, KG_ERR_INVALID, "kg_scan_scores_dense: null argument");
+	KG_CUDA(c, cudaSetDevice(c->device));
+	const uint64_t *dev = nullptr;
+	kg_status st = acquire_tile(c, rows, n_rows, &dev);
+	if (st != KG_OK) return st;
+	KgRowView view;
+	st = memory_view(c, dev, n_rows, &view);
+	if (st != KG_OK) return st;
+	uint8_t *d_keep = nullptr;
+	double *d_scores = nullptr;
+	KG_CUDA(c, cudaMalloc((void **)&d_keep, n_rows));
+	cudaError_t me = cudaMalloc((void **)&d_scores, (size_t)c->n_pheno * n_rows * sizeof(double));
+	if (me != cudaSuccess) { cudaFree(d_keep); KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc dense scores: %s", cudaGetErrorString(me)); }
+	cudaMemsetAsync(d_scores, 0, (size_t)c->n_pheno * n_rows * sizeof(double), c->stream);
+	KgScanParams prm = scan_params(c, view, 0);
+	prm.keep_out = d_keep;
+	prm.scores_out = d_scores;
+	st = launch_exact_pt<1>(c, prm);
+	if (st == KG_OK) st = release_tile(c);
+	cudaError_t e1 = cudaStreamSynchronize(c->stream);
+	cudaError_t e2 = cudaMemcpy(keep, d_keep, n_rows, cudaMemcpyDeviceToHost);
+	cudaError_t e3 = cudaMemcpy(scores, d_scores, (size_t)c->n_pheno * n_rows * sizeof(double), cudaMemcpyDeviceToHost);
+	cudaFree(d_keep);
+	cudaFree(d_scores);
+	if (st != KG_OK) return st;
+	KG_CUDA(c, e1); KG_CUDA(c, e2); KG_CUDA(c, e3);
+	return KG_OK;
+}
+
+// ------------------------------------------------------------------------------------- kinship
+extern "C" size_t kg_kinship_accum_len(const kg_ctx *c) { return c ? (size_t)c->n_used * c->n_used + 1 : 0; }
+
+extern "C" kg_status kg_kinship_begin(kg_ctx *c, uint64_t min_count, uint64_t *accum_dev) {
+	if (!c) return KG_ERR_INVALID;
+	KG_CUDA(c, cudaSetDevice(c->device));
+	KG_CUDA(c, cudaStreamSynchronize(c->stream));
+	const size_t len = kg_kinship_accum_len(c);
+	if (c->own_accum) { cudaFree(c->d_accum); c->own_accum = false; }
+	c->d_accum = nullptr;
+	if (accum_dev) {
+		c->d_accum = reinterpret_cast<unsigned long long *>(accum_dev);
+	} else {
+		cudaError_t me = cudaMalloc((void **)&c->d_accum, len * 8);
+		if (me != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc kinship accumulator: %s", cudaGetErrorString(me));
+		c->own_accum = true;
+	}
+	KG_CUDA(c, cudaMemsetAsync(c->d_accum, 0, len * 8, c->stream));
+	c->kin_min_count = min_count;
+	c->kin_active = true;
+	return kg_tc_prepare_kinship(c);
+}
+
+extern "C" kg_status kg_kinship_submit(kg_ctx *c, const uint64_t *rows, uint64_t n_rows) {
+	if (!c) return KG_ERR_INVALID;
+	if (!c->kin_active) KG_FAIL(c, KG_ERR_STATE, "kg_kinship_submit: call kg_kinship_begin first");
+	if (n_rows == 0) return KG_OK;
+	if (!rows) KG_FAIL(c, KG_ERR_INVALID, "kg_kinship_submit: null rows");
+	if (n_rows >= (1ull << 31)) KG_FAIL(c, KG_ERR_INVALID, "kg_kinship_submit: tile too large (max 2^31-1 rows)");
+	KG_CUDA(c, cudaSetDevice(c->device));
+	const uint64_t *dev = nullptr;
+	kg_status st = acquire_tile(c, rows, n_rows, &dev);
+	if (st != KG_OK) return st;
+	KgRowView view;
+	st = memory_view(c, dev, n_rows, &view);
+	if (st != KG_OK) return st;
+	// MAC filter bits + kept count
+	const size_t kb_need = (size_t)((n_rows + 31) / 32);
+	if (c->keep_bits_cap < kb_need) {
+		KG_CUDA(c, cudaStreamSynchronize(c->stream));
+		cudaFree(c->d_keep_bits);
+		c->d_keep_bits = nullptr;
+		cudaError_t me = cudaMalloc((void **)&c->d_keep_bits, kb_need * 4);
+		if (me != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc keep bits: %s", cudaGetErrorString(me));
+		c->keep_bits_cap = kb_need;
+	}
+	const uint64_t *mask = c->identity ? c->d_file_mask : c->d_mem_mask;
+	const unsigned long long n2 = (unsigned long long)c->n_used * c->n_used;
+	{
+		const unsigned grid = (unsigned)std::min<uint64_t>((n_rows + 255) / 256, (uint64_t)c->sm_count * 8);
+		kg_prefilter_kernel<<<std::max(grid, 1u), 256, 0, c->stream>>>(view, mask, (uint32_t)c->n_used,
+		                                                               (uint32_t)std::min<uint64_t>(c->kin_min_count, 0xFFFFFFFFull),
+		                                                               c->d_keep_bits, c->d_accum + n2);
+		KG_LAUNCH_CHECK(c);
+	}
+	bool use_tc = false;
+	if (c->kin_engine == 2) use_tc = true;
+	else if (c->kin_engine == 0) use_tc = kg_tc_kinship_available(c);
+	if (use_tc && !kg_tc_kinship_available(c))
+		KG_FAIL(c, KG_ERR_INVALID, "tensor kinship engine unavailable: %s", c->tc.why_unavailable.c_str());
+	if (use_tc) {
+		st = kg_tc_kinship_tile(c, view);
+		if (st != KG_OK) return st;
+	} else {
+		const uint32_t t64 = (uint32_t)((c->n_used + 63) / 64);
+		const uint32_t pair_tiles = t64 * (t64 + 1) / 2;
+		const uint64_t n_chunks = (n_rows + KG_KIN_CHUNK_ROWS - 1) / KG_KIN_CHUNK_ROWS;
+		uint64_t splits = ((uint64_t)c->sm_count * 4 + pair_tiles - 1) / pair_tiles;
+		splits = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(splits, n_chunks), 65535));
+		dim3 grid(pair_tiles, (unsigned)splits);
+		kg_kinship_popc_kernel<<<grid, 256, 0, c->stream>>>(view, c->d_keep_bits, (uint32_t)c->n_used, t64, c->d_accum);
+		KG_LAUNCH_CHECK(c);
+	}
+	return release_tile(c);
+}
+
+extern "C" kg_status kg_kinship_fetch(kg_ctx *c, uint64_t *ibs, uint64_t *kept_rows) {
+	if (!c) return KG_ERR_INVALID;
+	if (!c->kin_active) KG_FAIL(c, KG_ERR_STATE, "kg_kinship_fetch: call kg_kinship_begin first");
+	KG_CUDA(c, cudaSetDevice(c->device));
+	KG_CUDA(c, cudaStreamSynchronize(c->stream));
+	const unsigned long long n2 = (unsigned long long)c->n_used * c->n_used;
+	unsigned long long M = 0;
+	KG_CUDA(c, cudaMemcpy(&M, c->d_accum + n2, 8, cudaMemcpyDeviceToHost));
+	if (kept_rows) *kept_rows = M;
+	if (ibs) {
+		if (!c->d_ibs) {
+			cudaError_t me = cudaMalloc((void **)&c->d_ibs, n2 * 8);
+			if (me != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc ibs: %s", cudaGetErrorString(me));
+		}
+		const unsigned grid = (unsigned)std::min<uint64_t>((n2 + 255) / 256, (uint64_t)c->sm_count * 8);
+		kg_kinship_finalize_kernel<<<std::max(grid, 1u), 256, 0, c->stream>>>(c->d_accum, (uint32_t)c->n_used, M, c->d_ibs);
+		KG_LAUNCH_CHECK(c);
+		KG_CUDA(c, cudaStreamSynchronize(c->stream));
+		KG_CUDA(c, cudaMemcpy(ibs, c->d_ibs, n2 * 8, cudaMemcpyDeviceToHost));
+	}
+	return KG_OK;
+}
+
+// ------------------------------------------------------------------------------------- synthetic
+extern "C" kg_status kg_synth_rows_device(kg_ctx *c, uint64_t seed, uint64_t first_row, uint64_t n_rows,
+                                          uint64_t *rows_dev) {
+	if (!c) return KG_ERR_INVALID;
+	if (n_rows == 0) return KG_OK;
+	if (!rows_dev) KG_FAIL(c, KG_ERR_INVALID, "kg_synth_rows_device: null output");
+	KG_CUDA(c, cudaSetDevice(c->device));
+	const uint64_t last_mask = (c->n_file % 64) ? ((1ull << (c->n_file % 64)) - 1ull) : ~0ull;
+	const uint64_t total = n_rows * (uint64_t)(c->w_file + 1);
+	const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->sm_count * 32);
+	kg_synth_rows_kernel<<<std::max(grid, 1u), 256, 0, c->stream>>>(seed, first_row, n_rows, c->w_file, last_mask, rows_dev);
+	KG_LAUNCH_CHECK(c);
+	return KG_OK;
+}
