@@ -67,7 +67,19 @@ typedef struct kg_hit {
 enum {
 	KG_OPT_SCAN_ENGINE = 1, /* 0 = auto, 1 = exact fp32-order kernel on every row, 2 = int8 tensor filter + exact refine */
 	KG_OPT_HIT_CAPACITY = 2, /* number of kg_hit the device hit buffer holds (default 1<<22); set before first submit */
-	KG_OPT_KINSHIP_ENGINE = 3 /* 0 = auto, 1 = popcount kernel, 2 = int8 tensor-core Gram */
+	KG_OPT_KINSHIP_ENGINE = 3, /* 0 = auto, 1 = popcount kernel, 2 = int8 tensor-core Gram */
+	KG_OPT_KERNEL_TIMING = 4   /* 1 = bracket every hot-path kernel launch with CUDA events on the context's stream
+	                              (read back with kg_kernel_time); 0 = off (default) */
+};
+
+/* Kernel classes reported by kg_kernel_time */
+enum {
+	KG_KERNEL_SCAN_EXACT = 0,  /* exact fp32-order score kernel over every (row, phenotype) */
+	KG_KERNEL_SCAN_FILTER = 1, /* int8 tensor-core bound kernel (candidate pairs) */
+	KG_KERNEL_SCAN_REFINE = 2, /* exact re-score of candidate pairs */
+	KG_KERNEL_KINSHIP = 3,     /* Gram accumulation (popcount or tensor-core engine) */
+	KG_KERNEL_AUX = 4,         /* squeeze / MAC prefilter / finalize / synthetic generator */
+	KG_KERNEL_CLASSES = 5
 };
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
@@ -146,6 +158,12 @@ kg_status kg_synth_rows_device(kg_ctx *ctx, uint64_t seed, uint64_t first_row, u
 
 /* Number of kernels this library launched since the context was created (bench "gpu_launches"). */
 uint64_t kg_launch_count(const kg_ctx *ctx);
+
+/* With KG_OPT_KERNEL_TIMING = 1: device time (CUDA events recorded on the context's stream around each
+ * launch), launch count and table rows processed, summed per kernel class since the last
+ * kg_kernel_time_reset.  Waits for the stream.  Any output pointer may be NULL. */
+kg_status kg_kernel_time(kg_ctx *ctx, int kernel_class, double *ms_total, uint64_t *launches, uint64_t *rows);
+kg_status kg_kernel_time_reset(kg_ctx *ctx);
 
 #ifdef __cplusplus
 }

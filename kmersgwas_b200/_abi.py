@@ -15,7 +15,9 @@ from . import build as _build
 
 KG_OK = 0
 KG_ERR_HITS_OVERFLOW = 4
-OPT_SCAN_ENGINE, OPT_HIT_CAPACITY, OPT_KINSHIP_ENGINE = 1, 2, 3
+OPT_SCAN_ENGINE, OPT_HIT_CAPACITY, OPT_KINSHIP_ENGINE, OPT_KERNEL_TIMING = 1, 2, 3, 4
+KERNEL_SCAN_EXACT, KERNEL_SCAN_FILTER, KERNEL_SCAN_REFINE, KERNEL_KINSHIP, KERNEL_AUX = 0, 1, 2, 3, 4
+KERNEL_CLASS_NAMES = ["scan_exact", "scan_filter", "scan_refine", "kinship", "aux"]
 
 HIT_DTYPE = np.dtype([("row", "<u8"), ("kmer", "<u8"), ("score", "<f8"), ("pheno", "<u4"), ("pad", "<u4")])
 
@@ -25,7 +27,7 @@ ABI_SYMBOLS = [
     "kg_scan_set_phenotypes", "kg_scan_set_thresholds", "kg_scan_submit", "kg_scan_fetch",
     "kg_scan_clear_hits", "kg_scan_scores_dense", "kg_kinship_begin", "kg_kinship_accum_len",
     "kg_kinship_submit", "kg_kinship_fetch", "kg_host_alloc", "kg_host_free", "kg_synth_rows_device",
-    "kg_launch_count",
+    "kg_launch_count", "kg_kernel_time", "kg_kernel_time_reset",
 ]
 
 
@@ -82,8 +84,22 @@ def load():
     lib.kg_synth_rows_device.argtypes = [vp, u64, u64, u64, vp]
     lib.kg_launch_count.argtypes = [vp]
     lib.kg_launch_count.restype = u64
+    lib.kg_kernel_time.argtypes = [vp, C.c_int, C.POINTER(C.c_double), u64p, u64p]
+    lib.kg_kernel_time_reset.argtypes = [vp]
     _lib = lib
     return lib
+
+
+def kernel_times(handle) -> dict:
+    """{class name: (ms_total, launches, rows)} of a kg_ctx handle (needs OPT_KERNEL_TIMING = 1)."""
+    lib = load()
+    out = {}
+    for i, name in enumerate(KERNEL_CLASS_NAMES):
+        ms, n, r = C.c_double(0), C.c_uint64(0), C.c_uint64(0)
+        if lib.kg_kernel_time(handle, i, C.byref(ms), C.byref(n), C.byref(r)) != KG_OK:
+            raise KgError(-1, lib.kg_last_error(handle).decode())
+        out[name] = (ms.value, int(n.value), int(r.value))
+    return out
 
 
 def _rows_ptr(rows):
@@ -142,6 +158,12 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self._lib.kg_launch_count(self._h))
+
+    def kernel_times(self) -> dict:
+        return kernel_times(self._h)
+
+    def kernel_times_reset(self):
+        self._chk(self._lib.kg_kernel_time_reset(self._h))
 
     # ---- scan
     def set_phenotypes(self, y: np.ndarray, min_count: int):

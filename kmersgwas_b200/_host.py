@@ -39,6 +39,8 @@ def load():
     lib.kgh_session_heap_dump.restype = None
     lib.kgh_session_stats.argtypes = [vp, vp, vp, vp, vp]
     lib.kgh_session_stats.restype = None
+    lib.kgh_session_io_bytes.argtypes = [vp, vp, vp]
+    lib.kgh_session_io_bytes.restype = None
     lib.kgh_session_log_size.argtypes = [vp]
     lib.kgh_session_log_size.restype = u64
     lib.kgh_session_log_copy.argtypes = [vp, vp]
@@ -125,6 +127,25 @@ class Session:
         a, b, c, d = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._lib.kgh_session_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
         return dict(rounds=a.value, hits_replayed=b.value, rows_scored=c.value, rows_kept=d.value)
+
+    def io_bytes(self):
+        """(small host->device bytes: thresholds, device->host bytes: hits + counters) so far."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._lib.kgh_session_io_bytes(self._h, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
+    def set_option(self, opt: int, value: int):
+        from ._abi import load as load_abi
+        if load_abi().kg_set_option(self.ctx_handle, opt, value) != 0:
+            raise RuntimeError("kg_set_option: " + load_abi().kg_last_error(self.ctx_handle).decode())
+
+    def kernel_times(self) -> dict:
+        from ._abi import kernel_times
+        return kernel_times(self.ctx_handle)
+
+    def kernel_times_reset(self):
+        from ._abi import load as load_abi
+        load_abi().kg_kernel_time_reset(self.ctx_handle)
 
     def hit_log(self):
         n = int(self._lib.kgh_session_log_size(self._h))

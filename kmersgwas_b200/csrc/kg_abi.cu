@@ -79,6 +79,14 @@ struct kg_ctx {
 	KgTcState tc;
 
 	int scan_engine = 0, kin_engine = 0;
+
+	// per-launch device timing (KG_OPT_KERNEL_TIMING)
+	bool timing = false;
+	struct TimedLaunch { cudaEvent_t beg, end; int cls; uint64_t rows; };
+	std::vector<TimedLaunch> timed_pending;
+	std::vector<cudaEvent_t> event_pool;
+	double timed_ms[KG_KERNEL_CLASSES] = {0};
+	uint64_t timed_launches[KG_KERNEL_CLASSES] = {0}, timed_rows[KG_KERNEL_CLASSES] = {0};
 };
 
 static std::string g_create_error;
@@ -108,6 +116,44 @@ static std::string g_create_error;
 		(ctx)->launches++;              \
 		KG_CUDA(ctx, cudaGetLastError()); \
 	} while (0)
+
+// ---- per-launch timing: events on the launching stream, resolved after the stream is synchronised
+static cudaEvent_t timing_event(kg_ctx *c) {
+	if (!c->event_pool.empty()) {
+		cudaEvent_t e = c->event_pool.back();
+		c->event_pool.pop_back();
+		return e;
+	}
+	cudaEvent_t e = nullptr;
+	cudaEventCreate(&e);
+	return e;
+}
+static void timing_begin(kg_ctx *c, int cls, uint64_t rows) {
+	if (!c->timing) return;
+	kg_ctx::TimedLaunch t{timing_event(c), timing_event(c), cls, rows};
+	cudaEventRecord(t.beg, c->stream);
+	c->timed_pending.push_back(t);
+}
+static void timing_end(kg_ctx *c) {
+	if (!c->timing || c->timed_pending.empty()) return;
+	cudaEventRecord(c->timed_pending.back().end, c->stream);
+}
+// call only after cudaStreamSynchronize(c->stream)
+static void timing_resolve(kg_ctx *c) {
+	for (const kg_ctx::TimedLaunch &t : c->timed_pending) {
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, t.beg, t.end) == cudaSuccess) {
+			c->timed_ms[t.cls] += ms;
+			c->timed_launches[t.cls]++;
+			c->timed_rows[t.cls] += t.rows;
+		} else {
+			cudaGetLastError();
+		}
+		c->event_pool.push_back(t.beg);
+		c->event_pool.push_back(t.end);
+	}
+	c->timed_pending.clear();
+}
 
 // tensor-core engine (needs kg_ctx and the macros above)
 #include "kg_tc.cuh"
@@ -226,6 +272,8 @@ extern "C" void kg_ctx_destroy(kg_ctx *c) {
 		if (c->slot_ready[i]) cudaEventDestroy(c->slot_ready[i]);
 		if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
 	}
+	for (const kg_ctx::TimedLaunch &t : c->timed_pending) { cudaEventDestroy(t.beg); cudaEventDestroy(t.end); }
+	for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -247,6 +295,9 @@ extern "C" kg_status kg_set_option(kg_ctx *c, int option, int64_t value) {
 		if (value < 0 || value > 2) KG_FAIL(c, KG_ERR_INVALID, "kinship engine must be 0, 1 or 2");
 		c->kin_engine = (int)value;
 		return KG_OK;
+	case KG_OPT_KERNEL_TIMING:
+		c->timing = value != 0;
+		return KG_OK;
 	default:
 		KG_FAIL(c, KG_ERR_INVALID, "unknown option %d", option);
 	}
@@ -257,6 +308,28 @@ extern "C" kg_status kg_sync(kg_ctx *c) {
 	KG_CUDA(c, cudaSetDevice(c->device));
 	KG_CUDA(c, cudaStreamSynchronize(c->copy_stream));
 	KG_CUDA(c, cudaStreamSynchronize(c->stream));
+	timing_resolve(c);
+	return KG_OK;
+}
+
+extern "C" kg_status kg_kernel_time(kg_ctx *c, int cls, double *ms_total, uint64_t *launches, uint64_t *rows) {
+	if (!c) return KG_ERR_INVALID;
+	if (cls < 0 || cls >= KG_KERNEL_CLASSES) KG_FAIL(c, KG_ERR_INVALID, "kg_kernel_time: bad kernel class %d", cls);
+	KG_CUDA(c, cudaSetDevice(c->device));
+	KG_CUDA(c, cudaStreamSynchronize(c->stream));
+	timing_resolve(c);
+	if (ms_total) *ms_total = c->timed_ms[cls];
+	if (launches) *launches = c->timed_launches[cls];
+	if (rows) *rows = c->timed_rows[cls];
+	return KG_OK;
+}
+
+extern "C" kg_status kg_kernel_time_reset(kg_ctx *c) {
+	if (!c) return KG_ERR_INVALID;
+	KG_CUDA(c, cudaSetDevice(c->device));
+	KG_CUDA(c, cudaStreamSynchronize(c->stream));
+	timing_resolve(c);
+	for (int i = 0; i < KG_KERNEL_CLASSES; i++) { c->timed_ms[i] = 0; c->timed_launches[i] = 0; c->timed_rows[i] = 0; }
 	return KG_OK;
 }
 
@@ -357,8 +430,10 @@ static kg_status memory_view(kg_ctx *c, const uint64_t *dev, uint64_t n_rows, Kg
 	KgRowView raw{dev, n_rows, c->w_file + 1, c->w_file};
 	const uint64_t total = n_rows * (uint64_t)(c->w_mem + 1);
 	const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->sm_count * 16);
+	timing_begin(c, KG_KERNEL_AUX, n_rows);
 	kg_squeeze_kernel<<<std::max(grid, 1u), 256, 0, c->stream>>>(raw, c->d_map_mem, (uint32_t)c->n_used, c->w_mem,
 	                                                             c->d_squeezed);
+	timing_end(c);
 	KG_LAUNCH_CHECK(c);
 	*view = KgRowView{c->d_squeezed, n_rows, c->w_mem + 1, c->w_mem};
 	return KG_OK;
@@ -436,10 +511,13 @@ static kg_status launch_exact(kg_ctx *c, const KgScanParams &prm) {
 	if (occ < 1) occ = 1;
 	const uint32_t p_tiles = (c->n_pheno + PT - 1) / PT;
 	const uint64_t n_chunks = (prm.view.n_rows + (64 * R) - 1) / (64 * R);
-	uint64_t gx = ((uint64_t)c->sm_count * occ + p_tiles - 1) / p_tiles;
+	// one resident wave: never more CTAs than (SMs x CTAs per SM), or the few extra CTAs double the time
+	uint64_t gx = ((uint64_t)c->sm_count * occ) / p_tiles;
 	gx = std::max<uint64_t>(1, std::min(gx, n_chunks));
 	dim3 grid((unsigned)gx, p_tiles);
+	timing_begin(c, KG_KERNEL_SCAN_EXACT, prm.view.n_rows);
 	kern<<<grid, 256, smem, c->stream>>>(prm);
+	timing_end(c);
 	KG_LAUNCH_CHECK(c);
 	return KG_OK;
 }
@@ -511,6 +589,7 @@ extern "C" kg_status kg_scan_fetch(kg_ctx *c, kg_hit *out, size_t cap, size_t *n
 	if (!c->d_y_lane) KG_FAIL(c, KG_ERR_STATE, "kg_scan_fetch: call kg_scan_set_phenotypes first");
 	KG_CUDA(c, cudaSetDevice(c->device));
 	KG_CUDA(c, cudaStreamSynchronize(c->stream));
+	timing_resolve(c);
 	unsigned long long cnt[4];
 	KG_CUDA(c, cudaMemcpy(cnt, c->d_counters, sizeof cnt, cudaMemcpyDeviceToHost));
 	if (cnt[0] > c->hit_capacity || cnt[2] > c->tc.pair_capacity) {
@@ -637,9 +716,11 @@ extern "C" kg_status kg_kinship_submit(kg_ctx *c, const uint64_t *rows, uint64_t
 	const unsigned long long n2 = (unsigned long long)c->n_used * c->n_used;
 	{
 		const unsigned grid = (unsigned)std::min<uint64_t>((n_rows + 255) / 256, (uint64_t)c->sm_count * 8);
+		timing_begin(c, KG_KERNEL_AUX, n_rows);
 		kg_prefilter_kernel<<<std::max(grid, 1u), 256, 0, c->stream>>>(view, mask, (uint32_t)c->n_used,
 		                                                               (uint32_t)std::min<uint64_t>(c->kin_min_count, 0xFFFFFFFFull),
 		                                                               c->d_keep_bits, c->d_accum + n2);
+		timing_end(c);
 		KG_LAUNCH_CHECK(c);
 	}
 	bool use_tc = false;
@@ -657,7 +738,9 @@ extern "C" kg_status kg_kinship_submit(kg_ctx *c, const uint64_t *rows, uint64_t
 		uint64_t splits = ((uint64_t)c->sm_count * 4 + pair_tiles - 1) / pair_tiles;
 		splits = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(splits, n_chunks), 65535));
 		dim3 grid(pair_tiles, (unsigned)splits);
+		timing_begin(c, KG_KERNEL_KINSHIP, n_rows);
 		kg_kinship_popc_kernel<<<grid, 256, 0, c->stream>>>(view, c->d_keep_bits, (uint32_t)c->n_used, t64, c->d_accum);
+		timing_end(c);
 		KG_LAUNCH_CHECK(c);
 	}
 	return release_tile(c);

@@ -85,6 +85,8 @@ void kgh_associate_rows(kg_ctx *ctx, BestAssociationsHeap *const *heaps, std::si
 		}
 		if (S.log_hits) S.hit_log.insert(S.hit_log.end(), S.hit_buf.begin(), S.hit_buf.end());
 		S.rows_kept += kept_round;
+		S.d2h_bytes += (uint64_t)n_hits * sizeof(kg_hit) + 4 * sizeof(uint64_t);
+		S.h2d_small_bytes += (uint64_t)P * sizeof(double);
 		done += round;
 		S.rows_scored += round;
 		S.rounds++;

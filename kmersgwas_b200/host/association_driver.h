@@ -20,6 +20,8 @@ struct AssociationDriverState {
 	bool log_hits = false;
 	std::vector<kg_hit> hit_log;
 	uint64_t rows_kept = 0;          // rows that passed the MAC filter (all rounds)
+	uint64_t d2h_bytes = 0;          // hits + counters copied back from the device
+	uint64_t h2d_small_bytes = 0;    // thresholds sent to the device (the tiles themselves are counted by the caller)
 };
 
 // Score rows [0, n_rows) (raw .table rows, host or device memory) against the phenotypes already set

@@ -84,6 +84,11 @@ void kgh_session_stats(kgh_session *s, uint64_t *rounds, uint64_t *hits_replayed
 	if (rows_kept) *rows_kept = s->state.rows_kept;
 }
 
+void kgh_session_io_bytes(kgh_session *s, uint64_t *h2d_small, uint64_t *d2h) {
+	if (h2d_small) *h2d_small = s->state.h2d_small_bytes;
+	if (d2h) *d2h = s->state.d2h_bytes;
+}
+
 // Multi-shard merge: replay the shards' hit logs, in global row order, into shard 0's heaps
 // (which are reset first).  Used by the world_size > 1 tests and the multi-GPU bench.
 uint64_t kgh_session_log_size(kgh_session *s) { return s->state.hit_log.size(); }
