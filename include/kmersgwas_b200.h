@@ -126,6 +126,12 @@ kg_status kg_scan_clear_hits(kg_ctx *ctx);
 kg_status kg_scan_scores_dense(kg_ctx *ctx, const uint64_t *rows, uint64_t n_rows,
                                uint8_t *keep, double *scores);
 
+/* Testing aid for scan engine 2 (int8 tensor-core filter): the filter's exact integer sums
+ * q[r * n_pheno + p] = sum over the set presence bits of row r of the int8-quantised, centred phenotype p,
+ * and (optional, may be NULL) the quantised values yq[p * 64 * W_file + file_column].  Host outputs.
+ * Fails with KG_ERR_INVALID when the engine is unavailable for the context's shape. */
+kg_status kg_scan_filter_sums(kg_ctx *ctx, const uint64_t *rows, uint64_t n_rows, int32_t *q, int8_t *yq);
+
 /* ---- kinship ----------------------------------------------------------------------------------
  * Replaces MultipleKmersDataBases::update_emma_kinshhip_calculation
  * (/root/reference/src/kmers_multiple_databases.cpp:418-438) over the rows load_kmers keeps. */

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "kg_scan_set_phenotypes", "kg_scan_set_thresholds", "kg_scan_submit", "kg_scan_fetch",
     "kg_scan_clear_hits", "kg_scan_scores_dense", "kg_kinship_begin", "kg_kinship_accum_len",
     "kg_kinship_submit", "kg_kinship_fetch", "kg_host_alloc", "kg_host_free", "kg_synth_rows_device",
-    "kg_launch_count", "kg_kernel_time", "kg_kernel_time_reset",
+    "kg_launch_count", "kg_kernel_time", "kg_kernel_time_reset", "kg_scan_filter_sums",
 ]
 
 
@@ -84,6 +84,7 @@ def load():
     lib.kg_synth_rows_device.argtypes = [vp, u64, u64, u64, vp]
     lib.kg_launch_count.argtypes = [vp]
     lib.kg_launch_count.restype = u64
+    lib.kg_scan_filter_sums.argtypes = [vp, vp, u64, vp, vp]
     lib.kg_kernel_time.argtypes = [vp, C.c_int, C.POINTER(C.c_double), u64p, u64p]
     lib.kg_kernel_time_reset.argtypes = [vp]
     _lib = lib
@@ -201,6 +202,13 @@ class Context:
                                                  keep.ctypes.data_as(C.POINTER(C.c_uint8)),
                                                  scores.ctypes.data_as(C.POINTER(C.c_double))))
         return keep.astype(bool), scores
+
+    def filter_sums(self, rows, n_rows: int):
+        """-> (q[n_rows, P] int32 exact sums of the tensor-core filter, yq[P, 64*W_file] int8 quantised phenotypes)"""
+        q = np.zeros((n_rows, self.n_pheno), dtype=np.int32)
+        yq = np.zeros((self.n_pheno, 64 * self.w_file), dtype=np.int8)
+        self._chk(self._lib.kg_scan_filter_sums(self._h, _rows_ptr(rows), int(n_rows), q.ctypes.data, yq.ctypes.data))
+        return q, yq
 
     # ---- kinship
     def kinship_accum_len(self) -> int:

@@ -79,6 +79,7 @@ struct kg_ctx {
 	KgTcState tc;
 
 	int scan_engine = 0, kin_engine = 0;
+	bool interval_used_filter = false;
 
 	// per-launch device timing (KG_OPT_KERNEL_TIMING)
 	bool timing = false;
@@ -570,6 +571,7 @@ extern "C" kg_status kg_scan_submit(kg_ctx *c, const uint64_t *rows, uint64_t n_
 	if (use_tc) {
 		st = kg_tc_scan_tile(c, dev, n_rows, first_row_id);
 		if (st != KG_OK) return st;
+		c->interval_used_filter = true;
 	} else {
 		KgRowView view;
 		st = memory_view(c, dev, n_rows, &view);
@@ -595,6 +597,8 @@ extern "C" kg_status kg_scan_fetch(kg_ctx *c, kg_hit *out, size_t cap, size_t *n
 	if (cnt[0] > c->hit_capacity || cnt[2] > c->tc.pair_capacity) {
 		// roll back to the last committed state; the caller resubmits in smaller pieces
 		unsigned long long reset[4] = {0, c->kept_committed, 0, 0};
+		c->tc.use_filter = false;
+		c->interval_used_filter = false;
 		KG_CUDA(c, cudaMemcpy(c->d_counters, reset, sizeof reset, cudaMemcpyHostToDevice));
 		c->rows_seen = c->rows_seen_committed;
 		c->pending = false;
@@ -608,7 +612,17 @@ extern "C" kg_status kg_scan_fetch(kg_ctx *c, kg_hit *out, size_t cap, size_t *n
 		KG_CUDA(c, cudaMemset(c->d_counters, 0, sizeof(unsigned long long)));
 		c->hits_sorted = false;
 	}
-	KG_CUDA(c, cudaMemset(c->d_counters + 2, 0, sizeof(unsigned long long)));
+	KG_CUDA(c, cudaMemset(c->d_counters + 2, 0, 2 * sizeof(unsigned long long)));
+	// auto engine: candidate density of the interval that just ended decides the next one
+	{
+		const uint64_t rows_iv = c->rows_seen - c->rows_seen_committed;
+		if (rows_iv > 0 && c->n_pheno > 0) {
+			const double cells = (double)rows_iv * (double)c->n_pheno;
+			if (c->interval_used_filter) c->tc.use_filter = (double)cnt[2] / cells < 0.02;
+			else c->tc.use_filter = (double)cnt[0] / cells < 0.002;
+		}
+		c->interval_used_filter = false;
+	}
 	c->kept_committed = cnt[1];
 	c->rows_seen_committed = c->rows_seen;
 	c->pending = false;
@@ -664,6 +678,20 @@ extern "C" kg_status kg_scan_scores_dense(kg_ctx *c, const uint64_t *rows, uint6
 	if (st != KG_OK) return st;
 	KG_CUDA(c, e1); KG_CUDA(c, e2); KG_CUDA(c, e3);
 	return KG_OK;
+}
+
+extern "C" kg_status kg_scan_filter_sums(kg_ctx *c, const uint64_t *rows, uint64_t n_rows, int32_t *q, int8_t *yq) {
+	if (!c) return KG_ERR_INVALID;
+	if (!c->d_y_lane) KG_FAIL(c, KG_ERR_STATE, "kg_scan_filter_sums: call kg_scan_set_phenotypes first");
+	if (n_rows == 0) return KG_OK;
+	if (!rows || !q) KG_FAIL(c, KG_ERR_INVALID, "kg_scan_filter_sums: null argument");
+	KG_CUDA(c, cudaSetDevice(c->device));
+	const uint64_t *dev = nullptr;
+	kg_status st = acquire_tile(c, rows, n_rows, &dev);
+	if (st != KG_OK) return st;
+	st = kg_tc_filter_debug(c, dev, n_rows, q, yq);
+	if (st != KG_OK) return st;
+	return release_tile(c);
 }
 
 // ------------------------------------------------------------------------------------- kinship

@@ -233,7 +233,8 @@ struct KgPairParams {
 	const uint64_t *file_mask;   // [W_file] m_map_mask
 	const double *thr;
 	const uint2 *pairs;          // (row in tile, phenotype)
-	const unsigned long long *n_pairs;  // device counter written by the filter kernel
+	const unsigned long long *n_pairs;  // device counter written by the filter kernel (end of this tile's pairs)
+	const unsigned long long *pair_begin;  // first pair of this tile (pairs of earlier tiles were refined already)
 	uint64_t pair_capacity;
 	kg_hit *hits;
 	unsigned long long *hit_count;
@@ -246,8 +247,9 @@ __global__ void __launch_bounds__(256) kg_scan_pairs_kernel(const KgPairParams p
 	const uint32_t grp_base = (threadIdx.x & 31) & ~3u;
 	unsigned long long n = *prm.n_pairs;
 	if (n > prm.pair_capacity) n = prm.pair_capacity;
-	const uint64_t n_iter = (n + 63) / 64 * 64;  // keep all lanes of a warp in the loop for the shuffles
-	for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2; i < n_iter;
+	const unsigned long long begin = *prm.pair_begin;
+	const uint64_t n_iter = begin + (n - begin + 63) / 64 * 64;  // keep all lanes of a warp in the loop for the shuffles
+	for (uint64_t i = begin + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2); i < n_iter;
 	     i += ((uint64_t)gridDim.x * blockDim.x) >> 2) {
 		const bool valid = i < n;
 		uint2 pr = valid ? prm.pairs[i] : make_uint2(0, 0);
@@ -291,4 +293,9 @@ __global__ void __launch_bounds__(256) kg_scan_pairs_kernel(const KgPairParams p
 			}
 		}
 	}
+}
+
+// after a tile's pairs are refined: the next tile's pairs start where this tile's ended
+__global__ void kg_scan_pairs_advance_kernel(const unsigned long long *n_pairs, unsigned long long *pair_begin) {
+	*pair_begin = *n_pairs;
 }
