@@ -75,8 +75,8 @@ enum {
 /* Kernel classes reported by kg_kernel_time */
 enum {
 	KG_KERNEL_SCAN_EXACT = 0,  /* exact fp32-order score kernel over every (row, phenotype) */
-	KG_KERNEL_SCAN_FILTER = 1, /* int8 tensor-core bound kernel (candidate pairs) */
-	KG_KERNEL_SCAN_REFINE = 2, /* exact re-score of candidate pairs */
+	KG_KERNEL_SCAN_FILTER = 1, /* int8 tensor-core bound kernel (lists the rows it cannot rule out) */
+	KG_KERNEL_SCAN_REFINE = 2, /* exact re-score of the listed rows (reported "rows" = rows re-scored) */
 	KG_KERNEL_KINSHIP = 3,     /* Gram accumulation (popcount or tensor-core engine) */
 	KG_KERNEL_AUX = 4,         /* squeeze / MAC prefilter / finalize / synthetic generator */
 	KG_KERNEL_CLASSES = 5
@@ -102,7 +102,8 @@ kg_status kg_sync(kg_ctx *ctx);
  * (associate_kmers.cpp:99-102).  May be called again to change phenotypes. */
 kg_status kg_scan_set_phenotypes(kg_ctx *ctx, const float *y, uint32_t n_pheno, uint64_t min_count);
 
-/* thresholds[p]: only (row, p) with score > thresholds[p] are reported; a negative threshold reports
+/* Stream-ordered and asynchronous: tiles already submitted keep the thresholds they were submitted with.
+ * thresholds[p]: only (row, p) with score > thresholds[p] are reported; a negative threshold reports
  * every row passing the MAC filter (heap not yet full).  The caller passes the current
  * BestAssociationsHeap::lowest_score of each phenotype's heap
  * (/root/reference/src/best_associations_heap.cpp:43-59: strict '>'); because that value never
@@ -113,13 +114,27 @@ kg_status kg_scan_set_thresholds(kg_ctx *ctx, const double *thresholds, uint32_t
  * context's hit buffer.  first_row_id: id given to the tile's first row (kg_hit.row). */
 kg_status kg_scan_submit(kg_ctx *ctx, const uint64_t *rows, uint64_t n_rows, uint64_t first_row_id);
 
-/* Wait for all submitted tiles; copy out up to cap hits, sorted by (pheno, row).  *n_hits = number
- * available (call again with a larger buffer if > cap; hits stay until kg_scan_clear_hits).
- * rows_seen / rows_kept (either may be NULL): totals since kg_scan_set_phenotypes -- rows_kept is the
- * reference's number_of_insertion() (.tested_kmers, associate_kmers.cpp:203-205). */
+/* Hits are produced in INTERVALS.  Every kg_scan_submit appends to the open interval; kg_scan_mark closes it
+ * without waiting for the device and opens the next one, so that the device scans interval i+1 while the host
+ * fetches and replays interval i.  At most one closed interval may be waiting for kg_scan_fetch. */
+kg_status kg_scan_mark(kg_ctx *ctx);
+
+/* Wait for the oldest closed interval (the open one is closed first when none is waiting).
+ * *n_hits = its number of hits.  If out != NULL and cap >= *n_hits, the hits are copied to out -- in NO particular
+ * order; a buffer from kg_host_alloc makes this a single DMA -- and the interval is consumed.  Otherwise it stays
+ * pending: call again with a large enough buffer, or drop it with kg_scan_clear_hits.
+ * rows_seen / rows_kept (either may be NULL): totals since kg_scan_set_phenotypes over every fetched interval
+ * including this one -- rows_kept is the reference's number_of_insertion() (.tested_kmers,
+ * associate_kmers.cpp:203-205).
+ * KG_ERR_HITS_OVERFLOW: the interval produced more hits than the hit buffer holds; it is dropped, its rows are not
+ * counted, and the caller must submit them again in smaller intervals. */
 kg_status kg_scan_fetch(kg_ctx *ctx, kg_hit *out, size_t cap, size_t *n_hits,
                         uint64_t *rows_seen, uint64_t *rows_kept);
+/* Drop the hits of a fetched-but-not-copied interval (its rows still count as seen). */
 kg_status kg_scan_clear_hits(kg_ctx *ctx);
+/* Wait for the device and drop every interval that has not been consumed (closed or open) WITHOUT counting
+ * its rows: the state is as it was after the last consumed interval (recovery after KG_ERR_HITS_OVERFLOW). */
+kg_status kg_scan_discard(kg_ctx *ctx);
 
 /* Testing / --k_mers_scores aid: exact scores of EVERY row of one tile.
  * keep[r] = row passes the MAC filter; scores[p * n_rows + r] valid where keep[r].  Host outputs. */

@@ -24,8 +24,8 @@ HIT_DTYPE = np.dtype([("row", "<u8"), ("kmer", "<u8"), ("score", "<f8"), ("pheno
 # every symbol include/kmersgwas_b200.h declares
 ABI_SYMBOLS = [
     "kg_abi_version", "kg_ctx_create", "kg_ctx_destroy", "kg_last_error", "kg_set_option", "kg_sync",
-    "kg_scan_set_phenotypes", "kg_scan_set_thresholds", "kg_scan_submit", "kg_scan_fetch",
-    "kg_scan_clear_hits", "kg_scan_scores_dense", "kg_kinship_begin", "kg_kinship_accum_len",
+    "kg_scan_set_phenotypes", "kg_scan_set_thresholds", "kg_scan_submit", "kg_scan_mark", "kg_scan_fetch",
+    "kg_scan_clear_hits", "kg_scan_discard", "kg_scan_scores_dense", "kg_kinship_begin", "kg_kinship_accum_len",
     "kg_kinship_submit", "kg_kinship_fetch", "kg_host_alloc", "kg_host_free", "kg_synth_rows_device",
     "kg_launch_count", "kg_kernel_time", "kg_kernel_time_reset", "kg_scan_filter_sums",
 ]
@@ -70,8 +70,10 @@ def load():
     lib.kg_scan_set_phenotypes.argtypes = [vp, C.POINTER(C.c_float), C.c_uint32, u64]
     lib.kg_scan_set_thresholds.argtypes = [vp, C.POINTER(C.c_double), C.c_uint32]
     lib.kg_scan_submit.argtypes = [vp, vp, u64, u64]
+    lib.kg_scan_mark.argtypes = [vp]
     lib.kg_scan_fetch.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t), u64p, u64p]
     lib.kg_scan_clear_hits.argtypes = [vp]
+    lib.kg_scan_discard.argtypes = [vp]
     lib.kg_scan_scores_dense.argtypes = [vp, vp, u64, C.POINTER(C.c_uint8), C.POINTER(C.c_double)]
     lib.kg_kinship_begin.argtypes = [vp, u64, vp]
     lib.kg_kinship_accum_len.argtypes = [vp]
@@ -183,16 +185,22 @@ class Context:
         self._keepalive = rows
         self._chk(self._lib.kg_scan_submit(self._h, _rows_ptr(rows), int(n_rows), int(first_row_id)))
 
-    def scan_fetch(self, clear: bool = True):
-        """-> (hits structured array sorted by (pheno,row), rows_seen, rows_kept)"""
+    def scan_discard(self):
+        self._chk(self._lib.kg_scan_discard(self._h))
+
+    def scan_mark(self):
+        self._chk(self._lib.kg_scan_mark(self._h))
+
+    def scan_fetch(self):
+        """Fetch the oldest interval -> (hits structured array sorted by (pheno, row), rows_seen, rows_kept).
+        (The C ABI returns hits in no particular order; sorting here is a convenience of this binding.)"""
         n = C.c_size_t(0)
         seen, kept = C.c_uint64(0), C.c_uint64(0)
         self._chk(self._lib.kg_scan_fetch(self._h, None, 0, C.byref(n), C.byref(seen), C.byref(kept)))
         hits = np.zeros(n.value, dtype=HIT_DTYPE)
         if n.value:
             self._chk(self._lib.kg_scan_fetch(self._h, hits.ctypes.data, n.value, C.byref(n), None, None))
-        if clear:
-            self._chk(self._lib.kg_scan_clear_hits(self._h))
+            hits = hits[np.lexsort((hits["row"], hits["pheno"]))]
         return hits, int(seen.value), int(kept.value)
 
     def scores_dense(self, rows, n_rows: int):

@@ -27,6 +27,7 @@ def load():
     lib.kgh_session_destroy.argtypes = [vp]
     lib.kgh_session_destroy.restype = None
     lib.kgh_session_associate.argtypes = [vp, vp, u64, u64]
+    lib.kgh_session_finish.argtypes = [vp]
     lib.kgh_session_ctx.argtypes = [vp]
     lib.kgh_session_ctx.restype = vp
     lib.kgh_session_heap_size.argtypes = [vp, u32]
@@ -104,6 +105,11 @@ class Session:
         self._keepalive = rows
         if self._lib.kgh_session_associate(self._h, _rows_ptr(rows), int(n_rows), int(first_row_id)) != 0:
             raise RuntimeError("kgh_session_associate: " + self._lib.kgh_last_error().decode())
+
+    def finish(self):
+        """Replay the round still in flight on the device; afterwards the heaps are final for the rows given so far."""
+        if self._lib.kgh_session_finish(self._h) != 0:
+            raise RuntimeError("kgh_session_finish: " + self._lib.kgh_last_error().decode())
 
     @property
     def ctx_handle(self):

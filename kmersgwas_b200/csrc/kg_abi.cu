@@ -45,14 +45,28 @@ struct kg_ctx {
 	std::vector<float> h_sums;
 	std::vector<double> h_thr;
 
-	// hits / counters
+	// hits / counters.  Hits are produced in intervals (kg_scan_mark): two sets of device buffers so that the
+	// device fills interval i+1 while the host fetches interval i.  d_hits / d_counters point at the OPEN interval.
+	struct ScanInterval {
+		kg_hit *d_hits = nullptr;
+		unsigned long long *d_cnt = nullptr;   // [0] hits [1] kept rows [2] rows listed by the filter (current tile)
+		                                       // [4] debug scratch [5] rows listed by the filter (whole interval)
+		unsigned long long *h_cnt = nullptr;   // pinned copy of d_cnt, valid once `done` has completed
+		cudaEvent_t done = nullptr;
+		uint64_t rows = 0;                     // rows submitted into this interval
+		bool closed = false;                   // marked, waiting for kg_scan_fetch
+		bool used_filter = false;
+	} iv[2];
+	int cur = 0;
 	kg_hit *d_hits = nullptr;
 	uint64_t hit_capacity = 1ull << 22;
-	unsigned long long *d_counters = nullptr;  // [0] hits  [1] kept  [2] pairs [3] spare
-	std::vector<kg_hit> h_hits;
-	bool hits_sorted = true;
-	uint64_t rows_seen = 0, rows_seen_committed = 0, kept_committed = 0;
-	bool pending = false;
+	unsigned long long *d_counters = nullptr;
+	uint64_t rows_seen_total = 0, kept_total = 0;   // over consumed intervals
+	cudaStream_t d2h_stream = nullptr;
+	// pinned staging ring for stream-ordered threshold updates (no host sync)
+	struct ThrStage { double *h_thr = nullptr; float2 *h_gc = nullptr; cudaEvent_t ev = nullptr; } thr_stage[4];
+	int thr_next = 0;
+	size_t thr_stage_p = 0, thr_stage_g = 0;
 
 	// tile upload
 	uint64_t *d_tile[2] = {nullptr, nullptr};
@@ -79,7 +93,6 @@ struct kg_ctx {
 	KgTcState tc;
 
 	int scan_engine = 0, kin_engine = 0;
-	bool interval_used_filter = false;
 
 	// per-launch device timing (KG_OPT_KERNEL_TIMING)
 	bool timing = false;
@@ -155,6 +168,11 @@ static void timing_resolve(kg_ctx *c) {
 	}
 	c->timed_pending.clear();
 }
+
+struct KgScanParams;
+static KgScanParams scan_params(kg_ctx *c, const KgRowView &view, uint64_t first_row_id);
+template <int MODE> static kg_status launch_exact_pt(kg_ctx *c, const KgScanParams &prm);
+static kg_status ensure_squeeze_scratch(kg_ctx *c, uint64_t n_rows);
 
 // tensor-core engine (needs kg_ctx and the macros above)
 #include "kg_tc.cuh"
@@ -236,8 +254,16 @@ static kg_status ctx_init(kg_ctx *c, int device, const kg_shape *shape, void *st
 	KG_CUDA(c, dev_alloc_copy(&c->d_file_mask, file_mask));
 	KG_CUDA(c, dev_alloc_copy(&c->d_mem_mask, mem_mask));
 	KG_CUDA(c, dev_alloc_copy(&c->d_mask32, mask32));
-	KG_CUDA(c, cudaMalloc((void **)&c->d_counters, 8 * sizeof(unsigned long long)));
-	KG_CUDA(c, cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long)));
+	KG_CUDA(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; i++) {
+		KG_CUDA(c, cudaMalloc((void **)&c->iv[i].d_cnt, 8 * sizeof(unsigned long long)));
+		KG_CUDA(c, cudaMemset(c->iv[i].d_cnt, 0, 8 * sizeof(unsigned long long)));
+		KG_CUDA(c, cudaMallocHost((void **)&c->iv[i].h_cnt, 8 * sizeof(unsigned long long)));
+		KG_CUDA(c, cudaEventCreateWithFlags(&c->iv[i].done, cudaEventDisableTiming));
+	}
+	for (int i = 0; i < 4; i++) KG_CUDA(c, cudaEventCreateWithFlags(&c->thr_stage[i].ev, cudaEventDisableTiming));
+	c->cur = 0;
+	c->d_counters = c->iv[0].d_cnt;
 	return KG_OK;
 }
 
@@ -262,7 +288,18 @@ extern "C" void kg_ctx_destroy(kg_ctx *c) {
 	if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
 	cudaFree(c->d_map_mem); cudaFree(c->d_map_lane); cudaFree(c->d_file_mask); cudaFree(c->d_mem_mask);
 	cudaFree(c->d_mask32); cudaFree(c->d_y_lane); cudaFree(c->d_sums); cudaFree(c->d_thr);
-	cudaFree(c->d_hits); cudaFree(c->d_counters); cudaFree(c->d_squeezed); cudaFree(c->d_keep_bits);
+	for (int i = 0; i < 2; i++) {
+		cudaFree(c->iv[i].d_hits); cudaFree(c->iv[i].d_cnt);
+		if (c->iv[i].h_cnt) cudaFreeHost(c->iv[i].h_cnt);
+		if (c->iv[i].done) cudaEventDestroy(c->iv[i].done);
+	}
+	for (int i = 0; i < 4; i++) {
+		if (c->thr_stage[i].h_thr) cudaFreeHost(c->thr_stage[i].h_thr);
+		if (c->thr_stage[i].h_gc) cudaFreeHost(c->thr_stage[i].h_gc);
+		if (c->thr_stage[i].ev) cudaEventDestroy(c->thr_stage[i].ev);
+	}
+	if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+	cudaFree(c->d_squeezed); cudaFree(c->d_keep_bits);
 	cudaFree(c->d_ibs);
 	if (c->own_accum) cudaFree(c->d_accum);
 	kg_tc_free(&c->tc);
@@ -289,7 +326,7 @@ extern "C" kg_status kg_set_option(kg_ctx *c, int option, int64_t value) {
 		return KG_OK;
 	case KG_OPT_HIT_CAPACITY:
 		if (value < 1) KG_FAIL(c, KG_ERR_INVALID, "hit capacity must be >= 1");
-		if (c->d_hits) KG_FAIL(c, KG_ERR_STATE, "hit capacity must be set before the first submit");
+		if (c->iv[0].d_hits) KG_FAIL(c, KG_ERR_STATE, "hit capacity must be set before the first submit");
 		c->hit_capacity = (uint64_t)value;
 		return KG_OK;
 	case KG_OPT_KINSHIP_ENGINE:
@@ -418,6 +455,21 @@ static kg_status memory_view(kg_ctx *c, const uint64_t *dev, uint64_t n_rows, Kg
 		*view = KgRowView{dev, n_rows, c->w_file + 1, c->w_file};
 		return KG_OK;
 	}
+	kg_status st0 = ensure_squeeze_scratch(c, n_rows);
+	if (st0 != KG_OK) return st0;
+	KgRowView raw{dev, n_rows, c->w_file + 1, c->w_file};
+	const uint64_t total = n_rows * (uint64_t)(c->w_mem + 1);
+	const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->sm_count * 16);
+	timing_begin(c, KG_KERNEL_AUX, n_rows);
+	kg_squeeze_kernel<<<std::max(grid, 1u), 256, 0, c->stream>>>(raw, c->d_map_mem, (uint32_t)c->n_used, c->w_mem,
+	                                                             c->d_squeezed, nullptr, nullptr);
+	timing_end(c);
+	KG_LAUNCH_CHECK(c);
+	*view = KgRowView{c->d_squeezed, n_rows, c->w_mem + 1, c->w_mem};
+	return KG_OK;
+}
+
+static kg_status ensure_squeeze_scratch(kg_ctx *c, uint64_t n_rows) {
 	const size_t need = (size_t)n_rows * (c->w_mem + 1) * 8;
 	if (c->squeezed_cap < need) {
 		KG_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -428,15 +480,6 @@ static kg_status memory_view(kg_ctx *c, const uint64_t *dev, uint64_t n_rows, Kg
 		if (me != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc(%zu) squeeze scratch: %s", need, cudaGetErrorString(me));
 		c->squeezed_cap = need;
 	}
-	KgRowView raw{dev, n_rows, c->w_file + 1, c->w_file};
-	const uint64_t total = n_rows * (uint64_t)(c->w_mem + 1);
-	const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->sm_count * 16);
-	timing_begin(c, KG_KERNEL_AUX, n_rows);
-	kg_squeeze_kernel<<<std::max(grid, 1u), 256, 0, c->stream>>>(raw, c->d_map_mem, (uint32_t)c->n_used, c->w_mem,
-	                                                             c->d_squeezed);
-	timing_end(c);
-	KG_LAUNCH_CHECK(c);
-	*view = KgRowView{c->d_squeezed, n_rows, c->w_mem + 1, c->w_mem};
 	return KG_OK;
 }
 
@@ -478,14 +521,30 @@ extern "C" kg_status kg_scan_set_phenotypes(kg_ctx *c, const float *y, uint32_t 
 	KG_CUDA(c, dev_alloc_copy(&c->d_sums, c->h_sums));
 	c->h_thr.assign(c->p_alloc, -1.0);
 	KG_CUDA(c, dev_alloc_copy(&c->d_thr, c->h_thr));
-	if (!c->d_hits) {
-		cudaError_t me = cudaMalloc((void **)&c->d_hits, c->hit_capacity * sizeof(kg_hit));
-		if (me != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc hit buffer: %s", cudaGetErrorString(me));
+	for (int i = 0; i < 2; i++) {
+		if (!c->iv[i].d_hits) {
+			cudaError_t me = cudaMalloc((void **)&c->iv[i].d_hits, c->hit_capacity * sizeof(kg_hit));
+			if (me != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc hit buffer: %s", cudaGetErrorString(me));
+		}
+		KG_CUDA(c, cudaMemset(c->iv[i].d_cnt, 0, 8 * sizeof(unsigned long long)));
+		c->iv[i].rows = 0;
+		c->iv[i].closed = false;
+		c->iv[i].used_filter = false;
 	}
-	KG_CUDA(c, cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long)));
-	c->h_hits.clear();
-	c->rows_seen = c->rows_seen_committed = c->kept_committed = 0;
-	c->pending = false;
+	c->cur = 0;
+	c->d_hits = c->iv[0].d_hits;
+	c->d_counters = c->iv[0].d_cnt;
+	c->rows_seen_total = c->kept_total = 0;
+	// (re)size the pinned threshold staging ring
+	for (int i = 0; i < 4; i++) {
+		KG_CUDA(c, cudaEventSynchronize(c->thr_stage[i].ev));
+		if (c->thr_stage[i].h_thr) cudaFreeHost(c->thr_stage[i].h_thr);
+		if (c->thr_stage[i].h_gc) cudaFreeHost(c->thr_stage[i].h_gc);
+		c->thr_stage[i].h_thr = nullptr;
+		c->thr_stage[i].h_gc = nullptr;
+		KG_CUDA(c, cudaMallocHost((void **)&c->thr_stage[i].h_thr, (size_t)c->p_alloc * sizeof(double)));
+		KG_CUDA(c, cudaMallocHost((void **)&c->thr_stage[i].h_gc, 32 * sizeof(float2)));
+	}
 	kg_status st = kg_tc_prepare_scan(c);
 	return st;
 }
@@ -495,10 +554,16 @@ extern "C" kg_status kg_scan_set_thresholds(kg_ctx *c, const double *thr, uint32
 	if (n_pheno != c->n_pheno || !c->d_thr) KG_FAIL(c, KG_ERR_STATE, "kg_scan_set_thresholds: phenotypes not set / count mismatch");
 	KG_CUDA(c, cudaSetDevice(c->device));
 	for (uint32_t p = 0; p < n_pheno; p++) c->h_thr[p] = thr[p];
-	// stream-ordered so tiles already queued keep the thresholds they were submitted with
-	KG_CUDA(c, cudaMemcpyAsync(c->d_thr, c->h_thr.data(), (size_t)c->p_alloc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-	KG_CUDA(c, cudaStreamSynchronize(c->stream));
-	return kg_tc_update_thresholds(c);
+	// stream-ordered through a pinned staging slot: tiles already queued keep the thresholds they were submitted
+	// with, and the host never waits for the device here
+	kg_ctx::ThrStage &stg = c->thr_stage[c->thr_next];
+	c->thr_next = (c->thr_next + 1) & 3;
+	KG_CUDA(c, cudaEventSynchronize(stg.ev));
+	memcpy(stg.h_thr, c->h_thr.data(), (size_t)c->p_alloc * sizeof(double));
+	KG_CUDA(c, cudaMemcpyAsync(c->d_thr, stg.h_thr, (size_t)c->p_alloc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	kg_status st = kg_tc_update_thresholds(c, stg.h_gc);
+	KG_CUDA(c, cudaEventRecord(stg.ev, c->stream));
+	return st;
 }
 
 template <int R, int PT, int MODE>
@@ -516,9 +581,9 @@ static kg_status launch_exact(kg_ctx *c, const KgScanParams &prm) {
 	uint64_t gx = ((uint64_t)c->sm_count * occ) / p_tiles;
 	gx = std::max<uint64_t>(1, std::min(gx, n_chunks));
 	dim3 grid((unsigned)gx, p_tiles);
-	timing_begin(c, KG_KERNEL_SCAN_EXACT, prm.view.n_rows);
+	if (MODE != 2) timing_begin(c, KG_KERNEL_SCAN_EXACT, prm.view.n_rows);   // MODE 2 is timed by the caller (refine class)
 	kern<<<grid, 256, smem, c->stream>>>(prm);
-	timing_end(c);
+	if (MODE != 2) timing_end(c);
 	KG_LAUNCH_CHECK(c);
 	return KG_OK;
 }
@@ -571,7 +636,7 @@ extern "C" kg_status kg_scan_submit(kg_ctx *c, const uint64_t *rows, uint64_t n_
 	if (use_tc) {
 		st = kg_tc_scan_tile(c, dev, n_rows, first_row_id);
 		if (st != KG_OK) return st;
-		c->interval_used_filter = true;
+		c->iv[c->cur].used_filter = true;
 	} else {
 		KgRowView view;
 		st = memory_view(c, dev, n_rows, &view);
@@ -580,9 +645,53 @@ extern "C" kg_status kg_scan_submit(kg_ctx *c, const uint64_t *rows, uint64_t n_
 		st = launch_exact_pt<0>(c, prm);
 		if (st != KG_OK) return st;
 	}
-	c->rows_seen += n_rows;
-	c->pending = true;
+	c->iv[c->cur].rows += n_rows;
 	return release_tile(c);
+}
+
+// resolve the timed launches that have completed (no stream sync)
+static void timing_resolve_completed(kg_ctx *c) {
+	size_t done = 0;
+	while (done < c->timed_pending.size() && cudaEventQuery(c->timed_pending[done].end) == cudaSuccess) done++;
+	cudaGetLastError();
+	if (!done) return;
+	std::vector<kg_ctx::TimedLaunch> rest(c->timed_pending.begin() + done, c->timed_pending.end());
+	c->timed_pending.resize(done);
+	timing_resolve(c);
+	c->timed_pending.swap(rest);
+}
+
+extern "C" kg_status kg_scan_mark(kg_ctx *c) {
+	if (!c) return KG_ERR_INVALID;
+	if (!c->d_y_lane) KG_FAIL(c, KG_ERR_STATE, "kg_scan_mark: call kg_scan_set_phenotypes first");
+	if (c->iv[c->cur ^ 1].closed)
+		KG_FAIL(c, KG_ERR_STATE, "kg_scan_mark: the previous interval has not been fetched yet");
+	KG_CUDA(c, cudaSetDevice(c->device));
+	kg_ctx::ScanInterval &v = c->iv[c->cur];
+	KG_CUDA(c, cudaMemcpyAsync(v.h_cnt, v.d_cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+	KG_CUDA(c, cudaEventRecord(v.done, c->stream));
+	v.closed = true;
+	c->cur ^= 1;
+	kg_ctx::ScanInterval &n = c->iv[c->cur];
+	n.rows = 0;
+	n.used_filter = false;
+	KG_CUDA(c, cudaMemsetAsync(n.d_cnt, 0, 8 * sizeof(unsigned long long), c->stream));
+	c->d_hits = n.d_hits;
+	c->d_counters = n.d_cnt;
+	return KG_OK;
+}
+
+// an interval leaves the pipeline: totals, auto-engine policy
+static void consume_interval(kg_ctx *c, kg_ctx::ScanInterval &v, bool count_rows) {
+	if (count_rows) {
+		c->rows_seen_total += v.rows;
+		c->kept_total += v.h_cnt[1];
+		if (c->timing) c->timed_rows[KG_KERNEL_SCAN_REFINE] += v.h_cnt[5];  // "rows" of the refine class = rows re-scored
+		// auto engine: if the filter could not rule out most rows of the interval, the next one runs dense
+		if (v.used_filter && v.rows > 0) c->tc.use_filter = (double)v.h_cnt[5] < 0.7 * (double)v.rows;
+		else c->tc.use_filter = true;
+	}
+	v.closed = false;
 }
 
 extern "C" kg_status kg_scan_fetch(kg_ctx *c, kg_hit *out, size_t cap, size_t *n_hits, uint64_t *rows_seen,
@@ -590,59 +699,58 @@ extern "C" kg_status kg_scan_fetch(kg_ctx *c, kg_hit *out, size_t cap, size_t *n
 	if (!c) return KG_ERR_INVALID;
 	if (!c->d_y_lane) KG_FAIL(c, KG_ERR_STATE, "kg_scan_fetch: call kg_scan_set_phenotypes first");
 	KG_CUDA(c, cudaSetDevice(c->device));
+	if (!c->iv[c->cur ^ 1].closed) {
+		kg_status st = kg_scan_mark(c);
+		if (st != KG_OK) return st;
+	}
+	kg_ctx::ScanInterval &v = c->iv[c->cur ^ 1];
+	KG_CUDA(c, cudaEventSynchronize(v.done));
+	timing_resolve_completed(c);
+	const unsigned long long n = v.h_cnt[0];
+	if (n > c->hit_capacity) {
+		// the interval is dropped (its rows are not counted): the caller resubmits them in smaller pieces
+		consume_interval(c, v, false);
+		KG_FAIL(c, KG_ERR_HITS_OVERFLOW, "%llu hits exceed the hit buffer (%llu): resubmit smaller tiles", n,
+		        (unsigned long long)c->hit_capacity);
+	}
+	if (n_hits) *n_hits = (size_t)n;
+	if (rows_seen) *rows_seen = c->rows_seen_total + v.rows;
+	if (rows_kept) *rows_kept = c->kept_total + v.h_cnt[1];
+	if (out && cap >= n) {
+		if (n) {
+			KG_CUDA(c, cudaMemcpyAsync(out, v.d_hits, n * sizeof(kg_hit), cudaMemcpyDeviceToHost, c->d2h_stream));
+			KG_CUDA(c, cudaStreamSynchronize(c->d2h_stream));
+		}
+		consume_interval(c, v, true);
+	} else if (n == 0) {
+		consume_interval(c, v, true);
+	}
+	return KG_OK;
+}
+
+extern "C" kg_status kg_scan_discard(kg_ctx *c) {
+	if (!c) return KG_ERR_INVALID;
+	if (!c->d_y_lane) return KG_OK;
+	KG_CUDA(c, cudaSetDevice(c->device));
 	KG_CUDA(c, cudaStreamSynchronize(c->stream));
 	timing_resolve(c);
-	unsigned long long cnt[4];
-	KG_CUDA(c, cudaMemcpy(cnt, c->d_counters, sizeof cnt, cudaMemcpyDeviceToHost));
-	if (cnt[0] > c->hit_capacity || cnt[2] > c->tc.pair_capacity) {
-		// roll back to the last committed state; the caller resubmits in smaller pieces
-		unsigned long long reset[4] = {0, c->kept_committed, 0, 0};
-		c->tc.use_filter = false;
-		c->interval_used_filter = false;
-		KG_CUDA(c, cudaMemcpy(c->d_counters, reset, sizeof reset, cudaMemcpyHostToDevice));
-		c->rows_seen = c->rows_seen_committed;
-		c->pending = false;
-		KG_FAIL(c, KG_ERR_HITS_OVERFLOW, "%llu hits / %llu candidate pairs exceed the buffers (%llu / %llu): resubmit smaller tiles",
-		        cnt[0], cnt[2], (unsigned long long)c->hit_capacity, (unsigned long long)c->tc.pair_capacity);
+	for (int i = 0; i < 2; i++) {
+		c->iv[i].closed = false;
+		c->iv[i].rows = 0;
+		c->iv[i].used_filter = false;
+		KG_CUDA(c, cudaMemsetAsync(c->iv[i].d_cnt, 0, 8 * sizeof(unsigned long long), c->stream));
 	}
-	if (cnt[0] > 0) {
-		const size_t old = c->h_hits.size();
-		c->h_hits.resize(old + cnt[0]);
-		KG_CUDA(c, cudaMemcpy(c->h_hits.data() + old, c->d_hits, cnt[0] * sizeof(kg_hit), cudaMemcpyDeviceToHost));
-		KG_CUDA(c, cudaMemset(c->d_counters, 0, sizeof(unsigned long long)));
-		c->hits_sorted = false;
-	}
-	KG_CUDA(c, cudaMemset(c->d_counters + 2, 0, 2 * sizeof(unsigned long long)));
-	// auto engine: candidate density of the interval that just ended decides the next one
-	{
-		const uint64_t rows_iv = c->rows_seen - c->rows_seen_committed;
-		if (rows_iv > 0 && c->n_pheno > 0) {
-			const double cells = (double)rows_iv * (double)c->n_pheno;
-			if (c->interval_used_filter) c->tc.use_filter = (double)cnt[2] / cells < 0.02;
-			else c->tc.use_filter = (double)cnt[0] / cells < 0.002;
-		}
-		c->interval_used_filter = false;
-	}
-	c->kept_committed = cnt[1];
-	c->rows_seen_committed = c->rows_seen;
-	c->pending = false;
-	if (!c->hits_sorted) {
-		std::sort(c->h_hits.begin(), c->h_hits.end(), [](const kg_hit &a, const kg_hit &b) {
-			return a.pheno != b.pheno ? a.pheno < b.pheno : a.row < b.row;
-		});
-		c->hits_sorted = true;
-	}
-	if (n_hits) *n_hits = c->h_hits.size();
-	if (out && cap) memcpy(out, c->h_hits.data(), std::min(cap, c->h_hits.size()) * sizeof(kg_hit));
-	if (rows_seen) *rows_seen = c->rows_seen;
-	if (rows_kept) *rows_kept = c->kept_committed;
 	return KG_OK;
 }
 
 extern "C" kg_status kg_scan_clear_hits(kg_ctx *c) {
 	if (!c) return KG_ERR_INVALID;
-	c->h_hits.clear();
-	c->hits_sorted = true;
+	kg_ctx::ScanInterval &v = c->iv[c->cur ^ 1];
+	if (v.closed) {
+		KG_CUDA(c, cudaSetDevice(c->device));
+		KG_CUDA(c, cudaEventSynchronize(v.done));
+		consume_interval(c, v, v.h_cnt[0] <= c->hit_capacity);
+	}
 	return KG_OK;
 }
 

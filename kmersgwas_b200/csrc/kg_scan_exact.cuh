@@ -33,6 +33,10 @@ struct KgScanParams {
 	uint64_t first_row_id;
 	uint8_t *keep_out;       // dense mode
 	double *scores_out;      // dense mode [P][n_rows]
+	// row-list mode (MODE 2): score only rows row_list[0 .. *row_list_count) of the view
+	const uint32_t *row_list;
+	const unsigned long long *row_list_count;
+	uint32_t list_compact;   // 1: the view holds the listed rows back to back (squeezed copies); row_list gives their ids
 };
 
 __device__ __forceinline__ double kg_score_epilogue(float l0, float l1, float l2, float l3, double Nd,
@@ -81,7 +85,8 @@ template <int PT>
 __host__ __device__ constexpr int kg_ys_group_stride() { return 32 * PT + 4; }
 
 // grid = (row workers, p tiles); block = 256 threads.
-// MODE 0: append hits (score > thr[p], or thr[p] < 0);  MODE 1: dense keep/scores output.
+// MODE 0: append hits (score > thr[p], or thr[p] < 0);  MODE 1: dense keep/scores output;
+// MODE 2: like 0 but over the rows listed by the tensor-core filter (kept rows are counted by the filter).
 template <int R, int PT, int MODE>
 __global__ void __launch_bounds__(256) kg_scan_exact_kernel(const KgScanParams prm) {
 	extern __shared__ __align__(16) float ys[];
@@ -108,8 +113,19 @@ __global__ void __launch_bounds__(256) kg_scan_exact_kernel(const KgScanParams p
 	const uint32_t stride32 = prm.view.stride * 2;
 	const uint32_t w32_in = prm.view.w_in * 2;
 
-	for (uint64_t chunk = blockIdx.x; chunk * ROWS_PER_CTA < prm.view.n_rows; chunk += gridDim.x) {
+	const uint64_t n_work = (MODE == 2) ? (uint64_t)*prm.row_list_count : prm.view.n_rows;
+	for (uint64_t chunk = blockIdx.x; chunk * ROWS_PER_CTA < n_work; chunk += gridDim.x) {
 		const uint64_t row0 = chunk * ROWS_PER_CTA + (uint64_t)warp * (8 * R) + row_sub;
+		uint64_t rows_of[R];   // view row of work item row0 + 8 r
+		uint64_t ids_of[R];    // row id inside the submitted tile (differs from rows_of for compacted lists)
+		bool valid_of[R];
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			const uint64_t item = row0 + (uint64_t)r * 8;
+			valid_of[r] = item < n_work;
+			ids_of[r] = (MODE == 2) ? (valid_of[r] ? (uint64_t)prm.row_list[item] : 0ull) : item;
+			rows_of[r] = (MODE == 2 && prm.list_compact) ? item : ids_of[r];
+		}
 		float acc[R][PT];
 		uint32_t n1[R];
 #pragma unroll
@@ -124,9 +140,9 @@ __global__ void __launch_bounds__(256) kg_scan_exact_kernel(const KgScanParams p
 			uint32_t w[R];
 #pragma unroll
 			for (int r = 0; r < R; r++) {
-				const uint64_t row = row0 + (uint64_t)r * 8;
+				const uint64_t row = rows_of[r];
 				uint32_t v = 0;
-				if (row < prm.view.n_rows && g < w32_in) v = __ldg(row32 + row * stride32 + 2 + g);
+				if (valid_of[r] && g < w32_in) v = __ldg(row32 + row * stride32 + 2 + g);
 				w[r] = v & m32;
 				n1[r] += __popc(w[r]);
 			}
@@ -154,13 +170,13 @@ __global__ void __launch_bounds__(256) kg_scan_exact_kernel(const KgScanParams p
 			uint32_t c = n1[r];
 			c += __shfl_xor_sync(0xffffffffu, c, 1);
 			c += __shfl_xor_sync(0xffffffffu, c, 2);
-			const uint64_t row = row0 + (uint64_t)r * 8;
-			const bool in_range = row < prm.view.n_rows;
+			const uint64_t row = rows_of[r];
+			const bool in_range = valid_of[r];
 			// :121  (popcnt >= mac) && (popcnt <= N - mac)
 			const bool keep = in_range && c >= prm.min_count && c + prm.min_count <= prm.n_used;
 			if (blockIdx.y == 0 && L == 0) {
 				if (MODE == 1) { if (in_range) prm.keep_out[row] = keep ? 1 : 0; }
-				else if (keep) atomicAdd(prm.kept_count, 1ull);
+				else if (MODE == 0 && keep) atomicAdd(prm.kept_count, 1ull);
 			}
 			const double N1d = (double)c;
 #pragma unroll
@@ -180,7 +196,7 @@ __global__ void __launch_bounds__(256) kg_scan_exact_kernel(const KgScanParams p
 							const unsigned long long pos = atomicAdd(prm.hit_count, 1ull);
 							if (pos < prm.hit_capacity) {
 								kg_hit h;
-								h.row = prm.first_row_id + row;
+								h.row = prm.first_row_id + ids_of[r];
 								h.kmer = prm.view.base[row * prm.view.stride];
 								h.score = score;
 								h.pheno = p;
@@ -198,14 +214,17 @@ __global__ void __launch_bounds__(256) kg_scan_exact_kernel(const KgScanParams p
 // ---- squeeze: raw file rows -> memory-order rows (load_kmers :125-132) -------------------------
 // map_lane[(4b+L)*32 + t] = (file_word << 6) | bit of memory sample 128b + 32L + 31 - t, 0xFFFFFFFF = pad
 // Here we need memory sample order directly: map_mem[i] for memory column i.
+// With row_list != NULL only the listed rows are squeezed, back to back (out row i = raw row row_list[i]).
 __global__ void kg_squeeze_kernel(KgRowView raw, const uint32_t *__restrict__ map_mem, uint32_t n_used,
-                                  uint32_t w_mem, uint64_t *__restrict__ out) {
-	const uint64_t total = raw.n_rows * (uint64_t)(w_mem + 1);
+                                  uint32_t w_mem, uint64_t *__restrict__ out, const uint32_t *__restrict__ row_list,
+                                  const unsigned long long *__restrict__ row_list_count) {
+	const uint64_t n_out = row_list ? (uint64_t)*row_list_count : raw.n_rows;
+	const uint64_t total = n_out * (uint64_t)(w_mem + 1);
 	for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
 	     idx += (uint64_t)gridDim.x * blockDim.x) {
 		const uint64_t r = idx / (w_mem + 1);
 		const uint32_t k = (uint32_t)(idx - r * (w_mem + 1));
-		const uint64_t *row = raw.base + r * raw.stride;
+		const uint64_t *row = raw.base + (row_list ? (uint64_t)row_list[r] : r) * raw.stride;
 		if (k == 0) { out[idx] = row[0]; continue; }
 		const uint32_t mw = k - 1;
 		uint64_t v = 0;
@@ -222,80 +241,3 @@ __global__ void kg_squeeze_kernel(KgRowView raw, const uint32_t *__restrict__ ma
 	}
 }
 
-// ---- exact refine of (row, phenotype) candidate pairs straight from RAW rows --------------------
-// 4 lanes (L) per pair, 288-step sequential chains; bits gathered through map_lane.
-struct KgPairParams {
-	KgRowView raw;               // raw file rows
-	uint32_t nb, n_used, n_pheno, min_count;
-	const float *y_lane;         // [P_pad][nb*128]
-	const float *sums;
-	const uint32_t *map_lane;    // [nb*128]
-	const uint64_t *file_mask;   // [W_file] m_map_mask
-	const double *thr;
-	const uint2 *pairs;          // (row in tile, phenotype)
-	const unsigned long long *n_pairs;  // device counter written by the filter kernel (end of this tile's pairs)
-	const unsigned long long *pair_begin;  // first pair of this tile (pairs of earlier tiles were refined already)
-	uint64_t pair_capacity;
-	kg_hit *hits;
-	unsigned long long *hit_count;
-	uint64_t hit_capacity;
-	uint64_t first_row_id;
-};
-
-__global__ void __launch_bounds__(256) kg_scan_pairs_kernel(const KgPairParams prm) {
-	const uint32_t L = threadIdx.x & 3;
-	const uint32_t grp_base = (threadIdx.x & 31) & ~3u;
-	unsigned long long n = *prm.n_pairs;
-	if (n > prm.pair_capacity) n = prm.pair_capacity;
-	const unsigned long long begin = *prm.pair_begin;
-	const uint64_t n_iter = begin + (n - begin + 63) / 64 * 64;  // keep all lanes of a warp in the loop for the shuffles
-	for (uint64_t i = begin + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2); i < n_iter;
-	     i += ((uint64_t)gridDim.x * blockDim.x) >> 2) {
-		const bool valid = i < n;
-		uint2 pr = valid ? prm.pairs[i] : make_uint2(0, 0);
-		const uint64_t *row = prm.raw.base + (uint64_t)pr.x * prm.raw.stride;
-		const float *y = prm.y_lane + (size_t)pr.y * (prm.nb * 128);
-		float acc = 0.0f;
-		if (valid) {
-			for (uint32_t b = 0; b < prm.nb; b++) {
-				const uint32_t g = b * 4 + L;
-#pragma unroll 4
-				for (uint32_t t = 0; t < 32; t++) {
-					const uint32_t m = __ldg(prm.map_lane + g * 32 + t);
-					if (m != 0xFFFFFFFFu) {
-						const uint64_t wv = __ldg(row + 1 + (m >> 6));
-						if ((wv >> (m & 63)) & 1ull) acc = __fadd_rn(acc, __ldg(y + g * 32 + t));
-					}
-				}
-			}
-		}
-		const float l0 = __shfl_sync(0xffffffffu, acc, grp_base + 0);
-		const float l1 = __shfl_sync(0xffffffffu, acc, grp_base + 1);
-		const float l2 = __shfl_sync(0xffffffffu, acc, grp_base + 2);
-		const float l3 = __shfl_sync(0xffffffffu, acc, grp_base + 3);
-		if (valid && L == 0) {
-			uint32_t c = 0;
-			for (uint32_t k = 0; k < prm.raw.w_in; k++) c += __popcll(row[1 + k] & prm.file_mask[k]);
-			const double score =
-			    kg_score_epilogue(l0, l1, l2, l3, (double)prm.n_used, (double)c, prm.sums[pr.y]);
-			const double th = prm.thr[pr.y];
-			if (th < 0.0 || score > th) {
-				const unsigned long long pos = atomicAdd(prm.hit_count, 1ull);
-				if (pos < prm.hit_capacity) {
-					kg_hit h;
-					h.row = prm.first_row_id + pr.x;
-					h.kmer = row[0];
-					h.score = score;
-					h.pheno = pr.y;
-					h.pad_ = 0;
-					prm.hits[pos] = h;
-				}
-			}
-		}
-	}
-}
-
-// after a tile's pairs are refined: the next tile's pairs start where this tile's ended
-__global__ void kg_scan_pairs_advance_kernel(const unsigned long long *n_pairs, unsigned long long *pair_begin) {
-	*pair_begin = *n_pairs;
-}

@@ -4,7 +4,8 @@
 // phenotype values (hard part 2).  The reference's result is defined by a float32
 // summation order, so the tensor core cannot produce it -- but it can prove, for almost every
 // (row, phenotype) pair, that the reference score cannot exceed the heap threshold.  Only the pairs it
-// cannot rule out go to the exact kernel (kg_scan_pairs_kernel), so the reported hits stay bit-identical.
+// cannot rule out send their ROW to the exact kernel (kg_scan_exact_kernel in row-list mode), so the reported
+// hits stay bit-identical.
 //
 // Bound (DESIGN.md section 4 has the derivation).  Per phenotype p, host side (kg_tc.cuh):
 //   ybar = sum_ref / N,  c_i = y_i - ybar,  s = max|c_i| / 127,  q_i = rint(c_i / s) in [-127, 127],
@@ -15,14 +16,19 @@
 //   |r_ref| <= N s ( |Q| + m/2 + kappa ),      kappa = (|e_tot| + gamma A + |N ybar - sum_ref|) / s + 1
 //   score_ref = r_ref^2 / den > thr   ==>   |Q| >= alpha sqrt(den) - m/2 - kappa,   alpha = sqrt(thr) / (N s)
 // with alpha rounded down and sqrt(den) rounded down, so no qualifying pair is ever dropped.
+// The phenotype columns are sorted by alpha and tested 16 at a time: max |Q| of the group against the group's
+// smallest alpha and largest kappa.  A row with no surviving group is ruled out for every phenotype.
 //
 // Kernel: persistent, one CTA per SM, 128-row blocks, warp-specialised:
 //   warp 0      bulk-async-copies raw 128-row blocks (contiguous 128 * 8(1+W) bytes) into a 2-stage ring
-//   warps 2-5   expand presence bits -> u8 {0,1} into K-major core-matrix A stages (16 KB = 128 rows x 128 columns)
+//   warps 2-9   expand presence bits -> u8 {0,0x80} into K-major core-matrix A stages (16 KB = 128 rows x 128 columns)
+//               with one 64-bit multiply per presence byte
 //   warp 1      one thread issues tcgen05.mma kind::i8 (M = 128, N = P_pad, K = 32 per instruction) into a
 //               double-buffered TMEM accumulator; B (quantised phenotypes, P_pad x K_pad s8) stays in smem
-//   warps 6-9   epilogue: masked popcount + MAC filter from the raw rows, tcgen05.ld of the 128 x P_pad
-//               accumulators, the bound test above, rare candidate pairs appended to a global list
+//   warps 10-13 epilogue: tcgen05.ld of the 128 x P_pad accumulators; column 0 of B is all-ones over the used
+//               columns, so its accumulator is the row popcount (MAC filter) for free; pass 1 takes max |Q| over the
+//               row with 3-input min/max and rules the whole row out against the loosest column bound; rows that
+//               survive (rare) are appended to a global row list for the exact kernel
 #pragma once
 #include "kg_common.cuh"
 #include "kg_tc_ptx.cuh"
@@ -32,26 +38,28 @@
 #define KG_F_A_STAGE_BYTES (KG_F_ROWS * KG_F_CHUNK_COLS)
 #define KG_F_A_STAGES 3
 #define KG_F_RAW_STAGES 2
-#define KG_F_THREADS 320
 #define KG_F_EXPAND_WARP0 2
-#define KG_F_EPI_WARP0 6
+#define KG_F_EXPAND_WARPS 8
+#define KG_F_EPI_WARP0 (KG_F_EXPAND_WARP0 + KG_F_EXPAND_WARPS)
+#define KG_F_THREADS ((KG_F_EPI_WARP0 + 4) * 32)
+#define KG_F_ONE 128             // value of a set presence bit in the u8 A operand (0x80)
 
 struct KgFilterParams {
 	const uint64_t *rows;      // raw tile, 16-byte aligned
 	uint64_t n_rows;
 	uint32_t w_file;           // presence words per row
 	uint32_t nc;               // A stages per block = ceil(w_file / 2)
-	uint32_t p_pad;            // UMMA N (multiple of 16, <= 256)
+	uint32_t p_pad;            // UMMA N (multiple of 16, <= 256): column 0 = all-ones (row popcount), the phenotypes follow
+	                           // sorted by their alpha so that the 16 columns of a group have similar bounds
 	uint32_t tcols;            // TMEM columns per accumulator buffer (power of two >= p_pad, >= 32)
 	const int8_t *yq_image;    // B operand in its shared-memory byte order, b_bytes long
 	uint32_t b_bytes;          // (p_pad / 8) * sbo_b
 	uint32_t sbo_b;            // nc * 1024
-	const float2 *pconst;      // [p_pad] (alpha, kappa); padding columns hold (+inf, 0)
-	const uint64_t *file_mask; // [w_file] used-column mask (m_map_mask)
+	const float2 *gconst;      // [p_pad / 16] per 16-column group: (min alpha, max kappa) over its phenotype columns, in
+	                           // accumulator units (x KG_F_ONE); groups without phenotype columns hold (+inf, 0)
 	uint32_t n_used, min_count;
-	uint2 *pairs;              // out: (row in tile, phenotype)
-	unsigned long long *n_pairs;
-	uint64_t pair_capacity;
+	uint32_t *row_list;        // out: rows of the tile (index inside the tile) that could not be ruled out, any order
+	unsigned long long *n_listed;   // device counter for row_list (zeroed before the launch); capacity = n_rows
 	unsigned long long *kept_count;
 	int32_t *q_out;            // debug mode: [n_rows][p_pad] accumulators
 };
@@ -59,19 +67,25 @@ struct KgFilterParams {
 __host__ __device__ inline uint32_t kg_filter_raw_stage_bytes(uint32_t w_file) { return KG_F_ROWS * 8u * (w_file + 1); }
 __host__ __device__ inline size_t kg_filter_smem_bytes(uint32_t w_file, uint32_t b_bytes, uint32_t p_pad) {
 	return 1024 /*alignment slack*/ + (size_t)b_bytes + (size_t)KG_F_A_STAGES * KG_F_A_STAGE_BYTES +
-	       (size_t)KG_F_RAW_STAGES * kg_filter_raw_stage_bytes(w_file) + (size_t)p_pad * 8 + (size_t)w_file * 8 + 256;
+	       (size_t)KG_F_RAW_STAGES * kg_filter_raw_stage_bytes(w_file) + (size_t)(p_pad / 16) * 8 + 256;
+}
+// K index (byte inside the A / B operands) of file column `col`: the expander's 64-bit multiply leaves bit i of
+// every presence byte in output byte 7 - i, so B is stored with the same permutation.
+__host__ __device__ inline uint32_t kg_filter_k_of_column(uint32_t col) { return (col & ~7u) | (7u - (col & 7u)); }
+
+// 8 presence bits -> 8 bytes of 0x80 / 0x00.  x * sum_j 2^(9j): bit i lands on positions i + 9j, all distinct
+// (no carries); position 8j + 7 (the top bit of byte j) receives bit 7 - j.
+__device__ __forceinline__ uint64_t kg_spread8(uint32_t byte) {
+	return ((uint64_t)byte * 0x8040201008040201ull) & 0x8080808080808080ull;
+}
+__device__ __forceinline__ void kg_expand_u32(uint32_t w, uint32_t smem_dst) {
+	const uint64_t a = kg_spread8(__byte_perm(w, 0, 0x4440)), b = kg_spread8(__byte_perm(w, 0, 0x4441));
+	const uint64_t c = kg_spread8(__byte_perm(w, 0, 0x4442)), d = kg_spread8(__byte_perm(w, 0, 0x4443));
+	asm volatile("st.shared.v2.b64 [%0], {%1,%2};" ::"r"(smem_dst), "l"(a), "l"(b) : "memory");
+	asm volatile("st.shared.v2.b64 [%0], {%1,%2};" ::"r"(smem_dst + 128), "l"(c), "l"(d) : "memory");
 }
 
-// 4 presence bits -> 4 bytes of 0/1 (bit k -> byte k): the partial products land on distinct bit positions
-__device__ __forceinline__ uint32_t kg_spread4(uint32_t nibble) { return (nibble * 0x00204081u) & 0x01010101u; }
-
-__device__ __forceinline__ void kg_expand16(uint32_t h, uint32_t smem_dst) {
-	const uint32_t a = kg_spread4(h & 15u), b = kg_spread4((h >> 4) & 15u), c = kg_spread4((h >> 8) & 15u),
-	               d = kg_spread4((h >> 12) & 15u);
-	asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(smem_dst), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
-template <int MODE>  // 0 = candidate pairs, 1 = debug: dump accumulators
+template <int MODE>  // 0 = list candidate rows, 1 = debug: dump accumulators
 __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const KgFilterParams prm) {
 	extern __shared__ uint8_t kg_f_smem_raw[];
 	// carve shared memory (1024-byte aligned base)
@@ -81,8 +95,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 	const uint32_t raw_stage_bytes = kg_filter_raw_stage_bytes(prm.w_file);
 	uint8_t *sRaw = sA + KG_F_A_STAGES * KG_F_A_STAGE_BYTES;
 	float2 *sConst = reinterpret_cast<float2 *>(sRaw + KG_F_RAW_STAGES * raw_stage_bytes);
-	uint64_t *sMask = reinterpret_cast<uint64_t *>(sConst + prm.p_pad);
-	uint64_t *bars = sMask + prm.w_file;
+	uint64_t *bars = reinterpret_cast<uint64_t *>(sConst + prm.p_pad / 16);
 	uint64_t *raw_full = bars, *raw_empty = bars + KG_F_RAW_STAGES;
 	uint64_t *a_full = bars + 2 * KG_F_RAW_STAGES, *a_empty = a_full + KG_F_A_STAGES;
 	uint64_t *tm_full = a_empty + KG_F_A_STAGES, *tm_empty = tm_full + 2;
@@ -94,14 +107,13 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 	const uint32_t row_bytes = 8u * (prm.w_file + 1);
 
 	if (threadIdx.x == 0) {
-		for (int i = 0; i < KG_F_RAW_STAGES; i++) { kg_mbar_init(&raw_full[i], 1); kg_mbar_init(&raw_empty[i], 8); }
-		for (int i = 0; i < KG_F_A_STAGES; i++) { kg_mbar_init(&a_full[i], 4); kg_mbar_init(&a_empty[i], 1); }
+		for (int i = 0; i < KG_F_RAW_STAGES; i++) { kg_mbar_init(&raw_full[i], 1); kg_mbar_init(&raw_empty[i], KG_F_EXPAND_WARPS); }
+		for (int i = 0; i < KG_F_A_STAGES; i++) { kg_mbar_init(&a_full[i], KG_F_EXPAND_WARPS); kg_mbar_init(&a_empty[i], 1); }
 		for (int i = 0; i < 2; i++) { kg_mbar_init(&tm_full[i], 1); kg_mbar_init(&tm_empty[i], 4); }
 		kg_mbar_init(b_full, 1);
 		kg_fence_mbar_init();
 	}
-	for (uint32_t i = threadIdx.x; i < prm.p_pad; i += blockDim.x) sConst[i] = prm.pconst[i];
-	for (uint32_t i = threadIdx.x; i < prm.w_file; i += blockDim.x) sMask[i] = prm.file_mask[i];
+	for (uint32_t i = threadIdx.x; i < prm.p_pad / 16; i += blockDim.x) sConst[i] = prm.gconst[i];
 	if (warp == 1) kg_tmem_alloc(tmem_slot, 2 * prm.tcols);
 	kg_tc_fence_before();
 	__syncthreads();
@@ -160,32 +172,29 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 			}
 		}
 	} else if (warp < KG_F_EPI_WARP0) {
-		// ===================== expanders: bits -> u8 core matrices =====================
-		const uint32_t r = threadIdx.x - KG_F_EXPAND_WARP0 * 32;  // row of the block
-		const uint32_t dst_row = (r & 7) * 16 + (r >> 3) * 1024;
+		// ===================== expanders: bits -> u8 core matrices (thread = row x one u64 word per stage) ===========
+		const uint32_t t = threadIdx.x - KG_F_EXPAND_WARP0 * 32;
+		const uint32_t r = t & (KG_F_ROWS - 1), half = t >> 7;
+		const uint32_t dst_row = (r & 7) * 16 + (r >> 3) * 1024 + half * 512;
 		const uint32_t sA_addr = kg_smem_u32(sA);
 		uint32_t it = 0, ait = 0;
 		for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, it++) {
 			const uint32_t rst = it % KG_F_RAW_STAGES, ruse = it / KG_F_RAW_STAGES;
 			kg_mbar_wait(&raw_full[rst], ruse & 1);
 			const uint64_t *row = reinterpret_cast<const uint64_t *>(sRaw + rst * raw_stage_bytes + r * row_bytes) + 1;
+			uint64_t w = (half < prm.w_file) ? row[half] : 0ull;
 			for (uint32_t c = 0; c < prm.nc; c++, ait++) {
 				const uint32_t st = ait % KG_F_A_STAGES, use = ait / KG_F_A_STAGES;
-				const uint64_t w0 = row[2 * c];
-				const uint64_t w1 = (2 * c + 1 < prm.w_file) ? row[2 * c + 1] : 0ull;
+				const uint32_t nxt = 2 * (c + 1) + half;
+				const uint64_t w_next = (nxt < prm.w_file) ? row[nxt] : 0ull;   // prefetch before the wait
 				kg_mbar_wait(&a_empty[st], (use & 1) ^ 1);
 				const uint32_t dst = sA_addr + st * KG_F_A_STAGE_BYTES + dst_row;
-				kg_expand16((uint32_t)w0 & 0xFFFFu, dst);
-				kg_expand16((uint32_t)(w0 >> 16) & 0xFFFFu, dst + 128);
-				kg_expand16((uint32_t)(w0 >> 32) & 0xFFFFu, dst + 256);
-				kg_expand16((uint32_t)(w0 >> 48), dst + 384);
-				kg_expand16((uint32_t)w1 & 0xFFFFu, dst + 512);
-				kg_expand16((uint32_t)(w1 >> 16) & 0xFFFFu, dst + 640);
-				kg_expand16((uint32_t)(w1 >> 32) & 0xFFFFu, dst + 768);
-				kg_expand16((uint32_t)(w1 >> 48), dst + 896);
+				kg_expand_u32((uint32_t)w, dst);
+				kg_expand_u32((uint32_t)(w >> 32), dst + 256);
 				kg_fence_proxy_async();
 				__syncwarp();
 				if (lane == 0) kg_mbar_arrive(&a_full[st]);
+				w = w_next;
 			}
 			__syncwarp();
 			if (lane == 0) kg_mbar_arrive(&raw_empty[rst]);
@@ -198,54 +207,84 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 		unsigned long long kept_local = 0;
 		uint32_t it = 0;
 		for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, it++) {
-			const uint32_t rst = it % KG_F_RAW_STAGES, ruse = it / KG_F_RAW_STAGES;
 			const uint64_t grow = (uint64_t)blk * KG_F_ROWS + r;
-			kg_mbar_wait(&raw_full[rst], ruse & 1);
-			uint32_t n1 = 0;
-			if (grow < prm.n_rows) {
-				const uint64_t *row = reinterpret_cast<const uint64_t *>(sRaw + rst * raw_stage_bytes + r * row_bytes) + 1;
-				for (uint32_t k = 0; k < prm.w_file; k++) n1 += __popcll(row[k] & sMask[k]);
-			}
-			__syncwarp();
-			if (lane == 0) kg_mbar_arrive(&raw_empty[rst]);
-			// load_kmers :121  (popcnt >= mac) && (popcnt <= N - mac)
-			const bool keep = grow < prm.n_rows && n1 >= prm.min_count && n1 + prm.min_count <= prm.n_used;
-			kept_local += __popc(__ballot_sync(0xffffffffu, keep));
-			const float n1f = (float)n1, n0f = Nf - n1f;
-			const float hm = 0.5f * fminf(n1f, n0f);
-			const float g = __fmul_rd(__fsqrt_rd(n1f * n0f), 0.999999f);   // <= sqrt(den), den exact in fp32 (< 2^24)
-
 			const uint32_t buf = it & 1;
 			kg_mbar_wait(&tm_full[buf], (it >> 1) & 1);
 			kg_tc_fence_after();
 			const uint32_t taddr = tmem_base + buf * prm.tcols + ((q4 * 32u) << 16);
-			for (uint32_t c0 = 0; c0 < prm.p_pad; c0 += 16) {
-				uint32_t v[16];
-				kg_tmem_ld16(taddr + c0, v);
-				kg_tmem_ld_wait();
-				if (MODE == 1) {
+			if (MODE == 1) {
+				for (uint32_t c0 = 0; c0 < prm.p_pad; c0 += 16) {
+					uint32_t v[16];
+					kg_tmem_ld16(taddr + c0, v);
+					kg_tmem_ld_wait();
 					if (grow < prm.n_rows) {
 #pragma unroll
 						for (int j = 0; j < 16; j++) prm.q_out[grow * prm.p_pad + c0 + j] = (int32_t)v[j];
 					}
-				} else {
+				}
+			} else {
+				// row popcount (column 0), then per 16-column group: max |accumulator| against the group's loosest bound
+				uint32_t n1 = 0;
+				float g = 0.f, hm = 0.f;
+				bool maybe = false;
+				for (uint32_t c0 = 0; c0 < prm.p_pad; c0 += 32) {
+					uint32_t v[16], u[16];
+					kg_tmem_ld16(taddr + c0, v);
+					const bool second = c0 + 16 < prm.p_pad;   // warp-uniform
+					if (second) kg_tmem_ld16(taddr + c0 + 16, u);
+					kg_tmem_ld_wait();
+					if (c0 == 0) {
+						n1 = v[0] / KG_F_ONE;
+						v[0] = 0;
+						const float n1f = (float)n1, n0f = Nf - n1f;
+						hm = (0.5f * KG_F_ONE) * fminf(n1f, n0f);
+						g = __fmul_rd(__fsqrt_rd(n1f * n0f), 0.999999f);   // <= sqrt(den); den is exact in fp32 (< 2^24)
+					}
+					{
+						int mx = 0, mn = 0;
 #pragma unroll
-					for (int j = 0; j < 16; j++) {
-						const float2 ak = sConst[c0 + j];
-						const float thr = __fsub_rd(__fmaf_rd(ak.x, g, -ak.y), hm);
-						const float qa = (float)abs((int32_t)v[j]);
-						if (keep && qa >= thr) {
-							const unsigned long long pos = atomicAdd(prm.n_pairs, 1ull);
-							if (pos < prm.pair_capacity) prm.pairs[pos] = make_uint2((uint32_t)grow, c0 + j);
+						for (int j = 0; j < 16; j += 2) {
+							mx = __vimax3_s32(mx, (int)v[j], (int)v[j + 1]);
+							mn = __vimin3_s32(mn, (int)v[j], (int)v[j + 1]);
 						}
+						const float2 gc = sConst[c0 >> 4];
+						maybe |= !((float)max(mx, -mn) < __fsub_rd(__fmaf_rd(gc.x, g, -gc.y), hm));
+					}
+					if (second) {
+						int mx = 0, mn = 0;
+#pragma unroll
+						for (int j = 0; j < 16; j += 2) {
+							mx = __vimax3_s32(mx, (int)u[j], (int)u[j + 1]);
+							mn = __vimin3_s32(mn, (int)u[j], (int)u[j + 1]);
+						}
+						const float2 gc = sConst[(c0 >> 4) + 1];
+						maybe |= !((float)max(mx, -mn) < __fsub_rd(__fmaf_rd(gc.x, g, -gc.y), hm));
 					}
 				}
+				// accumulators are in registers: hand the TMEM buffer back to the MMA warp before the row test
+				kg_tc_fence_before();
+				__syncwarp();
+				if (lane == 0) kg_mbar_arrive(&tm_empty[buf]);
+				// load_kmers :121  (popcnt >= mac) && (popcnt <= N - mac)
+				const bool keep = grow < prm.n_rows && n1 >= prm.min_count && n1 + prm.min_count <= prm.n_used;
+				kept_local += __popc(__ballot_sync(0xffffffffu, keep));
+				maybe = maybe && keep;
+				// rows that could not be ruled out go to the exact kernel (all phenotypes of the row are re-scored in
+				// the reference's fp32 order); one atomic per warp
+				const uint32_t mb = __ballot_sync(0xffffffffu, maybe);
+				if (mb) {
+					unsigned long long basep = 0;
+					if (lane == 0) basep = atomicAdd(prm.n_listed, (unsigned long long)__popc(mb));
+					basep = __shfl_sync(0xffffffffu, basep, 0);
+					if (maybe) prm.row_list[basep + __popc(mb & ((1u << lane) - 1u))] = (uint32_t)grow;
+				}
 			}
-			kg_tc_fence_before();
-			__syncwarp();
-			if (lane == 0) kg_mbar_arrive(&tm_empty[buf]);
+			if (MODE == 1) {
+				kg_tc_fence_before();
+				__syncwarp();
+				if (lane == 0) kg_mbar_arrive(&tm_empty[buf]);
+			}
 		}
-		if (lane == 0 && kept_local && q4 == 0) { /* each row is counted by exactly one epilogue warp */ }
 		if (lane == 0 && kept_local) atomicAdd(prm.kept_count, kept_local);
 	}
 

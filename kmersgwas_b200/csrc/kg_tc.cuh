@@ -6,20 +6,30 @@
 #include "kg_scan_filter.cuh"
 
 static void kg_tc_free(KgTcState *tc) {
-	cudaFree(tc->d_pairs); cudaFree(tc->d_yq); cudaFree(tc->d_pconst); cudaFree(tc->d_scratch); cudaFree(tc->d_aligned);
-	tc->d_pairs = nullptr; tc->d_yq = nullptr; tc->d_pconst = nullptr; tc->d_scratch = nullptr; tc->d_aligned = nullptr;
+	cudaFree(tc->d_row_list); cudaFree(tc->d_yq); cudaFree(tc->d_gconst); cudaFree(tc->d_scratch); cudaFree(tc->d_aligned);
+	tc->d_row_list = nullptr; tc->d_yq = nullptr; tc->d_gconst = nullptr; tc->d_scratch = nullptr; tc->d_aligned = nullptr;
 	tc->aligned_cap = 0;
+	tc->row_list_cap = 0;
+	for (int i = 0; i < 2; i++) {
+		if (tc->img_ev[i]) { cudaEventDestroy(tc->img_ev[i]); tc->img_ev[i] = nullptr; }
+		if (tc->h_img_pinned[i]) { cudaFreeHost(tc->h_img_pinned[i]); tc->h_img_pinned[i] = nullptr; }
+	}
 }
 static bool kg_tc_scan_available(const kg_ctx *c) { return c->tc.scan_ready; }
 static bool kg_tc_kinship_available(const kg_ctx *c) { return c->tc.kin_ready; }
 
-// Auto engine choice: the filter pays off once candidate pairs are rare (every pair costs an exact
-// 4-lane re-score); while heaps are cold or thresholds low, the dense exact kernel is cheaper.
+// Auto engine choice: the filter needs a threshold for every phenotype (heaps full); it then pays off unless
+// it fails to rule out most rows (every listed row is re-scored by the exact kernel anyway).
 static bool kg_tc_scan_profitable(const kg_ctx *c) {
 	if (!c->tc.scan_ready) return false;
 	for (uint32_t p = 0; p < c->n_pheno; p++)
 		if (c->h_thr[p] < 0.0) return false;
 	return c->tc.use_filter;
+}
+
+// byte offset of B element (column n, K index k) in the shared-memory image (K-major core matrices, no swizzle)
+static size_t kg_tc_b_offset(const KgTcState &tc, uint32_t n, uint32_t k) {
+	return (size_t)(n % 8) * 16 + (size_t)(n / 8) * tc.sbo_b + (size_t)(k / 16) * 128 + (k % 16);
 }
 
 static float kg_float_down(double x) {  // largest float <= x
@@ -33,38 +43,99 @@ static float kg_float_up(double x) {  // smallest float >= x
 	return f;
 }
 
-// (alpha, kappa) of every phenotype column from the current thresholds (see kg_scan_filter.cuh header)
-static kg_status kg_tc_update_thresholds(kg_ctx *c) {
+// Column order + per-group (alpha, kappa) from the current thresholds, and the B image in that order
+// (see kg_scan_filter.cuh header).  Column 0 = all-ones (popcount); phenotypes follow sorted by alpha.
+static kg_status kg_tc_update_thresholds(kg_ctx *c, float2 *gc_pinned) {
 	KgTcState &tc = c->tc;
 	if (!tc.scan_ready) return KG_OK;
-	std::vector<float2> pc(tc.p_pad);
-	for (uint32_t p = 0; p < tc.p_pad; p++) {
-		if (p >= c->n_pheno) { pc[p] = make_float2(INFINITY, 0.0f); continue; }
+	const uint32_t P = c->n_pheno, N = (uint32_t)c->n_used;
+	std::vector<float> alpha(P), kappa(P);
+	for (uint32_t p = 0; p < P; p++) {
 		const double thr = c->h_thr[p];
-		if (tc.degenerate[p] || !(thr >= 0.0) || !std::isfinite(thr)) { pc[p] = make_float2(0.0f, 3.0e38f); continue; }
-		const double alpha = std::sqrt(thr) / ((double)c->n_used * tc.scale[p]) * (1.0 - 1e-6);
-		pc[p] = make_float2(kg_float_down(alpha), tc.kappa[p]);
+		if (tc.degenerate[p] || !(thr >= 0.0) || !std::isfinite(thr)) {
+			alpha[p] = 0.0f;      // no bound: every kept row is listed
+			kappa[p] = 3.0e38f;
+		} else {
+			const double a = std::sqrt(thr) / ((double)N * tc.scale[p]) * (1.0 - 1e-6);
+			alpha[p] = kg_float_down(a * KG_F_ONE);
+			kappa[p] = kg_float_up((double)tc.kappa[p] * KG_F_ONE);
+		}
 	}
-	KG_CUDA(c, cudaMemcpyAsync(tc.d_pconst, pc.data(), pc.size() * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
-	KG_CUDA(c, cudaStreamSynchronize(c->stream));
+	std::vector<uint32_t> order(P);
+	for (uint32_t p = 0; p < P; p++) order[p] = p;
+	std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return alpha[x] < alpha[y]; });
+	std::vector<uint32_t> col_of(P);
+	for (uint32_t k = 0; k < P; k++) col_of[order[k]] = 1 + k;
+	const uint32_t n_groups = tc.p_pad / 16;
+	// tightness of a column assignment = sum over phenotypes of the alpha their group tests with
+	auto tightness = [&](const std::vector<uint32_t> &cols) {
+		std::vector<float> amin(n_groups, INFINITY);
+		for (uint32_t p = 0; p < P; p++) amin[cols[p] / 16] = std::min(amin[cols[p] / 16], alpha[p]);
+		double t = 0.0;
+		for (uint32_t p = 0; p < P; p++) t += amin[cols[p] / 16];
+		return t;
+	};
+	// keep the uploaded column order while it is within 1 % of the sorted one (thresholds drift together)
+	const bool reorder = tc.col_of.size() != P || tightness(col_of) > 1.01 * tightness(tc.col_of);
+	if (!reorder) col_of = tc.col_of;
+	if (n_groups > 32) KG_FAIL(c, KG_ERR_STATE, "filter group constants exceed the staging slot");
+	float2 *gc = gc_pinned;
+	for (uint32_t g = 0; g < n_groups; g++) gc[g] = make_float2(INFINITY, 0.0f);
+	for (uint32_t p = 0; p < P; p++) {
+		float2 &g = gc[col_of[p] / 16];
+		g.x = std::min(g.x, alpha[p]);
+		g.y = std::max(g.y, kappa[p]);
+	}
+	if (reorder) {
+		// pinned image ring: the copy is stream-ordered behind the kernels still reading the old image
+		if (!tc.h_img_pinned[0]) {
+			for (int i = 0; i < 2; i++) {
+				KG_CUDA(c, cudaMallocHost((void **)&tc.h_img_pinned[i], tc.b_bytes));
+				KG_CUDA(c, cudaEventCreateWithFlags(&tc.img_ev[i], cudaEventDisableTiming));
+			}
+			tc.img_bytes = tc.b_bytes;
+		}
+		const int slot = tc.img_next;
+		tc.img_next ^= 1;
+		KG_CUDA(c, cudaEventSynchronize(tc.img_ev[slot]));
+		int8_t *img = tc.h_img_pinned[slot];
+		memset(img, 0, tc.b_bytes);
+		for (uint32_t i = 0; i < N; i++)  // column 0: 1 on every used file column -> accumulator = KG_F_ONE * popcount
+			img[kg_tc_b_offset(tc, 0, kg_filter_k_of_column(c->map_word[i] * 64 + c->map_bit[i]))] = 1;
+		for (uint32_t p = 0; p < P; p++) {
+			const int8_t *q = tc.h_q.data() + (size_t)p * N;
+			for (uint32_t i = 0; i < N; i++)
+				img[kg_tc_b_offset(tc, col_of[p], kg_filter_k_of_column(c->map_word[i] * 64 + c->map_bit[i]))] = q[i];
+		}
+		tc.col_of = col_of;
+		tc.h_yq_image.assign(img, img + tc.b_bytes);
+		KG_CUDA(c, cudaMemcpyAsync(tc.d_yq, img, tc.b_bytes, cudaMemcpyHostToDevice, c->stream));
+		KG_CUDA(c, cudaEventRecord(tc.img_ev[slot], c->stream));
+	}
+	KG_CUDA(c, cudaMemcpyAsync(tc.d_gconst, gc, n_groups * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
 	return KG_OK;
 }
 
 static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	KgTcState &tc = c->tc;
 	tc.scan_ready = false;
-	tc.use_filter = false;
-	cudaFree(tc.d_yq); cudaFree(tc.d_pconst);
-	tc.d_yq = nullptr; tc.d_pconst = nullptr;
+	tc.use_filter = true;
+	cudaFree(tc.d_yq); cudaFree(tc.d_gconst);
+	tc.d_yq = nullptr; tc.d_gconst = nullptr;
+	tc.col_of.clear();
+	for (int i = 0; i < 2; i++) {
+		if (tc.img_ev[i]) { cudaEventSynchronize(tc.img_ev[i]); cudaEventDestroy(tc.img_ev[i]); tc.img_ev[i] = nullptr; }
+		if (tc.h_img_pinned[i]) { cudaFreeHost(tc.h_img_pinned[i]); tc.h_img_pinned[i] = nullptr; }
+	}
 	const uint32_t P = c->n_pheno, N = (uint32_t)c->n_used;
-	tc.p_pad = (P + 15) / 16 * 16;
+	tc.p_pad = (P + 1 + 15) / 16 * 16;  // + the all-ones column
 	tc.nc = (c->w_file + 1) / 2;
 	tc.sbo_b = tc.nc * 1024;
 	tc.b_bytes = (tc.p_pad / 8) * tc.sbo_b;
 	tc.tcols = 32;
 	while (tc.tcols < tc.p_pad) tc.tcols *= 2;
 	if (c->min_count < 1) { tc.why_unavailable = "min_count = 0 (rows with an empty group have no finite bound)"; return KG_OK; }
-	if (tc.p_pad > 256) { tc.why_unavailable = "more than 256 phenotype columns per pass"; return KG_OK; }
+	if (tc.p_pad > 256) { tc.why_unavailable = "more than 255 phenotype columns per pass"; return KG_OK; }
 	if (tc.sbo_b > 0x3FFFu * 16) { tc.why_unavailable = "table too wide for the B descriptor stride"; return KG_OK; }
 	const size_t smem = kg_filter_smem_bytes(c->w_file, tc.b_bytes, tc.p_pad);
 	if (smem > 227u * 1024) {
@@ -73,8 +144,8 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	}
 	tc.smem_bytes = smem;
 
-	// quantise: centred, symmetric int8, in FILE column order (unused columns stay 0)
-	std::vector<int8_t> img(tc.b_bytes, 0);
+	// quantise: centred, symmetric int8 per phenotype
+	tc.h_q.assign((size_t)P * N, 0);
 	tc.scale.assign(P, 0.0);
 	tc.kappa.assign(P, 0.0f);
 	tc.degenerate.assign(P, 0);
@@ -96,35 +167,38 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 		const double s = amax / 127.0;
 		if (bad || !(s > 1e-30)) { tc.degenerate[p] = 1; continue; }
 		double e_tot = 0.0;
+		int8_t *qrow = tc.h_q.data() + (size_t)p * N;
 		for (uint32_t i = 0; i < N; i++) {
 			double q = std::nearbyint(cen[i] / s);
 			q = std::max(-127.0, std::min(127.0, q));
 			e_tot += cen[i] - s * q;
-			const uint32_t k = c->map_word[i] * 64 + c->map_bit[i];
-			img[(size_t)(p % 8) * 16 + (size_t)(p / 8) * tc.sbo_b + (size_t)(k / 16) * 128 + (k % 16)] = (int8_t)q;
+			qrow[i] = (int8_t)q;
 		}
 		const double t = std::fabs((double)N * ybar - sum_ref);
 		// + 1e-9 A: double rounding in the centring; + 1: float32 evaluation slack of the device-side test
 		const double kappa = (std::fabs(e_tot) + gamma * A + t + 1e-9 * A) / s + 1.0;
-		if (!(kappa < 1e30)) { tc.degenerate[p] = 1; continue; }
+		if (!(kappa < 1e30)) {
+			tc.degenerate[p] = 1;
+			std::fill(qrow, qrow + N, (int8_t)0);
+			continue;
+		}
 		tc.scale[p] = s;
 		tc.kappa[p] = kg_float_up(kappa);
 	}
-	cudaError_t e = cudaMalloc((void **)&tc.d_yq, img.size());
+	cudaError_t e = cudaMalloc((void **)&tc.d_yq, tc.b_bytes);
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc quantised phenotypes: %s", cudaGetErrorString(e));
-	KG_CUDA(c, cudaMemcpy(tc.d_yq, img.data(), img.size(), cudaMemcpyHostToDevice));
-	tc.h_yq_image.swap(img);
-	e = cudaMalloc((void **)&tc.d_pconst, tc.p_pad * sizeof(float2));
+	e = cudaMalloc((void **)&tc.d_gconst, (tc.p_pad / 16) * sizeof(float2));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc filter constants: %s", cudaGetErrorString(e));
-	if (!tc.d_pairs) {
-		e = cudaMalloc((void **)&tc.d_pairs, tc.pair_capacity * sizeof(uint2));
-		if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc candidate pairs: %s", cudaGetErrorString(e));
-	}
 	KG_CUDA(c, cudaFuncSetAttribute(kg_scan_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	KG_CUDA(c, cudaFuncSetAttribute(kg_scan_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	tc.scan_ready = true;
 	tc.why_unavailable.clear();
-	return kg_tc_update_thresholds(c);
+	kg_ctx::ThrStage &stg = c->thr_stage[c->thr_next];
+	c->thr_next = (c->thr_next + 1) & 3;
+	kg_status st = kg_tc_update_thresholds(c, stg.h_gc);
+	KG_CUDA(c, cudaEventRecord(stg.ev, c->stream));
+	KG_CUDA(c, cudaStreamSynchronize(c->stream));
+	return st;
 }
 
 // the bulk-copy producer needs a 16-byte aligned tile: realign odd device pointers through a scratch copy
@@ -158,22 +232,44 @@ static KgFilterParams kg_tc_filter_params(kg_ctx *c, const uint64_t *dev, uint64
 	f.yq_image = tc.d_yq;
 	f.b_bytes = tc.b_bytes;
 	f.sbo_b = tc.sbo_b;
-	f.pconst = tc.d_pconst;
-	f.file_mask = c->d_file_mask;
+	f.gconst = tc.d_gconst;
 	f.n_used = (uint32_t)c->n_used;
 	f.min_count = (uint32_t)std::min<uint64_t>(c->min_count, 0xFFFFFFFFull);
-	f.pairs = tc.d_pairs;
-	f.n_pairs = c->d_counters + 2;
-	f.pair_capacity = tc.pair_capacity;
+	f.row_list = tc.d_row_list;
+	f.n_listed = c->d_counters + 2;
 	f.kept_count = c->d_counters + 1;
 	return f;
 }
 
+static kg_status kg_tc_ensure_row_list(kg_ctx *c, uint64_t n_rows) {
+	KgTcState &tc = c->tc;
+	if (tc.row_list_cap >= n_rows) return KG_OK;
+	KG_CUDA(c, cudaStreamSynchronize(c->stream));
+	cudaFree(tc.d_row_list);
+	tc.d_row_list = nullptr;
+	tc.row_list_cap = 0;
+	const uint64_t cap = std::max<uint64_t>(n_rows, 1u << 20);
+	cudaError_t e = cudaMalloc((void **)&tc.d_row_list, cap * sizeof(uint32_t));
+	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc filter row list: %s", cudaGetErrorString(e));
+	tc.row_list_cap = cap;
+	return KG_OK;
+}
+
+__global__ void kg_add_counter_kernel(const unsigned long long *src, unsigned long long *dst) { *dst += *src; }
+
+// filter the tile on the tensor cores, then re-score the rows it could not rule out with the exact kernel
 static kg_status kg_tc_scan_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_rows, uint64_t first_row_id) {
 	KgTcState &tc = c->tc;
 	const uint64_t *dev = nullptr;
 	kg_status st = kg_tc_aligned_tile(c, dev_in, n_rows, &dev);
 	if (st != KG_OK) return st;
+	st = kg_tc_ensure_row_list(c, n_rows);
+	if (st != KG_OK) return st;
+	if (!c->identity) {
+		st = ensure_squeeze_scratch(c, n_rows);
+		if (st != KG_OK) return st;
+	}
+	KG_CUDA(c, cudaMemsetAsync(c->d_counters + 2, 0, sizeof(unsigned long long), c->stream));
 	KgFilterParams f = kg_tc_filter_params(c, dev, n_rows);
 	const uint32_t n_blocks = (uint32_t)((n_rows + KG_F_ROWS - 1) / KG_F_ROWS);
 	const unsigned grid = std::max(1u, std::min<uint32_t>(n_blocks, (uint32_t)c->sm_count));
@@ -182,31 +278,28 @@ static kg_status kg_tc_scan_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_r
 	timing_end(c);
 	KG_LAUNCH_CHECK(c);
 
-	KgPairParams pp;
-	memset(&pp, 0, sizeof pp);
-	pp.raw = KgRowView{dev, n_rows, c->w_file + 1, c->w_file};
-	pp.nb = c->nb;
-	pp.n_used = (uint32_t)c->n_used;
-	pp.n_pheno = c->n_pheno;
-	pp.min_count = f.min_count;
-	pp.y_lane = c->d_y_lane;
-	pp.sums = c->d_sums;
-	pp.map_lane = c->d_map_lane;
-	pp.file_mask = c->d_file_mask;
-	pp.thr = c->d_thr;
-	pp.pairs = tc.d_pairs;
-	pp.n_pairs = c->d_counters + 2;
-	pp.pair_capacity = tc.pair_capacity;
-	pp.pair_begin = c->d_counters + 3;
-	pp.hits = c->d_hits;
-	pp.hit_count = c->d_counters + 0;
-	pp.hit_capacity = c->hit_capacity;
-	pp.first_row_id = first_row_id;
+	KgRowView view{dev, n_rows, c->w_file + 1, c->w_file};
+	uint32_t compact = 0;
+	if (!c->identity) {
+		// memory-order copies of the listed rows only
+		const unsigned sg = (unsigned)c->sm_count * 8;
+		timing_begin(c, KG_KERNEL_AUX, 0);
+		kg_squeeze_kernel<<<sg, 256, 0, c->stream>>>(view, c->d_map_mem, (uint32_t)c->n_used, c->w_mem, c->d_squeezed,
+		                                            tc.d_row_list, c->d_counters + 2);
+		timing_end(c);
+		KG_LAUNCH_CHECK(c);
+		view = KgRowView{c->d_squeezed, n_rows, c->w_mem + 1, c->w_mem};
+		compact = 1;
+	}
+	KgScanParams prm = scan_params(c, view, first_row_id);
+	prm.row_list = tc.d_row_list;
+	prm.row_list_count = c->d_counters + 2;
+	prm.list_compact = compact;
 	timing_begin(c, KG_KERNEL_SCAN_REFINE, 0);
-	kg_scan_pairs_kernel<<<(unsigned)c->sm_count * 4, 256, 0, c->stream>>>(pp);
+	st = launch_exact_pt<2>(c, prm);
 	timing_end(c);
-	KG_LAUNCH_CHECK(c);
-	kg_scan_pairs_advance_kernel<<<1, 1, 0, c->stream>>>(c->d_counters + 2, c->d_counters + 3);
+	if (st != KG_OK) return st;
+	kg_add_counter_kernel<<<1, 1, 0, c->stream>>>(c->d_counters + 2, c->d_counters + 5);
 	KG_LAUNCH_CHECK(c);
 	return KG_OK;
 }
@@ -223,8 +316,6 @@ static kg_status kg_tc_filter_debug(kg_ctx *c, const uint64_t *dev_in, uint64_t 
 	cudaError_t e = cudaMalloc((void **)&d_q, (size_t)n_rows * tc.p_pad * sizeof(int32_t));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc debug sums: %s", cudaGetErrorString(e));
 	f.q_out = d_q;
-	unsigned long long dummy_kept_host = 0;
-	(void)dummy_kept_host;
 	f.kept_count = c->d_counters + 4;  // scratch counter: the debug pass must not change rows_kept
 	const uint32_t n_blocks = (uint32_t)((n_rows + KG_F_ROWS - 1) / KG_F_ROWS);
 	const unsigned grid = std::max(1u, std::min<uint32_t>(n_blocks, (uint32_t)c->sm_count));
@@ -237,13 +328,16 @@ static kg_status kg_tc_filter_debug(kg_ctx *c, const uint64_t *dev_in, uint64_t 
 	cudaFree(d_q);
 	KG_CUDA(c, e1); KG_CUDA(c, e2); KG_CUDA(c, e3);
 	for (uint64_t r = 0; r < n_rows; r++)
-		for (uint32_t p = 0; p < c->n_pheno; p++) q_host[r * c->n_pheno + p] = q[r * tc.p_pad + p];
+		for (uint32_t p = 0; p < c->n_pheno; p++) {
+			const int32_t v = q[r * tc.p_pad + tc.col_of[p]];
+			if (v % KG_F_ONE != 0) KG_FAIL(c, KG_ERR_STATE, "filter accumulator not a multiple of %d", KG_F_ONE);
+			q_host[r * c->n_pheno + p] = v / KG_F_ONE;
+		}
 	if (yq_host) {
 		const uint32_t kpad = 64 * c->w_file;
 		for (uint32_t p = 0; p < c->n_pheno; p++)
-			for (uint32_t k = 0; k < kpad; k++)
-				yq_host[(size_t)p * kpad + k] =
-				    tc.h_yq_image[(size_t)(p % 8) * 16 + (size_t)(p / 8) * tc.sbo_b + (size_t)(k / 16) * 128 + (k % 16)];
+			for (uint32_t col = 0; col < kpad; col++)
+				yq_host[(size_t)p * kpad + col] = tc.h_yq_image[kg_tc_b_offset(tc, tc.col_of[p], kg_filter_k_of_column(col))];
 	}
 	return KG_OK;
 }

@@ -1,5 +1,6 @@
 // kg_tc_state.cuh -- per-context state of the tcgen05 (int8 tensor-core) engines.
 #pragma once
+#include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
 #include <vector>
@@ -9,12 +10,18 @@ struct KgTcState {
 	bool kin_ready = false;
 	bool use_filter = false;               // auto engine: candidate density is low enough for the filter
 	std::string why_unavailable = "tensor-core engine not initialised";
-	uint64_t pair_capacity = 1ull << 22;   // candidate (row, phenotype) pairs per fetch interval
-	uint2 *d_pairs = nullptr;
+	uint32_t *d_row_list = nullptr;        // rows of the current tile the filter could not rule out
+	uint64_t row_list_cap = 0;
 	// scan filter: quantised centred phenotypes in UMMA (K-major core matrix) layout + per-phenotype constants
 	int8_t *d_yq = nullptr;
-	float2 *d_pconst = nullptr;            // [p_pad] (alpha, kappa)
-	std::vector<int8_t> h_yq_image;
+	float2 *d_gconst = nullptr;            // [p_pad / 16] per column group (min alpha, max kappa)
+	std::vector<int8_t> h_yq_image;        // B image as uploaded (columns in the current alpha order)
+	std::vector<int8_t> h_q;               // [P][n_used] quantised phenotypes, memory (phenotype-file) order
+	std::vector<uint32_t> col_of;          // [P] B / accumulator column of phenotype p
+	int8_t *h_img_pinned[2] = {nullptr, nullptr};   // pinned staging of the B image (stream-ordered re-uploads)
+	cudaEvent_t img_ev[2] = {nullptr, nullptr};
+	int img_next = 0;
+	size_t img_bytes = 0;
 	std::vector<double> scale;             // [P] quantisation step s_p
 	std::vector<float> kappa;              // [P]
 	std::vector<uint8_t> degenerate;       // [P] phenotype column the bound cannot handle: always a candidate

@@ -50,6 +50,8 @@ void run_shard(Shard &sh, const vector<vector<float> > &y, size_t min_count, siz
 			if (pattern_counter) sh.db->update_presence_absence_pattern_counter(*pattern_counter);
 			kgh_associate_rows(ctx, hp.data(), hp.size(), sh.db->loaded_rows(), sh.db->rows_loaded(), sh.db->row_offset(),
 			                   1 + sh.db->file_words(), sh.state);
+			// the batch buffer is reused by the next load_kmers: drain the round still in flight
+			kgh_associate_finish(ctx, hp.data(), hp.size(), sh.state);
 			t1 = get_time();
 			if (verbose) cerr << "Associations [" << batch_index << "]\t" << (t1 - t0) / 60. << "min" << endl;
 			t0 = get_time();

@@ -1,11 +1,12 @@
 // association_driver.cpp -- see association_driver.h.
 //
-// The batch is cut into rounds.  Each round the device reports every (row, p) whose score is
-// > heap_p.lowest_score as of the START of the round (every kept row while heap_p is not full); the
-// hits come back sorted by (phenotype, row) and are replayed through the real heaps; thresholds are
-// then refreshed.  lowest_score never decreases (best_associations_heap.cpp:43-59), so the candidate
-// set is a superset of what the sequential reference heap accepts, and a dropped row could not have
-// changed the heap (strict '>'): the heap state, ties included, is identical to the reference's.
+// The rows are cut into rounds = device hit intervals.  For each round the device reports every (row, p) whose
+// score is > heap_p.lowest_score as the host knew it when the round was submitted (every kept row while heap_p
+// is not full).  lowest_score never decreases (best_associations_heap.cpp:43-59), so a stale threshold only adds
+// candidates: the candidate set is a superset of what the sequential reference heap accepts, and a dropped row
+// could not have changed the heap (strict '>').  The candidates are grouped by phenotype, sorted by row and
+// replayed through the real heaps -- one task per phenotype, like the reference's CTPL fan-out -- which
+// reproduces the reference heap state, ties included.
 #include "association_driver.h"
 
 #include <algorithm>
@@ -14,7 +15,8 @@
 
 namespace {
 const uint64_t kSubTileRows = 1ull << 20;   // rows per device submit: the H2D copy of sub-tile i+1 overlaps the kernels of i
-const uint64_t kMaxRoundRows = 1ull << 24;  // rows between two threshold refreshes once the heaps are warm
+const uint64_t kMaxRoundRows = 1ull << 21;  // rows per round once the heaps are warm
+const uint64_t kMinWarmRound = 1ull << 16;
 const uint64_t kHitBudget = 1ull << 21;     // expected hits per round (the device buffer holds 1 << 22 by default)
 
 void check(kg_ctx *ctx, kg_status st, const char *what) {
@@ -22,16 +24,149 @@ void check(kg_ctx *ctx, kg_status st, const char *what) {
 }
 }  // namespace
 
+// ------------------------------------------------------------------------------------------ pool
+KghTaskPool::KghTaskPool(unsigned n_threads) {
+	for (unsigned i = 1; i < n_threads; i++) m_workers.emplace_back([this] { worker(); });
+}
+
+KghTaskPool::~KghTaskPool() {
+	{
+		std::lock_guard<std::mutex> lk(m_mu);
+		m_stop = true;
+	}
+	m_cv_work.notify_all();
+	for (std::thread &t : m_workers) t.join();
+}
+
+void KghTaskPool::drain() {
+	for (;;) {
+		const std::size_t i = m_next.fetch_add(1, std::memory_order_relaxed);
+		if (i >= m_n) return;
+		(*m_fn)(i);
+	}
+}
+
+void KghTaskPool::worker() {
+	uint64_t seen = 0;
+	for (;;) {
+		{
+			std::unique_lock<std::mutex> lk(m_mu);
+			m_cv_work.wait(lk, [&] { return m_stop || m_generation != seen; });
+			if (m_stop) return;
+			seen = m_generation;
+		}
+		drain();
+		{
+			std::lock_guard<std::mutex> lk(m_mu);
+			if (--m_active == 0) m_cv_done.notify_one();
+		}
+	}
+}
+
+void KghTaskPool::run(std::size_t n_tasks, const std::function<void(std::size_t)> &fn) {
+	if (n_tasks == 0) return;
+	if (m_workers.empty() || n_tasks == 1) {
+		for (std::size_t i = 0; i < n_tasks; i++) fn(i);
+		return;
+	}
+	{
+		std::lock_guard<std::mutex> lk(m_mu);
+		m_fn = &fn;
+		m_n = n_tasks;
+		m_next.store(0, std::memory_order_relaxed);
+		m_active = m_workers.size();
+		m_generation++;
+	}
+	m_cv_work.notify_all();
+	drain();
+	std::unique_lock<std::mutex> lk(m_mu);
+	m_cv_done.wait(lk, [&] { return m_active == 0; });
+	m_fn = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------ state
+AssociationDriverState::AssociationDriverState() {}
+
+AssociationDriverState::~AssociationDriverState() {
+	if (hit_buf && pinned_owner) kg_host_free(pinned_owner, hit_buf);
+	delete pool;
+}
+
+// ------------------------------------------------------------------------------------------ replay
+// Fetch the interval that is in flight and replay it.  Returns false if the device reported a hit overflow
+// (the interval was dropped; nothing was replayed).
+static bool replay_in_flight(kg_ctx *ctx, BestAssociationsHeap *const *heaps, std::size_t P, AssociationDriverState &S) {
+	if (!S.in_flight) return true;
+	std::size_t n_hits = 0;
+	uint64_t seen = 0, kept_now = 0;
+	kg_status st = kg_scan_fetch(ctx, nullptr, 0, &n_hits, &seen, &kept_now);
+	if (st == KG_ERR_HITS_OVERFLOW) {
+		S.in_flight = false;
+		return false;
+	}
+	check(ctx, st, "kg_scan_fetch");
+	if (n_hits) {
+		if (S.hit_cap < n_hits) {
+			if (S.hit_buf) kg_host_free(S.pinned_owner, S.hit_buf);
+			S.hit_buf = nullptr;
+			S.hit_cap = 0;
+			const std::size_t cap = std::max<std::size_t>(n_hits + n_hits / 2, 1u << 16);
+			void *p = nullptr;
+			check(ctx, kg_host_alloc(ctx, cap * sizeof(kg_hit), &p), "kg_host_alloc");
+			S.hit_buf = static_cast<kg_hit *>(p);
+			S.hit_cap = cap;
+			S.pinned_owner = ctx;
+		}
+		check(ctx, kg_scan_fetch(ctx, S.hit_buf, S.hit_cap, &n_hits, &seen, &kept_now), "kg_scan_fetch");
+	}
+	const uint64_t kept_round = kept_now - S.kept_seen;
+	S.kept_seen = kept_now;
+
+	// group by phenotype (counting sort), then one task per phenotype: sort by row + replay through its heap
+	S.bucket_off.assign(P + 1, 0);
+	for (std::size_t i = 0; i < n_hits; i++) S.bucket_off[S.hit_buf[i].pheno + 1]++;
+	for (std::size_t j = 0; j < P; j++) S.bucket_off[j + 1] += S.bucket_off[j];
+	S.bucketed.resize(n_hits);
+	{
+		std::vector<std::size_t> at(S.bucket_off.begin(), S.bucket_off.end() - 1);
+		for (std::size_t i = 0; i < n_hits; i++) S.bucketed[at[S.hit_buf[i].pheno]++] = S.hit_buf[i];
+	}
+	if (!S.pool) {
+		unsigned hw = std::thread::hardware_concurrency();
+		if (hw == 0) hw = 4;
+		S.pool = new KghTaskPool(std::max(1u, std::min<unsigned>(std::min<unsigned>(hw, 32u), (unsigned)P)));
+	}
+	kg_hit *const base = S.bucketed.data();
+	const std::vector<std::size_t> &off = S.bucket_off;
+	S.pool->run(P, [&](std::size_t j) {
+		kg_hit *b = base + off[j], *e = base + off[j + 1];
+		std::sort(b, e, [](const kg_hit &x, const kg_hit &y) { return x.row < y.row; });
+		heaps[j]->add_hits(b, (std::size_t)(e - b));
+		heaps[j]->note_tested_rows((std::size_t)(kept_round - (uint64_t)(e - b)));
+	});
+	if (S.log_hits) S.hit_log.insert(S.hit_log.end(), S.bucketed.begin(), S.bucketed.end());
+	S.rows_kept += kept_round;
+	S.rows_scored += S.in_flight_rows;
+	S.hits_replayed += n_hits;
+	S.d2h_bytes += (uint64_t)n_hits * sizeof(kg_hit) + 8 * sizeof(uint64_t);
+	S.rounds++;
+	S.in_flight = false;
+	S.in_flight_rows = 0;
+	return true;
+}
+
+void kgh_associate_finish(kg_ctx *ctx, BestAssociationsHeap *const *heaps, std::size_t P, AssociationDriverState &S) {
+	if (!replay_in_flight(ctx, heaps, P, S))
+		throw std::runtime_error("kgh_associate_finish: hit buffer overflow in the last round (raise KG_OPT_HIT_CAPACITY)");
+}
+
 void kgh_associate_rows(kg_ctx *ctx, BestAssociationsHeap *const *heaps, std::size_t P, const uint64_t *rows,
                         uint64_t n_rows, uint64_t first_row_id, std::size_t stride, AssociationDriverState &S) {
 	S.thr.resize(P);
-	uint64_t kept_before = 0;
-	{
-		std::size_t n_hits = 0;
-		uint64_t seen = 0;
-		check(ctx, kg_scan_fetch(ctx, nullptr, 0, &n_hits, &seen, &kept_before), "kg_scan_fetch");
-	}
 	uint64_t done = 0;
+	uint64_t shrink = 1;          // after an overflow: divide the round size
+	uint64_t flight_begin = 0;    // first row (of this call) of the interval in flight, for the overflow redo
+	bool flight_is_ours = false;  // the interval in flight holds rows of THIS call
 	while (done < n_rows) {
 		std::size_t cold = 0, need = 0;
 		uint64_t kmax = 1;
@@ -43,65 +178,61 @@ void kgh_associate_rows(kg_ctx *ctx, BestAssociationsHeap *const *heaps, std::si
 				need = std::max(need, heaps[j]->capacity() - heaps[j]->size());
 			}
 		}
+		if (cold && S.in_flight) {
+			// cold heaps take every kept row: their thresholds must be exact, so no round stays in flight
+			if (!replay_in_flight(ctx, heaps, P, S)) throw std::runtime_error("kgh_associate_rows: hit overflow while filling the heaps");
+			flight_is_ours = false;
+			continue;
+		}
 		uint64_t round;
 		if (cold) {
 			// every kept row of a cold phenotype is a hit: bound rows x cold phenotypes
 			round = std::min<uint64_t>(need + need / 4 + 64, std::max<uint64_t>(kHitBudget / cold, 1));
 		} else {
-			// warm: expected hits per phenotype ~ K * round / rows_so_far -> the round grows with the scan
-			const double per_row = (double)(P * kmax) / (double)std::max<uint64_t>(S.rows_scored, 1);
-			round = std::min<uint64_t>(std::max<uint64_t>((uint64_t)((double)kHitBudget / per_row), 4096), kMaxRoundRows);
+			// warm: expected hits per phenotype ~ K * round / rows_so_far (x2: thresholds are one round stale)
+			const double per_row = 2.0 * (double)(P * kmax) / (double)std::max<uint64_t>(S.rows_submitted, 1);
+			round = std::min<uint64_t>(std::max<uint64_t>((uint64_t)((double)kHitBudget / per_row), kMinWarmRound), kMaxRoundRows);
 		}
-		round = std::min<uint64_t>(std::max<uint64_t>(round, 1), n_rows - done);
-		std::size_t n_hits = 0;
-		uint64_t kept_now = 0;
-		for (;;) {
-			check(ctx, kg_scan_set_thresholds(ctx, S.thr.data(), (uint32_t)P), "kg_scan_set_thresholds");
-			for (uint64_t off = 0; off < round; off += kSubTileRows) {
-				const uint64_t n = std::min<uint64_t>(kSubTileRows, round - off);
-				check(ctx, kg_scan_submit(ctx, rows + (done + off) * stride, n, first_row_id + done + off), "kg_scan_submit");
-			}
-			uint64_t seen = 0;
-			const kg_status st = kg_scan_fetch(ctx, nullptr, 0, &n_hits, &seen, &kept_now);
-			if (st == KG_ERR_HITS_OVERFLOW && round > 1) {
-				round = std::max<uint64_t>(round / 4, 1);  // the library rolled its counters back
-				continue;
-			}
-			check(ctx, st, "kg_scan_fetch");
-			break;
-		}
-		S.hit_buf.resize(n_hits);
-		if (n_hits) check(ctx, kg_scan_fetch(ctx, S.hit_buf.data(), n_hits, &n_hits, nullptr, nullptr), "kg_scan_fetch");
-		check(ctx, kg_scan_clear_hits(ctx), "kg_scan_clear_hits");
-		const uint64_t kept_round = kept_now - kept_before;
-		kept_before = kept_now;
-		std::size_t i = 0;
-		for (std::size_t j = 0; j < P; j++) {  // hits are sorted by (phenotype, row)
-			std::size_t e = i;
-			while (e < n_hits && S.hit_buf[e].pheno == j) e++;
-			heaps[j]->add_hits(S.hit_buf.data() + i, e - i);
-			heaps[j]->note_tested_rows((std::size_t)(kept_round - (e - i)));
-			i = e;
-		}
-		if (S.log_hits) S.hit_log.insert(S.hit_log.end(), S.hit_buf.begin(), S.hit_buf.end());
-		S.rows_kept += kept_round;
-		S.d2h_bytes += (uint64_t)n_hits * sizeof(kg_hit) + 4 * sizeof(uint64_t);
+		round = std::max<uint64_t>(round / shrink, 1);
+		round = std::min<uint64_t>(round, n_rows - done);
+
+		check(ctx, kg_scan_set_thresholds(ctx, S.thr.data(), (uint32_t)P), "kg_scan_set_thresholds");
 		S.h2d_small_bytes += (uint64_t)P * sizeof(double);
+		for (uint64_t off = 0; off < round; off += kSubTileRows) {
+			const uint64_t n = std::min<uint64_t>(kSubTileRows, round - off);
+			check(ctx, kg_scan_submit(ctx, rows + (done + off) * stride, n, first_row_id + done + off), "kg_scan_submit");
+		}
+		// the device now works on this round; meanwhile replay the previous one
+		if (!replay_in_flight(ctx, heaps, P, S)) {
+			// overflow in the previous round: drop everything not replayed, redo from that round in smaller pieces
+			check(ctx, kg_scan_discard(ctx), "kg_scan_discard");
+			if (!flight_is_ours) throw std::runtime_error("kgh_associate_rows: hit overflow in a round of an earlier call");
+			S.rows_submitted -= done - flight_begin;
+			done = flight_begin;
+			shrink *= 4;
+			flight_is_ours = false;
+			continue;
+		}
+		check(ctx, kg_scan_mark(ctx), "kg_scan_mark");
+		S.in_flight = true;
+		S.in_flight_rows = round;
+		flight_begin = done;
+		flight_is_ours = true;
+		S.rows_submitted += round;
 		done += round;
-		S.rows_scored += round;
-		S.rounds++;
-		S.hits_replayed += n_hits;
+		if (cold) {
+			if (!replay_in_flight(ctx, heaps, P, S)) {
+				check(ctx, kg_scan_discard(ctx), "kg_scan_discard");
+				S.rows_submitted -= done - flight_begin;
+				done = flight_begin;
+				shrink *= 4;
+			}
+			flight_is_ours = false;
+		}
 	}
 }
 
-void kgh_merge_shards(std::vector<AssociationDriverState *> &shards, BestAssociationsHeap *const *final_heaps,
-                      std::size_t P) {
-	std::vector<kg_hit> all;
-	uint64_t kept = 0;
-	for (AssociationDriverState *s : shards) {
-		all.insert(all.end(), s->hit_log.begin(), s->hit_log.end());
-		kept += s->rows_kept;
-	}
+void kgh_merge_hit_log(std::vector<kg_hit> &all, uint64_t kept, BestAssociationsHeap *const *final_heaps, std::size_t P) {
 	std::sort(all.begin(), all.end(), [](const kg_hit &a, const kg_hit &b) {
 		return a.pheno != b.pheno ? a.pheno < b.pheno : a.row < b.row;
 	});
@@ -113,4 +244,15 @@ void kgh_merge_shards(std::vector<AssociationDriverState *> &shards, BestAssocia
 		final_heaps[j]->note_tested_rows((std::size_t)(kept - (e - i)));
 		i = e;
 	}
+}
+
+void kgh_merge_shards(std::vector<AssociationDriverState *> &shards, BestAssociationsHeap *const *final_heaps,
+                      std::size_t P) {
+	std::vector<kg_hit> all;
+	uint64_t kept = 0;
+	for (AssociationDriverState *s : shards) {
+		all.insert(all.end(), s->hit_log.begin(), s->hit_log.end());
+		kept += s->rows_kept;
+	}
+	kgh_merge_hit_log(all, kept, final_heaps, P);
 }

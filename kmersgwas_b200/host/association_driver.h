@@ -1,33 +1,86 @@
 // association_driver.h -- the batch loop of associate_kmers (reference associate_kmers.cpp:123-148)
 // over the C ABI: device candidates -> exact replay through BestAssociationsHeap.
 // Used by MultipleKmersDataBases::add_kmers_to_heaps, the CLI and the C API for bench / tests.
+//
+// The reference fans one CTPL task per phenotype out over a loaded batch (associate_kmers.cpp:134-141) and joins
+// them before loading the next batch.  Here the device scores all phenotypes of a round of rows at once, and
+// the host keeps the same per-phenotype task structure for the part that stays on the CPU -- replaying the
+// device's candidate hits through the P independent heaps on a small thread pool -- while the device already
+// scans the next round (one hit interval in flight, kg_scan_mark / kg_scan_fetch).
 #ifndef KGH_ASSOCIATION_DRIVER_H
 #define KGH_ASSOCIATION_DRIVER_H
 
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "best_associations_heap.h"
 #include "kmersgwas_b200.h"
 
+// Minimal fork-join pool: run(n, fn) calls fn(i) for i in [0, n) on the workers and the calling thread.
+class KghTaskPool {
+	public:
+		explicit KghTaskPool(unsigned n_threads);
+		~KghTaskPool();
+		KghTaskPool(const KghTaskPool &) = delete;
+		KghTaskPool &operator=(const KghTaskPool &) = delete;
+		void run(std::size_t n_tasks, const std::function<void(std::size_t)> &fn);
+		unsigned threads() const { return (unsigned)m_workers.size() + 1; }
+	private:
+		void worker();
+		void drain();
+		std::vector<std::thread> m_workers;
+		std::mutex m_mu;
+		std::condition_variable m_cv_work, m_cv_done;
+		const std::function<void(std::size_t)> *m_fn = nullptr;
+		std::size_t m_n = 0;
+		std::atomic<std::size_t> m_next{0};
+		std::size_t m_active = 0;
+		uint64_t m_generation = 0;
+		bool m_stop = false;
+};
+
 struct AssociationDriverState {
-	uint64_t rows_scored = 0;        // rows scored since the phenotypes were set on the context
-	uint64_t rounds = 0;             // threshold refreshes so far
+	AssociationDriverState();
+	~AssociationDriverState();
+	AssociationDriverState(const AssociationDriverState &) = delete;
+	AssociationDriverState &operator=(const AssociationDriverState &) = delete;
+
+	uint64_t rows_scored = 0;        // rows whose hits have been replayed
+	uint64_t rows_submitted = 0;     // rows handed to the device since the phenotypes were set
+	uint64_t rounds = 0;             // hit intervals so far
 	uint64_t hits_replayed = 0;      // candidates replayed through the heaps
-	std::vector<kg_hit> hit_buf;
+	uint64_t rows_kept = 0;          // rows that passed the MAC filter (replayed intervals)
+	uint64_t d2h_bytes = 0;          // hits + counters copied back from the device
+	uint64_t h2d_small_bytes = 0;    // thresholds sent to the device (the tiles themselves are counted by the caller)
 	std::vector<double> thr;
 	// Multi-GPU shards: keep every replayed candidate so that the shards' logs can be merged and
 	// replayed once more, in global row order, through the final heaps (kgh_merge_shards).
 	bool log_hits = false;
 	std::vector<kg_hit> hit_log;
-	uint64_t rows_kept = 0;          // rows that passed the MAC filter (all rounds)
-	uint64_t d2h_bytes = 0;          // hits + counters copied back from the device
-	uint64_t h2d_small_bytes = 0;    // thresholds sent to the device (the tiles themselves are counted by the caller)
+
+	// ---- pipeline state
+	bool in_flight = false;          // the open device interval holds submitted rows whose hits are not replayed yet
+	uint64_t in_flight_rows = 0;
+	uint64_t kept_seen = 0;          // rows_kept total reported by the last fetch
+	kg_ctx *pinned_owner = nullptr;
+	kg_hit *hit_buf = nullptr;       // pinned (kg_host_alloc)
+	std::size_t hit_cap = 0;
+	std::vector<kg_hit> bucketed;    // hits of the current interval grouped by phenotype
+	std::vector<std::size_t> bucket_off;
+	KghTaskPool *pool = nullptr;
 };
 
 // Score rows [0, n_rows) (raw .table rows, host or device memory) against the phenotypes already set
 // on ctx, feeding heaps[p].  Row ids = first_row_id + index.  Throws std::runtime_error on ABI errors.
+// On return the LAST round may still be in flight on the device (its hits not yet in the heaps): call
+// kgh_associate_finish before reading the heaps.  Host rows must stay valid until then.
 void kgh_associate_rows(kg_ctx *ctx, BestAssociationsHeap *const *heaps, std::size_t n_heaps, const uint64_t *rows,
                         uint64_t n_rows, uint64_t first_row_id, std::size_t stride_words, AssociationDriverState &state);
+void kgh_associate_finish(kg_ctx *ctx, BestAssociationsHeap *const *heaps, std::size_t n_heaps, AssociationDriverState &state);
 
 // Exact merge of row-sharded scans.  Each shard ran kgh_associate_rows on its own
 // contiguous row block with log_hits = true and its own (local) heaps.  A shard's local threshold is
@@ -37,5 +90,8 @@ void kgh_associate_rows(kg_ctx *ctx, BestAssociationsHeap *const *heaps, std::si
 // included; rows_kept sums to the reference's number_of_insertion().
 void kgh_merge_shards(std::vector<AssociationDriverState *> &shards, BestAssociationsHeap *const *final_heaps,
                       std::size_t n_heaps);
+// Same for already concatenated logs (any order).
+void kgh_merge_hit_log(std::vector<kg_hit> &all, uint64_t rows_kept, BestAssociationsHeap *const *final_heaps,
+                       std::size_t n_heaps);
 
 #endif

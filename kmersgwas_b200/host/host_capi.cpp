@@ -53,6 +53,8 @@ kgh_session *kgh_session_create(int device, uint64_t n_file, uint64_t n_used, co
 	return s.release();
 }
 
+// The last round of the call may stay in flight on the device (its hits are replayed by the next call or by
+// kgh_session_finish); host rows must stay valid until then.  Every accessor below finishes first.
 int kgh_session_associate(kgh_session *s, const uint64_t *rows, uint64_t n_rows, uint64_t first_row_id) {
 	try {
 		kgh_associate_rows(s->ctx, s->hp.data(), s->hp.size(), rows, n_rows, first_row_id, s->stride, s->state);
@@ -63,12 +65,23 @@ int kgh_session_associate(kgh_session *s, const uint64_t *rows, uint64_t n_rows,
 	}
 }
 
+int kgh_session_finish(kgh_session *s) {
+	try {
+		kgh_associate_finish(s->ctx, s->hp.data(), s->hp.size(), s->state);
+		return 0;
+	} catch (const std::exception &e) {
+		g_err = e.what();
+		return 1;
+	}
+}
+
 void *kgh_session_ctx(kgh_session *s) { return s->ctx; }
-uint64_t kgh_session_heap_size(kgh_session *s, uint32_t p) { return s->heaps[p].size(); }
-uint64_t kgh_session_tested(kgh_session *s, uint32_t p) { return s->heaps[p].number_of_insertion(); }
-double kgh_session_threshold(kgh_session *s, uint32_t p) { return s->heaps[p].device_threshold(); }
+uint64_t kgh_session_heap_size(kgh_session *s, uint32_t p) { kgh_session_finish(s); return s->heaps[p].size(); }
+uint64_t kgh_session_tested(kgh_session *s, uint32_t p) { kgh_session_finish(s); return s->heaps[p].number_of_insertion(); }
+double kgh_session_threshold(kgh_session *s, uint32_t p) { kgh_session_finish(s); return s->heaps[p].device_threshold(); }
 
 void kgh_session_heap_dump(kgh_session *s, uint32_t p, uint64_t *kmers, double *scores, uint64_t *rows) {
+	kgh_session_finish(s);
 	const std::vector<AssociationScoreHeap> e = s->heaps[p].entries_in_pop_order();
 	for (std::size_t i = 0; i < e.size(); i++) {
 		kmers[i] = std::get<0>(e[i]);
@@ -78,6 +91,7 @@ void kgh_session_heap_dump(kgh_session *s, uint32_t p, uint64_t *kmers, double *
 }
 
 void kgh_session_stats(kgh_session *s, uint64_t *rounds, uint64_t *hits_replayed, uint64_t *rows_scored, uint64_t *rows_kept) {
+	kgh_session_finish(s);
 	if (rounds) *rounds = s->state.rounds;
 	if (hits_replayed) *hits_replayed = s->state.hits_replayed;
 	if (rows_scored) *rows_scored = s->state.rows_scored;
@@ -91,7 +105,7 @@ void kgh_session_io_bytes(kgh_session *s, uint64_t *h2d_small, uint64_t *d2h) {
 
 // Multi-shard merge: replay the shards' hit logs, in global row order, into shard 0's heaps
 // (which are reset first).  Used by the world_size > 1 tests and the multi-GPU bench.
-uint64_t kgh_session_log_size(kgh_session *s) { return s->state.hit_log.size(); }
+uint64_t kgh_session_log_size(kgh_session *s) { kgh_session_finish(s); return s->state.hit_log.size(); }
 void kgh_session_log_copy(kgh_session *s, kg_hit *out) {
 	if (!s->state.hit_log.empty()) memcpy(out, s->state.hit_log.data(), s->state.hit_log.size() * sizeof(kg_hit));
 }
@@ -108,13 +122,10 @@ kgh_heapset *kgh_heapset_create(const uint64_t *kbest, uint32_t n_pheno) {
 void kgh_heapset_destroy(kgh_heapset *h) { delete h; }
 // hits: concatenated shard logs (any order); rows_kept: total kept rows over all shards
 void kgh_heapset_merge(kgh_heapset *h, const kg_hit *hits, uint64_t n_hits, uint64_t rows_kept) {
-	AssociationDriverState st;
-	st.hit_log.assign(hits, hits + n_hits);
-	st.rows_kept = rows_kept;
-	std::vector<AssociationDriverState *> shards(1, &st);
+	std::vector<kg_hit> all(hits, hits + n_hits);
 	std::vector<BestAssociationsHeap *> hp;
 	for (auto &x : h->heaps) hp.push_back(&x);
-	kgh_merge_shards(shards, hp.data(), hp.size());
+	kgh_merge_hit_log(all, rows_kept, hp.data(), hp.size());
 }
 uint64_t kgh_heapset_size(kgh_heapset *h, uint32_t p) { return h->heaps[p].size(); }
 uint64_t kgh_heapset_tested(kgh_heapset *h, uint32_t p) { return h->heaps[p].number_of_insertion(); }

@@ -154,6 +154,8 @@ void MultipleKmersDataBases::ensure_phenotypes(const vector<vector<float> > &sco
 	m_pheno_flat.swap(flat);
 	m_pheno_min_cnt = min_cnt;
 	m_driver.rows_scored = 0;
+	m_driver.rows_submitted = 0;
+	m_driver.kept_seen = 0;
 }
 
 void MultipleKmersDataBases::add_kmers_to_heap(BestAssociationsHeap &heap, vector<float> scores, const size_t &min_cnt) const {
@@ -163,6 +165,7 @@ void MultipleKmersDataBases::add_kmers_to_heap(BestAssociationsHeap &heap, vecto
 	ensure_phenotypes(vector<vector<float> >(1, scores), min_cnt);
 	BestAssociationsHeap *hp = &heap;
 	kgh_associate_rows(m_ctx, &hp, 1, m_batch, m_rows_loaded, m_row_offset, 1 + m_hash_words_db_file, m_driver);
+	kgh_associate_finish(m_ctx, &hp, 1, m_driver);
 }
 
 // All phenotypes of the loaded batch in one device pass (reference loop body associate_kmers.cpp:134-141
@@ -176,6 +179,7 @@ void MultipleKmersDataBases::add_kmers_to_heaps(vector<BestAssociationsHeap> &he
 	vector<BestAssociationsHeap *> hp(heaps.size());
 	for (size_t j = 0; j < heaps.size(); j++) hp[j] = &heaps[j];
 	kgh_associate_rows(m_ctx, hp.data(), hp.size(), m_batch, m_rows_loaded, m_row_offset, 1 + m_hash_words_db_file, m_driver);
+	kgh_associate_finish(m_ctx, hp.data(), hp.size(), m_driver);
 }
 
 // ---- kinship ---------------------------------------------------------------------------------------
