@@ -253,8 +253,13 @@ def our_arm(args):
     resident = min(W + K, max(2, int(free_b * 0.6) // (R * row_bytes)))
     bufs = [torch.empty(R * stride, dtype=torch.int64, device="cuda") for _ in range(resident)]
 
+    # Scan position.  The timed steps should look like the bulk of the 2.3e9-row job, not like its first 2 %
+    # (where the heaps have seen few rows, thresholds are low and most of the time goes into exact re-scoring of
+    # candidates): --prefill-rows rows per GPU are scanned first, untimed, through the same associate loop.
+    prefill_steps = (args.prefill_rows + R - 1) // R
+
     def first_row(step):
-        return (step * world + rank) * R
+        return ((prefill_steps + step) * world + rank) * R
 
     def fill(buf, step):
         st = abi.kg_synth_rows_device(h, SEED_TABLE, first_row(step), R, buf.data_ptr())
@@ -262,6 +267,14 @@ def our_arm(args):
 
     launches0 = None
     with torch.cuda.stream(stream):
+        t_pre0 = time.perf_counter()
+        for ps in range(prefill_steps):
+            b = bufs[ps % 2]
+            st = abi.kg_synth_rows_device(h, SEED_TABLE, (ps * world + rank) * R, R, b.data_ptr())
+            assert st == 0, abi.kg_last_error(h)
+            sess.associate(b.data_ptr(), R, (ps * world + rank) * R)   # refills of b are stream-ordered behind its scan
+        sess.finish()
+        prefill_s = time.perf_counter() - t_pre0
         for s in range(min(resident, W + K)):
             fill(bufs[s], s)
         stream.synchronize()
@@ -301,6 +314,9 @@ def our_arm(args):
             fill(bufs[0], W + K + i)
             stream.synchronize()
             host[i].copy_(bufs[0])
+        for i in range(min(2, n_e2e)):   # untimed: first touch of the pinned buffers by the DMA engine
+            sess.associate(host[i].data_ptr(), R, first_row(W + K + i))
+        sess.finish()
         torch.cuda.synchronize()
         io2 = sess.io_bytes()
         ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -370,6 +386,9 @@ def our_arm(args):
                 "workload": f"BASELINE configs[1] shape: {n} samples x {p} phenotypes (1 + {p - 1} permutations), best K={args.kbest}, "
                             f"maf {MAF}/mac {MAC}; step = one {R}-row batch ({R * row_bytes / 1e6:.0f} MB, > 126 MB L2) per GPU through the "
                             f"associate loop; every step scans new rows, heaps carry over (full table = {2.3e9 / R:.0f} such steps streamed)",
+                "scan_position": f"timed steps cover rows [{(prefill_steps + W) * R * world}, {(prefill_steps + W + K) * R * world}) of the job: "
+                                 f"{prefill_steps * R} rows per GPU were scanned untimed first ({prefill_s:.1f} s) so that heap thresholds "
+                                 f"are those of the bulk of the 2.3e9-row scan; --prefill-rows 0 times the cold start instead",
                 "rows_per_step_per_gpu": R, "row_bytes": row_bytes, "l2": "inputs larger than L2, each step reads a different batch",
                 "scan_engine": args.scan_engine, "parallelism": f"k-mer-block shards x{world}, no data-path collective",
                 "hits_replayed_per_step": (stats1["hits_replayed"] - stats0["hits_replayed"]) / K,
@@ -492,6 +511,7 @@ def main():
     ap.add_argument("--kinship-engine", type=int, default=0)
     ap.add_argument("--kinship-rows", type=int, default=1 << 20)
     ap.add_argument("--e2e-buffers", type=int, default=3)
+    ap.add_argument("--prefill-rows", type=int, default=1 << 28, help="rows per GPU scanned untimed before the warm-up steps")
     ap.add_argument("--cpu-rows", type=int, default=400000, help="rows of the cpu_baseline sample")
     ap.add_argument("--ref-rows", type=int, default=200000, help="rows per step of --impl reference")
     ap.add_argument("--warmup-ref", type=int, default=1)

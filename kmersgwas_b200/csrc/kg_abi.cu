@@ -64,7 +64,7 @@ struct kg_ctx {
 	uint64_t rows_seen_total = 0, kept_total = 0;   // over consumed intervals
 	cudaStream_t d2h_stream = nullptr;
 	// pinned staging ring for stream-ordered threshold updates (no host sync)
-	struct ThrStage { double *h_thr = nullptr; float2 *h_gc = nullptr; cudaEvent_t ev = nullptr; } thr_stage[4];
+	struct ThrStage { double *h_thr = nullptr; struct KgFilterGroupConst *h_gc = nullptr; cudaEvent_t ev = nullptr; } thr_stage[4];
 	int thr_next = 0;
 	size_t thr_stage_p = 0, thr_stage_g = 0;
 
@@ -543,7 +543,7 @@ extern "C" kg_status kg_scan_set_phenotypes(kg_ctx *c, const float *y, uint32_t 
 		c->thr_stage[i].h_thr = nullptr;
 		c->thr_stage[i].h_gc = nullptr;
 		KG_CUDA(c, cudaMallocHost((void **)&c->thr_stage[i].h_thr, (size_t)c->p_alloc * sizeof(double)));
-		KG_CUDA(c, cudaMallocHost((void **)&c->thr_stage[i].h_gc, 32 * sizeof(float2)));
+		KG_CUDA(c, cudaMallocHost((void **)&c->thr_stage[i].h_gc, 16 * 48));
 	}
 	kg_status st = kg_tc_prepare_scan(c);
 	return st;

@@ -81,6 +81,10 @@ __device__ __forceinline__ void kg_pred_add(float (&acc)[PT], const float (&y)[P
 	}
 }
 
+#ifndef KG_EXACT_UNROLL
+#define KG_EXACT_UNROLL 4
+#endif
+
 template <int PT>
 __host__ __device__ constexpr int kg_ys_group_stride() { return 32 * PT + 4; }
 
@@ -147,21 +151,28 @@ __global__ void __launch_bounds__(256) kg_scan_exact_kernel(const KgScanParams p
 				n1[r] += __popc(w[r]);
 			}
 			const float *yg = ys + g * GS;
+			// 32 steps in groups of KG_EXACT_UNROLL: the fully unrolled body (2 k+ FADDs) overflowed the
+			// instruction caches (ncu: "no_instruction" was the top stall); a short body stays resident
+#pragma unroll 1
+			for (int t0 = 0; t0 < 32; t0 += KG_EXACT_UNROLL) {
+				const uint32_t m0 = 0x80000000u >> t0;
 #pragma unroll
-			for (int t = 0; t < 32; t++) {
-				float yv[PT];
-				if constexpr (PT >= 4) {
+				for (int k = 0; k < KG_EXACT_UNROLL; k++) {
+					const int t = t0 + k;
+					float yv[PT];
+					if constexpr (PT >= 4) {
 #pragma unroll
-					for (int q = 0; q < PT; q += 4) {
-						const float4 f = *reinterpret_cast<const float4 *>(yg + t * PT + q);
-						yv[q] = f.x; yv[q + 1] = f.y; yv[q + 2] = f.z; yv[q + 3] = f.w;
+						for (int q = 0; q < PT; q += 4) {
+							const float4 f = *reinterpret_cast<const float4 *>(yg + t * PT + q);
+							yv[q] = f.x; yv[q + 1] = f.y; yv[q + 2] = f.z; yv[q + 3] = f.w;
+						}
+					} else {
+#pragma unroll
+						for (int q = 0; q < PT; q++) yv[q] = yg[t * PT + q];
 					}
-				} else {
 #pragma unroll
-					for (int q = 0; q < PT; q++) yv[q] = yg[t * PT + q];
+					for (int r = 0; r < R; r++) kg_pred_add<PT>(acc[r], yv, w[r] & (m0 >> k));
 				}
-#pragma unroll
-				for (int r = 0; r < R; r++) kg_pred_add<PT>(acc[r], yv, w[r] & (0x80000000u >> t));
 			}
 		}
 		// ---- epilogue: N1 over the 4 lanes of the row, MAC filter, lane combine, double score

@@ -13,8 +13,9 @@
 //   gamma = float32 error of the reference's lane sums.
 // Per row (bits S, N1 = |S|, m = min(N1, N - N1), den = N1 (N - N1)) the tensor core gives the EXACT integer
 //   Q = sum_{i in S} q_i, and
-//   |r_ref| <= N s ( |Q| + m/2 + kappa ),      kappa = (|e_tot| + gamma A + |N ybar - sum_ref|) / s + 1
-//   score_ref = r_ref^2 / den > thr   ==>   |Q| >= alpha sqrt(den) - m/2 - kappa,   alpha = sqrt(thr) / (N s)
+//   |r_ref| <= N s ( |Q| + F(m) + kappa ),      kappa = (|e_tot| + gamma A + |N ybar - sum_ref|) / s + 1
+//   F(m) = largest possible |sum of e_i / s| over m samples = max(sum of the m largest positive, m largest negative
+//   errors) <= m / 2;  score_ref = r_ref^2 / den > thr  ==>  |Q| >= alpha sqrt(den) - F(m) - kappa, alpha = sqrt(thr)/(N s)
 // with alpha rounded down and sqrt(den) rounded down, so no qualifying pair is ever dropped.
 // The phenotype columns are sorted by alpha and tested 16 at a time: max |Q| of the group against the group's
 // smallest alpha and largest kappa.  A row with no surviving group is ruled out for every phenotype.
@@ -44,6 +45,17 @@
 #define KG_F_THREADS ((KG_F_EPI_WARP0 + 4) * 32)
 #define KG_F_ONE 128             // value of a set presence bit in the u8 A operand (0x80)
 
+// Per 16-column group: the loosest bound of its phenotype columns, in accumulator units (x KG_F_ONE).
+//   a row is ruled out for the group iff  max |Q| < alpha * sqrt(den) - kappa - slack(m),
+//   slack(m) = min_k (line_a[k] + line_b[k] * m)  >=  max over the group's phenotypes of the largest possible
+//   |sum of rounding errors| over any m samples (sorted-prefix sums of the positive / negative errors; the lines
+//   are upper tangents of that table, see kg_tc.cuh).
+struct KgFilterGroupConst {
+	float alpha, kappa;
+	float line_a[4], line_b[4];
+	float pad_[2];
+};
+
 struct KgFilterParams {
 	const uint64_t *rows;      // raw tile, 16-byte aligned
 	uint64_t n_rows;
@@ -55,8 +67,7 @@ struct KgFilterParams {
 	const int8_t *yq_image;    // B operand in its shared-memory byte order, b_bytes long
 	uint32_t b_bytes;          // (p_pad / 8) * sbo_b
 	uint32_t sbo_b;            // nc * 1024
-	const float2 *gconst;      // [p_pad / 16] per 16-column group: (min alpha, max kappa) over its phenotype columns, in
-	                           // accumulator units (x KG_F_ONE); groups without phenotype columns hold (+inf, 0)
+	const KgFilterGroupConst *gconst;   // [p_pad / 16]; groups without phenotype columns hold alpha = +inf
 	uint32_t n_used, min_count;
 	uint32_t *row_list;        // out: rows of the tile (index inside the tile) that could not be ruled out, any order
 	unsigned long long *n_listed;   // device counter for row_list (zeroed before the launch); capacity = n_rows
@@ -67,7 +78,7 @@ struct KgFilterParams {
 __host__ __device__ inline uint32_t kg_filter_raw_stage_bytes(uint32_t w_file) { return KG_F_ROWS * 8u * (w_file + 1); }
 __host__ __device__ inline size_t kg_filter_smem_bytes(uint32_t w_file, uint32_t b_bytes, uint32_t p_pad) {
 	return 1024 /*alignment slack*/ + (size_t)b_bytes + (size_t)KG_F_A_STAGES * KG_F_A_STAGE_BYTES +
-	       (size_t)KG_F_RAW_STAGES * kg_filter_raw_stage_bytes(w_file) + (size_t)(p_pad / 16) * 8 + 256;
+	       (size_t)KG_F_RAW_STAGES * kg_filter_raw_stage_bytes(w_file) + (size_t)(p_pad / 16) * sizeof(KgFilterGroupConst) + 256;
 }
 // K index (byte inside the A / B operands) of file column `col`: the expander's 64-bit multiply leaves bit i of
 // every presence byte in output byte 7 - i, so B is stored with the same permutation.
@@ -85,6 +96,14 @@ __device__ __forceinline__ void kg_expand_u32(uint32_t w, uint32_t smem_dst) {
 	asm volatile("st.shared.v2.b64 [%0], {%1,%2};" ::"r"(smem_dst + 128), "l"(c), "l"(d) : "memory");
 }
 
+// alpha * g - kappa - slack(m), every step rounded towards -inf (a lower threshold only lists more rows)
+__device__ __forceinline__ float kg_filter_group_threshold(const KgFilterGroupConst &gc, float g, float m) {
+	float slack = __fmaf_ru(gc.line_b[0], m, gc.line_a[0]);
+#pragma unroll
+	for (int k = 1; k < 4; k++) slack = fminf(slack, __fmaf_ru(gc.line_b[k], m, gc.line_a[k]));
+	return __fsub_rd(__fmaf_rd(gc.alpha, g, -gc.kappa), slack);
+}
+
 template <int MODE>  // 0 = list candidate rows, 1 = debug: dump accumulators
 __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const KgFilterParams prm) {
 	extern __shared__ uint8_t kg_f_smem_raw[];
@@ -94,7 +113,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 	uint8_t *sA = sB + prm.b_bytes;
 	const uint32_t raw_stage_bytes = kg_filter_raw_stage_bytes(prm.w_file);
 	uint8_t *sRaw = sA + KG_F_A_STAGES * KG_F_A_STAGE_BYTES;
-	float2 *sConst = reinterpret_cast<float2 *>(sRaw + KG_F_RAW_STAGES * raw_stage_bytes);
+	KgFilterGroupConst *sConst = reinterpret_cast<KgFilterGroupConst *>(sRaw + KG_F_RAW_STAGES * raw_stage_bytes);
 	uint64_t *bars = reinterpret_cast<uint64_t *>(sConst + prm.p_pad / 16);
 	uint64_t *raw_full = bars, *raw_empty = bars + KG_F_RAW_STAGES;
 	uint64_t *a_full = bars + 2 * KG_F_RAW_STAGES, *a_empty = a_full + KG_F_A_STAGES;
@@ -237,7 +256,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 						n1 = v[0] / KG_F_ONE;
 						v[0] = 0;
 						const float n1f = (float)n1, n0f = Nf - n1f;
-						hm = (0.5f * KG_F_ONE) * fminf(n1f, n0f);
+						hm = fminf(n1f, n0f);                              // m = size of the smaller group
 						g = __fmul_rd(__fsqrt_rd(n1f * n0f), 0.999999f);   // <= sqrt(den); den is exact in fp32 (< 2^24)
 					}
 					{
@@ -247,8 +266,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 							mx = __vimax3_s32(mx, (int)v[j], (int)v[j + 1]);
 							mn = __vimin3_s32(mn, (int)v[j], (int)v[j + 1]);
 						}
-						const float2 gc = sConst[c0 >> 4];
-						maybe |= !((float)max(mx, -mn) < __fsub_rd(__fmaf_rd(gc.x, g, -gc.y), hm));
+						maybe |= !((float)max(mx, -mn) < kg_filter_group_threshold(sConst[c0 >> 4], g, hm));
 					}
 					if (second) {
 						int mx = 0, mn = 0;
@@ -257,8 +275,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 							mx = __vimax3_s32(mx, (int)u[j], (int)u[j + 1]);
 							mn = __vimin3_s32(mn, (int)u[j], (int)u[j + 1]);
 						}
-						const float2 gc = sConst[(c0 >> 4) + 1];
-						maybe |= !((float)max(mx, -mn) < __fsub_rd(__fmaf_rd(gc.x, g, -gc.y), hm));
+						maybe |= !((float)max(mx, -mn) < kg_filter_group_threshold(sConst[(c0 >> 4) + 1], g, hm));
 					}
 				}
 				// accumulators are in registers: hand the TMEM buffer back to the MMA warp before the row test

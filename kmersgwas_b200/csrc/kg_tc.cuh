@@ -45,7 +45,7 @@ static float kg_float_up(double x) {  // smallest float >= x
 
 // Column order + per-group (alpha, kappa) from the current thresholds, and the B image in that order
 // (see kg_scan_filter.cuh header).  Column 0 = all-ones (popcount); phenotypes follow sorted by alpha.
-static kg_status kg_tc_update_thresholds(kg_ctx *c, float2 *gc_pinned) {
+static kg_status kg_tc_update_thresholds(kg_ctx *c, KgFilterGroupConst *gc_pinned) {
 	KgTcState &tc = c->tc;
 	if (!tc.scan_ready) return KG_OK;
 	const uint32_t P = c->n_pheno, N = (uint32_t)c->n_used;
@@ -78,13 +78,48 @@ static kg_status kg_tc_update_thresholds(kg_ctx *c, float2 *gc_pinned) {
 	// keep the uploaded column order while it is within 1 % of the sorted one (thresholds drift together)
 	const bool reorder = tc.col_of.size() != P || tightness(col_of) > 1.01 * tightness(tc.col_of);
 	if (!reorder) col_of = tc.col_of;
-	if (n_groups > 32) KG_FAIL(c, KG_ERR_STATE, "filter group constants exceed the staging slot");
-	float2 *gc = gc_pinned;
-	for (uint32_t g = 0; g < n_groups; g++) gc[g] = make_float2(INFINITY, 0.0f);
+	if (n_groups > 16) KG_FAIL(c, KG_ERR_STATE, "filter group constants exceed the staging slot");
+	if (reorder) {
+		// slack lines of every group for the new column assignment: upper tangents of
+		// U_g(m) = max over the group's phenotypes of F_p(m), m in [0, N/2]  (F_p: kg_tc_prepare_scan)
+		const uint32_t M = N / 2;
+		tc.group_lines.assign((size_t)n_groups * 8, 0.0f);
+		std::vector<double> U(M + 1);
+		for (uint32_t g = 0; g < n_groups; g++) {
+			std::fill(U.begin(), U.end(), 0.0);
+			bool any = false;
+			for (uint32_t p = 0; p < P; p++) {
+				if (col_of[p] / 16 != g || tc.degenerate[p]) continue;
+				any = true;
+				const float *F = tc.slack_table.data() + (size_t)p * (M + 1);
+				for (uint32_t m = 0; m <= M; m++) U[m] = std::max(U[m], (double)F[m]);
+			}
+			if (!any) continue;
+			const uint32_t anchor[4] = {std::max(1u, M / 16), std::max(1u, M / 5), std::max(1u, M / 2), std::max(1u, M - 1)};
+			for (int k = 0; k < 4; k++) {
+				const uint32_t m0 = std::min(anchor[k], M > 0 ? M - 1 : 0);
+				const double slope = M > 0 ? std::max(0.0, U[std::min(m0 + 1, M)] - U[m0]) : 0.0;
+				double icpt = 0.0;
+				for (uint32_t m = 0; m <= M; m++) icpt = std::max(icpt, U[m] - slope * (double)m);
+				tc.group_lines[(size_t)g * 8 + k] = kg_float_up(icpt * (1.0 + 1e-6) * KG_F_ONE);
+				tc.group_lines[(size_t)g * 8 + 4 + k] = kg_float_up(slope * (1.0 + 1e-6) * KG_F_ONE);
+			}
+		}
+	}
+	KgFilterGroupConst *gc = gc_pinned;
+	for (uint32_t g = 0; g < n_groups; g++) {
+		gc[g].alpha = INFINITY;
+		gc[g].kappa = 0.0f;
+		for (int k = 0; k < 4; k++) {
+			gc[g].line_a[k] = tc.group_lines[(size_t)g * 8 + k];
+			gc[g].line_b[k] = tc.group_lines[(size_t)g * 8 + 4 + k];
+		}
+		gc[g].pad_[0] = gc[g].pad_[1] = 0.0f;
+	}
 	for (uint32_t p = 0; p < P; p++) {
-		float2 &g = gc[col_of[p] / 16];
-		g.x = std::min(g.x, alpha[p]);
-		g.y = std::max(g.y, kappa[p]);
+		KgFilterGroupConst &g = gc[col_of[p] / 16];
+		g.alpha = std::min(g.alpha, alpha[p]);
+		g.kappa = std::max(g.kappa, kappa[p]);
 	}
 	if (reorder) {
 		// pinned image ring: the copy is stream-ordered behind the kernels still reading the old image
@@ -112,7 +147,7 @@ static kg_status kg_tc_update_thresholds(kg_ctx *c, float2 *gc_pinned) {
 		KG_CUDA(c, cudaMemcpyAsync(tc.d_yq, img, tc.b_bytes, cudaMemcpyHostToDevice, c->stream));
 		KG_CUDA(c, cudaEventRecord(tc.img_ev[slot], c->stream));
 	}
-	KG_CUDA(c, cudaMemcpyAsync(tc.d_gconst, gc, n_groups * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+	KG_CUDA(c, cudaMemcpyAsync(tc.d_gconst, gc, n_groups * sizeof(KgFilterGroupConst), cudaMemcpyHostToDevice, c->stream));
 	return KG_OK;
 }
 
@@ -151,6 +186,10 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	tc.degenerate.assign(P, 0);
 	const double gamma = (double)(c->nb * 32 + 3) * ldexp(1.0, -24) * 1.001;  // fp32 lane-sum error of the reference
 	std::vector<double> cen(N);
+	// F_p(m), m = 0 .. N/2: the largest |sum of e_i / s| any m samples can have
+	const uint32_t Mhalf = N / 2;
+	tc.slack_table.assign((size_t)P * (Mhalf + 1), 0.0f);
+	std::vector<double> epos, eneg;
 	for (uint32_t p = 0; p < P; p++) {
 		const float *y = c->h_y.data() + (size_t)p * N;
 		const double sum_ref = (double)c->h_sums[p];
@@ -168,11 +207,26 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 		if (bad || !(s > 1e-30)) { tc.degenerate[p] = 1; continue; }
 		double e_tot = 0.0;
 		int8_t *qrow = tc.h_q.data() + (size_t)p * N;
+		epos.clear();
+		eneg.clear();
 		for (uint32_t i = 0; i < N; i++) {
 			double q = std::nearbyint(cen[i] / s);
 			q = std::max(-127.0, std::min(127.0, q));
-			e_tot += cen[i] - s * q;
+			const double e = cen[i] - s * q;
+			e_tot += e;
 			qrow[i] = (int8_t)q;
+			if (e > 0) epos.push_back(e / s); else if (e < 0) eneg.push_back(-e / s);
+		}
+		{
+			std::sort(epos.begin(), epos.end(), std::greater<double>());
+			std::sort(eneg.begin(), eneg.end(), std::greater<double>());
+			float *F = tc.slack_table.data() + (size_t)p * (Mhalf + 1);
+			double sp = 0.0, sn = 0.0;
+			for (uint32_t m = 1; m <= Mhalf; m++) {
+				if (m <= epos.size()) sp += epos[m - 1];
+				if (m <= eneg.size()) sn += eneg[m - 1];
+				F[m] = kg_float_up(std::max(sp, sn) * (1.0 + 1e-9) + 1e-9 * (double)m);  // + double rounding of e_i
+			}
 		}
 		const double t = std::fabs((double)N * ybar - sum_ref);
 		// + 1e-9 A: double rounding in the centring; + 1: float32 evaluation slack of the device-side test
@@ -187,7 +241,7 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	}
 	cudaError_t e = cudaMalloc((void **)&tc.d_yq, tc.b_bytes);
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc quantised phenotypes: %s", cudaGetErrorString(e));
-	e = cudaMalloc((void **)&tc.d_gconst, (tc.p_pad / 16) * sizeof(float2));
+	e = cudaMalloc((void **)&tc.d_gconst, (tc.p_pad / 16) * sizeof(KgFilterGroupConst));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc filter constants: %s", cudaGetErrorString(e));
 	KG_CUDA(c, cudaFuncSetAttribute(kg_scan_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	KG_CUDA(c, cudaFuncSetAttribute(kg_scan_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

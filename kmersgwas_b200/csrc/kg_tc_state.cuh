@@ -14,7 +14,9 @@ struct KgTcState {
 	uint64_t row_list_cap = 0;
 	// scan filter: quantised centred phenotypes in UMMA (K-major core matrix) layout + per-phenotype constants
 	int8_t *d_yq = nullptr;
-	float2 *d_gconst = nullptr;            // [p_pad / 16] per column group (min alpha, max kappa)
+	struct KgFilterGroupConst *d_gconst = nullptr;   // [p_pad / 16] per column group, see kg_scan_filter.cuh
+	std::vector<float> slack_table;        // [P][N/2 + 1] F_p(m): largest |sum of rounding errors / s| over m samples
+	std::vector<float> group_lines;        // [p_pad / 16][8] upper tangents (4 intercepts, 4 slopes) of max_p F_p per group
 	std::vector<int8_t> h_yq_image;        // B image as uploaded (columns in the current alpha order)
 	std::vector<int8_t> h_q;               // [P][n_used] quantised phenotypes, memory (phenotype-file) order
 	std::vector<uint32_t> col_of;          // [P] B / accumulator column of phenotype p
