@@ -51,6 +51,7 @@ struct kg_ctx {
 		kg_hit *d_hits = nullptr;
 		unsigned long long *d_cnt = nullptr;   // [0] hits [1] kept rows [2] rows listed by the filter (current tile)
 		                                       // [4] debug scratch [5] rows listed by the filter (whole interval)
+		                                       // [6] (row, column group) pairs listed (whole interval)
 		unsigned long long *h_cnt = nullptr;   // pinned copy of d_cnt, valid once `done` has completed
 		cudaEvent_t done = nullptr;
 		uint64_t rows = 0;                     // rows submitted into this interval
@@ -172,6 +173,7 @@ static void timing_resolve(kg_ctx *c) {
 struct KgScanParams;
 static KgScanParams scan_params(kg_ctx *c, const KgRowView &view, uint64_t first_row_id);
 template <int MODE> static kg_status launch_exact_pt(kg_ctx *c, const KgScanParams &prm);
+static kg_status launch_exact_list(kg_ctx *c, const KgScanParams &prm, uint32_t n_tiles);
 static kg_status ensure_squeeze_scratch(kg_ctx *c, uint64_t n_rows);
 
 // tensor-core engine (needs kg_ctx and the macros above)
@@ -588,6 +590,23 @@ static kg_status launch_exact(kg_ctx *c, const KgScanParams &prm) {
 	return KG_OK;
 }
 
+// list mode (MODE 2): one grid column per tile of 8 filter columns; the lists' lengths are only known on the device,
+// so the grid is one full wave and every CTA loops over its tile's list
+static kg_status launch_exact_list(kg_ctx *c, const KgScanParams &prm, uint32_t n_tiles) {
+	constexpr int GS = kg_ys_group_stride<8>();
+	const size_t smem = (size_t)c->nb * 4 * GS * sizeof(float);
+	auto kern = kg_scan_exact_kernel<2, 8, 2>;
+	KG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int occ = 1;
+	KG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+	if (occ < 1) occ = 1;
+	const uint64_t gx = std::max<uint64_t>(1, ((uint64_t)c->sm_count * occ) / n_tiles);
+	dim3 grid((unsigned)gx, n_tiles);
+	kern<<<grid, 256, smem, c->stream>>>(prm);
+	KG_LAUNCH_CHECK(c);
+	return KG_OK;
+}
+
 template <int MODE>
 static kg_status launch_exact_pt(kg_ctx *c, const KgScanParams &prm) {
 	switch (c->pt) {
@@ -686,9 +705,11 @@ static void consume_interval(kg_ctx *c, kg_ctx::ScanInterval &v, bool count_rows
 	if (count_rows) {
 		c->rows_seen_total += v.rows;
 		c->kept_total += v.h_cnt[1];
-		if (c->timing) c->timed_rows[KG_KERNEL_SCAN_REFINE] += v.h_cnt[5];  // "rows" of the refine class = rows re-scored
-		// auto engine: if the filter could not rule out most rows of the interval, the next one runs dense
-		if (v.used_filter && v.rows > 0) c->tc.use_filter = (double)v.h_cnt[5] < 0.7 * (double)v.rows;
+		if (c->timing) c->timed_rows[KG_KERNEL_SCAN_REFINE] += v.h_cnt[6];  // "rows" of the refine class = (row, 16-phenotype group) pairs re-scored
+		// auto engine: the exact kernel re-scores 2 tiles of 8 phenotypes per listed (row, group); if that is more
+		// work than scoring every row against every phenotype, the next interval runs dense
+		if (v.used_filter && v.rows > 0)
+			c->tc.use_filter = 16.0 * (double)v.h_cnt[6] < 0.8 * (double)v.rows * (double)c->n_pheno;
 		else c->tc.use_filter = true;
 	}
 	v.closed = false;

@@ -33,10 +33,16 @@ struct KgScanParams {
 	uint64_t first_row_id;
 	uint8_t *keep_out;       // dense mode
 	double *scores_out;      // dense mode [P][n_rows]
-	// row-list mode (MODE 2): score only rows row_list[0 .. *row_list_count) of the view
+	// list mode (MODE 2), fed by the tensor-core filter.  row_list[pos] = tile row of every row the filter could not
+	// rule out; the filter tests 16 phenotype columns at a time, and group_list[g * group_cap + k] = pos of the k-th
+	// row that survived the test of group g.  blockIdx.y = tile of 8 filter columns: tile tau re-scores the rows of
+	// group tau / 2 against the phenotypes tile_pheno[8 tau .. 8 tau + 7] (-1 = no phenotype in that column).
 	const uint32_t *row_list;
-	const unsigned long long *row_list_count;
-	uint32_t list_compact;   // 1: the view holds the listed rows back to back (squeezed copies); row_list gives their ids
+	const uint32_t *group_list;
+	const unsigned long long *group_count;   // [n_groups]
+	uint64_t group_cap;
+	const int32_t *tile_pheno;
+	uint32_t list_compact;   // 1: the view holds the listed rows back to back (squeezed copies), indexed by pos
 };
 
 __device__ __forceinline__ double kg_score_epilogue(float l0, float l1, float l2, float l3, double Nd,
@@ -97,12 +103,21 @@ __global__ void __launch_bounds__(256) kg_scan_exact_kernel(const KgScanParams p
 	constexpr int GS = kg_ys_group_stride<PT>();
 	const uint32_t ng = prm.nb * 4;
 	const uint32_t p0 = blockIdx.y * PT;
+	const uint64_t n_work = (MODE == 2) ? (uint64_t)prm.group_count[blockIdx.y >> 1] : prm.view.n_rows;
+	if (MODE == 2 && n_work == 0) return;   // nothing survived in this tile's group
 
-	// stage this CTA's y tile:  ys[g*GS + t*PT + q] = y_lane[p0+q][g*32 + t]
+	// stage this CTA's y tile:  ys[g*GS + t*PT + q] = y_lane[phenotype of slot q][g*32 + t]
 	for (uint32_t i = threadIdx.x; i < ng * 32 * PT; i += blockDim.x) {
 		const uint32_t q = i / (ng * 32);
 		const uint32_t gt = i - q * (ng * 32);
-		ys[(gt >> 5) * GS + (gt & 31) * PT + q] = prm.y_lane[(size_t)(p0 + q) * (ng * 32) + gt];
+		float v;
+		if (MODE == 2) {
+			const int32_t ph = prm.tile_pheno[p0 + q];
+			v = ph >= 0 ? prm.y_lane[(size_t)ph * (ng * 32) + gt] : 0.0f;
+		} else {
+			v = prm.y_lane[(size_t)(p0 + q) * (ng * 32) + gt];
+		}
+		ys[(gt >> 5) * GS + (gt & 31) * PT + q] = v;
 	}
 	__syncthreads();
 
@@ -117,7 +132,7 @@ __global__ void __launch_bounds__(256) kg_scan_exact_kernel(const KgScanParams p
 	const uint32_t stride32 = prm.view.stride * 2;
 	const uint32_t w32_in = prm.view.w_in * 2;
 
-	const uint64_t n_work = (MODE == 2) ? (uint64_t)*prm.row_list_count : prm.view.n_rows;
+	const uint32_t *glist = (MODE == 2) ? prm.group_list + (size_t)(blockIdx.y >> 1) * prm.group_cap : nullptr;
 	for (uint64_t chunk = blockIdx.x; chunk * ROWS_PER_CTA < n_work; chunk += gridDim.x) {
 		const uint64_t row0 = chunk * ROWS_PER_CTA + (uint64_t)warp * (8 * R) + row_sub;
 		uint64_t rows_of[R];   // view row of work item row0 + 8 r
@@ -127,8 +142,14 @@ __global__ void __launch_bounds__(256) kg_scan_exact_kernel(const KgScanParams p
 		for (int r = 0; r < R; r++) {
 			const uint64_t item = row0 + (uint64_t)r * 8;
 			valid_of[r] = item < n_work;
-			ids_of[r] = (MODE == 2) ? (valid_of[r] ? (uint64_t)prm.row_list[item] : 0ull) : item;
-			rows_of[r] = (MODE == 2 && prm.list_compact) ? item : ids_of[r];
+			if (MODE == 2) {
+				const uint32_t pos = valid_of[r] ? glist[item] : 0u;
+				ids_of[r] = valid_of[r] ? (uint64_t)prm.row_list[pos] : 0ull;
+				rows_of[r] = prm.list_compact ? (uint64_t)pos : ids_of[r];
+			} else {
+				ids_of[r] = item;
+				rows_of[r] = item;
+			}
 		}
 		float acc[R][PT];
 		uint32_t n1[R];
@@ -196,8 +217,9 @@ __global__ void __launch_bounds__(256) kg_scan_exact_kernel(const KgScanParams p
 				const float l1 = __shfl_sync(0xffffffffu, acc[r][q], grp_base + 1);
 				const float l2 = __shfl_sync(0xffffffffu, acc[r][q], grp_base + 2);
 				const float l3 = __shfl_sync(0xffffffffu, acc[r][q], grp_base + 3);
-				const uint32_t p = p0 + q;
-				if ((q & 3) == (int)L && keep && p < prm.n_pheno) {
+				const int32_t ph = (MODE == 2) ? prm.tile_pheno[p0 + q] : (int32_t)(p0 + q);
+				const uint32_t p = (uint32_t)ph;
+				if ((q & 3) == (int)L && keep && ph >= 0 && p < prm.n_pheno) {
 					const double score = kg_score_epilogue(l0, l1, l2, l3, Nd, N1d, prm.sums[p]);
 					if (MODE == 1) {
 						prm.scores_out[(size_t)p * prm.view.n_rows + row] = score;

@@ -71,6 +71,9 @@ struct KgFilterParams {
 	uint32_t n_used, min_count;
 	uint32_t *row_list;        // out: rows of the tile (index inside the tile) that could not be ruled out, any order
 	unsigned long long *n_listed;   // device counter for row_list (zeroed before the launch); capacity = n_rows
+	uint32_t *group_list;      // out: group_list[g * group_cap + k] = position in row_list of the k-th row whose
+	unsigned long long *group_count;   // 16-column group g survived; group_count[g] zeroed before the launch
+	uint64_t group_cap;        // = capacity of row_list (n_rows)
 	unsigned long long *kept_count;
 	int32_t *q_out;            // debug mode: [n_rows][p_pad] accumulators
 };
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 				// row popcount (column 0), then per 16-column group: max |accumulator| against the group's loosest bound
 				uint32_t n1 = 0;
 				float g = 0.f, hm = 0.f;
-				bool maybe = false;
+				uint32_t gmask = 0;   // bit k: group k could not be ruled out for this row
 				for (uint32_t c0 = 0; c0 < prm.p_pad; c0 += 32) {
 					uint32_t v[16], u[16];
 					kg_tmem_ld16(taddr + c0, v);
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 							mx = __vimax3_s32(mx, (int)v[j], (int)v[j + 1]);
 							mn = __vimin3_s32(mn, (int)v[j], (int)v[j + 1]);
 						}
-						maybe |= !((float)max(mx, -mn) < kg_filter_group_threshold(sConst[c0 >> 4], g, hm));
+						if (!((float)max(mx, -mn) < kg_filter_group_threshold(sConst[c0 >> 4], g, hm))) gmask |= 1u << (c0 >> 4);
 					}
 					if (second) {
 						int mx = 0, mn = 0;
@@ -275,25 +278,35 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 							mx = __vimax3_s32(mx, (int)u[j], (int)u[j + 1]);
 							mn = __vimin3_s32(mn, (int)u[j], (int)u[j + 1]);
 						}
-						maybe |= !((float)max(mx, -mn) < kg_filter_group_threshold(sConst[(c0 >> 4) + 1], g, hm));
+						if (!((float)max(mx, -mn) < kg_filter_group_threshold(sConst[(c0 >> 4) + 1], g, hm)))
+							gmask |= 1u << ((c0 >> 4) + 1);
 					}
 				}
-				// accumulators are in registers: hand the TMEM buffer back to the MMA warp before the row test
+				// accumulators are in registers: hand the TMEM buffer back to the MMA warp before the bookkeeping
 				kg_tc_fence_before();
 				__syncwarp();
 				if (lane == 0) kg_mbar_arrive(&tm_empty[buf]);
 				// load_kmers :121  (popcnt >= mac) && (popcnt <= N - mac)
 				const bool keep = grow < prm.n_rows && n1 >= prm.min_count && n1 + prm.min_count <= prm.n_used;
 				kept_local += __popc(__ballot_sync(0xffffffffu, keep));
-				maybe = maybe && keep;
-				// rows that could not be ruled out go to the exact kernel (all phenotypes of the row are re-scored in
-				// the reference's fp32 order); one atomic per warp
-				const uint32_t mb = __ballot_sync(0xffffffffu, maybe);
+				if (!keep) gmask = 0;
+				// rows that could not be ruled out go to the exact kernel, which re-scores them (in the reference's fp32
+				// order) against the phenotypes of the surviving groups only; one atomic per warp and list
+				const uint32_t mb = __ballot_sync(0xffffffffu, gmask != 0);
 				if (mb) {
 					unsigned long long basep = 0;
 					if (lane == 0) basep = atomicAdd(prm.n_listed, (unsigned long long)__popc(mb));
 					basep = __shfl_sync(0xffffffffu, basep, 0);
-					if (maybe) prm.row_list[basep + __popc(mb & ((1u << lane) - 1u))] = (uint32_t)grow;
+					const uint32_t pos = (uint32_t)basep + __popc(mb & ((1u << lane) - 1u));
+					if (gmask) prm.row_list[pos] = (uint32_t)grow;
+					for (uint32_t k = 0; k < prm.p_pad / 16; k++) {
+						const uint32_t gb = __ballot_sync(0xffffffffu, (gmask >> k) & 1u);
+						if (!gb) continue;
+						unsigned long long gbase = 0;
+						if (lane == 0) gbase = atomicAdd(prm.group_count + k, (unsigned long long)__popc(gb));
+						gbase = __shfl_sync(0xffffffffu, gbase, 0);
+						if ((gmask >> k) & 1u) prm.group_list[(size_t)k * prm.group_cap + gbase + __popc(gb & ((1u << lane) - 1u))] = pos;
+					}
 				}
 			}
 			if (MODE == 1) {

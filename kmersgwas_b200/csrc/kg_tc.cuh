@@ -6,7 +6,9 @@
 #include "kg_scan_filter.cuh"
 
 static void kg_tc_free(KgTcState *tc) {
-	cudaFree(tc->d_row_list); cudaFree(tc->d_yq); cudaFree(tc->d_gconst); cudaFree(tc->d_scratch); cudaFree(tc->d_aligned);
+	cudaFree(tc->d_row_list); cudaFree(tc->d_group_list); cudaFree(tc->d_group_count); cudaFree(tc->d_tile_pheno);
+	tc->d_group_list = nullptr; tc->d_group_count = nullptr; tc->d_tile_pheno = nullptr;
+	cudaFree(tc->d_yq); cudaFree(tc->d_gconst); cudaFree(tc->d_scratch); cudaFree(tc->d_aligned);
 	tc->d_row_list = nullptr; tc->d_yq = nullptr; tc->d_gconst = nullptr; tc->d_scratch = nullptr; tc->d_aligned = nullptr;
 	tc->aligned_cap = 0;
 	tc->row_list_cap = 0;
@@ -125,7 +127,7 @@ static kg_status kg_tc_update_thresholds(kg_ctx *c, KgFilterGroupConst *gc_pinne
 		// pinned image ring: the copy is stream-ordered behind the kernels still reading the old image
 		if (!tc.h_img_pinned[0]) {
 			for (int i = 0; i < 2; i++) {
-				KG_CUDA(c, cudaMallocHost((void **)&tc.h_img_pinned[i], tc.b_bytes));
+				KG_CUDA(c, cudaMallocHost((void **)&tc.h_img_pinned[i], tc.b_bytes + tc.p_pad * sizeof(int32_t)));
 				KG_CUDA(c, cudaEventCreateWithFlags(&tc.img_ev[i], cudaEventDisableTiming));
 			}
 			tc.img_bytes = tc.b_bytes;
@@ -143,6 +145,11 @@ static kg_status kg_tc_update_thresholds(kg_ctx *c, KgFilterGroupConst *gc_pinne
 				img[kg_tc_b_offset(tc, col_of[p], kg_filter_k_of_column(c->map_word[i] * 64 + c->map_bit[i]))] = q[i];
 		}
 		tc.col_of = col_of;
+		// exact-kernel tiles of 8 filter columns -> phenotype index (staged at the tail of the pinned image slot)
+		int32_t *tp = reinterpret_cast<int32_t *>(img + tc.b_bytes);
+		for (uint32_t k = 0; k < tc.p_pad; k++) tp[k] = -1;
+		for (uint32_t p = 0; p < P; p++) tp[col_of[p]] = (int32_t)p;
+		KG_CUDA(c, cudaMemcpyAsync(tc.d_tile_pheno, tp, tc.p_pad * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
 		tc.h_yq_image.assign(img, img + tc.b_bytes);
 		KG_CUDA(c, cudaMemcpyAsync(tc.d_yq, img, tc.b_bytes, cudaMemcpyHostToDevice, c->stream));
 		KG_CUDA(c, cudaEventRecord(tc.img_ev[slot], c->stream));
@@ -241,6 +248,12 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	}
 	cudaError_t e = cudaMalloc((void **)&tc.d_yq, tc.b_bytes);
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc quantised phenotypes: %s", cudaGetErrorString(e));
+	cudaFree(tc.d_tile_pheno); cudaFree(tc.d_group_count);
+	tc.d_tile_pheno = nullptr; tc.d_group_count = nullptr;
+	e = cudaMalloc((void **)&tc.d_tile_pheno, tc.p_pad * sizeof(int32_t));
+	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc tile table: %s", cudaGetErrorString(e));
+	e = cudaMalloc((void **)&tc.d_group_count, 16 * sizeof(unsigned long long));
+	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc group counters: %s", cudaGetErrorString(e));
 	e = cudaMalloc((void **)&tc.d_gconst, (tc.p_pad / 16) * sizeof(KgFilterGroupConst));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc filter constants: %s", cudaGetErrorString(e));
 	KG_CUDA(c, cudaFuncSetAttribute(kg_scan_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -291,6 +304,9 @@ static KgFilterParams kg_tc_filter_params(kg_ctx *c, const uint64_t *dev, uint64
 	f.min_count = (uint32_t)std::min<uint64_t>(c->min_count, 0xFFFFFFFFull);
 	f.row_list = tc.d_row_list;
 	f.n_listed = c->d_counters + 2;
+	f.group_list = tc.d_group_list;
+	f.group_count = tc.d_group_count;
+	f.group_cap = tc.row_list_cap;
 	f.kept_count = c->d_counters + 1;
 	return f;
 }
@@ -300,16 +316,25 @@ static kg_status kg_tc_ensure_row_list(kg_ctx *c, uint64_t n_rows) {
 	if (tc.row_list_cap >= n_rows) return KG_OK;
 	KG_CUDA(c, cudaStreamSynchronize(c->stream));
 	cudaFree(tc.d_row_list);
+	cudaFree(tc.d_group_list);
 	tc.d_row_list = nullptr;
+	tc.d_group_list = nullptr;
 	tc.row_list_cap = 0;
 	const uint64_t cap = std::max<uint64_t>(n_rows, 1u << 20);
 	cudaError_t e = cudaMalloc((void **)&tc.d_row_list, cap * sizeof(uint32_t));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc filter row list: %s", cudaGetErrorString(e));
+	e = cudaMalloc((void **)&tc.d_group_list, (size_t)(tc.p_pad / 16) * cap * sizeof(uint32_t));
+	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc filter group lists: %s", cudaGetErrorString(e));
 	tc.row_list_cap = cap;
 	return KG_OK;
 }
 
 __global__ void kg_add_counter_kernel(const unsigned long long *src, unsigned long long *dst) { *dst += *src; }
+__global__ void kg_sum_counters_kernel(const unsigned long long *src, uint32_t n, unsigned long long *dst) {
+	unsigned long long t = 0;
+	for (uint32_t i = 0; i < n; i++) t += src[i];
+	*dst += t;
+}
 
 // filter the tile on the tensor cores, then re-score the rows it could not rule out with the exact kernel
 static kg_status kg_tc_scan_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_rows, uint64_t first_row_id) {
@@ -324,6 +349,7 @@ static kg_status kg_tc_scan_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_r
 		if (st != KG_OK) return st;
 	}
 	KG_CUDA(c, cudaMemsetAsync(c->d_counters + 2, 0, sizeof(unsigned long long), c->stream));
+	KG_CUDA(c, cudaMemsetAsync(tc.d_group_count, 0, 16 * sizeof(unsigned long long), c->stream));
 	KgFilterParams f = kg_tc_filter_params(c, dev, n_rows);
 	const uint32_t n_blocks = (uint32_t)((n_rows + KG_F_ROWS - 1) / KG_F_ROWS);
 	const unsigned grid = std::max(1u, std::min<uint32_t>(n_blocks, (uint32_t)c->sm_count));
@@ -347,13 +373,18 @@ static kg_status kg_tc_scan_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_r
 	}
 	KgScanParams prm = scan_params(c, view, first_row_id);
 	prm.row_list = tc.d_row_list;
-	prm.row_list_count = c->d_counters + 2;
+	prm.group_list = tc.d_group_list;
+	prm.group_count = tc.d_group_count;
+	prm.group_cap = tc.row_list_cap;
+	prm.tile_pheno = tc.d_tile_pheno;
 	prm.list_compact = compact;
 	timing_begin(c, KG_KERNEL_SCAN_REFINE, 0);
-	st = launch_exact_pt<2>(c, prm);
+	st = launch_exact_list(c, prm, tc.p_pad / 8);
 	timing_end(c);
 	if (st != KG_OK) return st;
 	kg_add_counter_kernel<<<1, 1, 0, c->stream>>>(c->d_counters + 2, c->d_counters + 5);
+	KG_LAUNCH_CHECK(c);
+	kg_sum_counters_kernel<<<1, 1, 0, c->stream>>>(tc.d_group_count, tc.p_pad / 16, c->d_counters + 6);
 	KG_LAUNCH_CHECK(c);
 	return KG_OK;
 }
@@ -364,6 +395,8 @@ static kg_status kg_tc_filter_debug(kg_ctx *c, const uint64_t *dev_in, uint64_t 
 	if (!tc.scan_ready) KG_FAIL(c, KG_ERR_INVALID, "tensor filter engine unavailable: %s", tc.why_unavailable.c_str());
 	const uint64_t *dev = nullptr;
 	kg_status st = kg_tc_aligned_tile(c, dev_in, n_rows, &dev);
+	if (st != KG_OK) return st;
+	st = kg_tc_ensure_row_list(c, n_rows);
 	if (st != KG_OK) return st;
 	KgFilterParams f = kg_tc_filter_params(c, dev, n_rows);
 	int32_t *d_q = nullptr;
