@@ -167,31 +167,36 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 			}
 		}
 	} else if (warp == 1) {
-		// ===================== MMA issuer (one thread) =====================
-		if (lane == 0) {
-			const uint32_t idesc = kg_umma_idesc_i8(KG_F_ROWS, prm.p_pad, false, true, false, false);
-			const uint32_t sA_addr = kg_smem_u32(sA), sB_addr = kg_smem_u32(sB);
-			kg_mbar_wait(b_full, 0);
-			uint32_t it = 0, ait = 0;
-			for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, it++) {
-				const uint32_t buf = it & 1;
-				kg_mbar_wait(&tm_empty[buf], ((it >> 1) & 1) ^ 1);
+		// ===================== MMA issuer =====================
+		// The whole warp runs the loop (so that descriptors and addresses live in uniform registers); one elected
+		// lane issues the tcgen05.mma / tcgen05.commit instructions.
+		const uint32_t idesc = kg_umma_idesc_i8(KG_F_ROWS, prm.p_pad, false, true, false, false);
+		const uint64_t a_desc0 = kg_umma_smem_desc(kg_smem_u32(sA), 128, 1024);        // stage 0, K offset 0
+		const uint64_t b_desc0 = kg_umma_smem_desc(kg_smem_u32(sB), 128, prm.sbo_b);   // column chunk 0
+		kg_mbar_wait(b_full, 0);
+		uint32_t it = 0, ait = 0;
+		for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, it++) {
+			const uint32_t buf = it & 1;
+			kg_mbar_wait(&tm_empty[buf], ((it >> 1) & 1) ^ 1);
+			kg_tc_fence_after();
+			const uint32_t d_tmem = tmem_base + buf * prm.tcols;
+			for (uint32_t c = 0; c < prm.nc; c++, ait++) {
+				const uint32_t st = ait % KG_F_A_STAGES, use = ait / KG_F_A_STAGES;
+				kg_mbar_wait(&a_full[st], use & 1);
 				kg_tc_fence_after();
-				const uint32_t d_tmem = tmem_base + buf * prm.tcols;
-				for (uint32_t c = 0; c < prm.nc; c++, ait++) {
-					const uint32_t st = ait % KG_F_A_STAGES, use = ait / KG_F_A_STAGES;
-					kg_mbar_wait(&a_full[st], use & 1);
-					kg_tc_fence_after();
+				if (kg_elect_one()) {
+					// descriptor address fields are in 16-byte units: one stage = 1024 units, one K = 32 step = 16 units,
+					// one 128-column chunk of B = 64 units
+					const uint64_t ad = a_desc0 + (uint64_t)(st * (KG_F_A_STAGE_BYTES >> 4));
+					const uint64_t bd = b_desc0 + (uint64_t)(c * 64);
 #pragma unroll
-					for (uint32_t kk = 0; kk < 4; kk++) {
-						const uint64_t ad = kg_umma_smem_desc(sA_addr + st * KG_F_A_STAGE_BYTES + kk * 256, 128, 1024);
-						const uint64_t bd = kg_umma_smem_desc(sB_addr + (c * 8 + kk * 2) * 128, 128, prm.sbo_b);
-						kg_umma_i8(d_tmem, ad, bd, idesc, (c | kk) != 0);
-					}
+					for (uint32_t kk = 0; kk < 4; kk++) kg_umma_i8(d_tmem, ad + kk * 16, bd + kk * 16, idesc, (c | kk) != 0);
 					kg_umma_commit(&a_empty[st]);
 				}
-				kg_umma_commit(&tm_full[buf]);
+				__syncwarp();
 			}
+			if (kg_elect_one()) kg_umma_commit(&tm_full[buf]);
+			__syncwarp();
 		}
 	} else if (warp < KG_F_EPI_WARP0) {
 		// ===================== expanders: bits -> u8 core matrices (thread = row x one u64 word per stage) ===========

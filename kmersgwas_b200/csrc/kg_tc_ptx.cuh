@@ -7,6 +7,17 @@
 
 __device__ __forceinline__ uint32_t kg_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of the (converged) warp: the same lane every time, so that tcgen05.commit sees the MMAs it issued
+__device__ __forceinline__ bool kg_elect_one() {
+	uint32_t pred;
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "elect.sync _|p, 0xffffffff;\n\t"
+	    "selp.u32 %0, 1, 0, p;\n\t}"
+	    : "=r"(pred));
+	return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------
 __device__ __forceinline__ void kg_mbar_init(uint64_t *bar, uint32_t count) {
 	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(kg_smem_u32(bar)), "r"(count) : "memory");
