@@ -22,11 +22,13 @@
 //
 // Kernel: persistent, one CTA per SM, 128-row blocks, warp-specialised:
 //   warp 0      bulk-async-copies raw 128-row blocks (contiguous 128 * 8(1+W) bytes) into a 2-stage ring
-//   warps 2-9   expand presence bits -> u8 {0,0x80} into K-major core-matrix A stages (16 KB = 128 rows x 128 columns)
-//               with one 64-bit multiply per presence byte
-//   warp 1      one thread issues tcgen05.mma kind::i8 (M = 128, N = P_pad, K = 32 per instruction) into a
-//               double-buffered TMEM accumulator; B (quantised phenotypes, P_pad x K_pad s8) stays in smem
-//   warps 10-13 epilogue: tcgen05.ld of the 128 x P_pad accumulators; column 0 of B is all-ones over the used
+//   warps 2-9   expand presence bits -> u8 {0,0x80} with one 64-bit multiply per presence byte and store them with
+//               tcgen05.st straight into TENSOR MEMORY (A operand from TMEM: lane = row, 4 bytes of K per column),
+//               8 stages of 128 columns; no shared-memory round trip and no proxy fence for A
+//   warp 1      one elected thread issues tcgen05.mma kind::i8 (M = 128, N = P_pad, K = 32 per instruction, A from
+//               TMEM, B from shared memory) into a double-buffered TMEM accumulator; B (quantised phenotypes,
+//               P_pad x K_pad s8, K-major core matrices, no swizzle) stays resident in shared memory
+//   warps 10-17 epilogue (two sets of 4 warps alternate blocks, one accumulator buffer each): tcgen05.ld of the 128 x P_pad accumulators; column 0 of B is all-ones over the used
 //               columns, so its accumulator is the row popcount (MAC filter) for free; pass 1 takes max |Q| over the
 //               row with 3-input min/max and rules the whole row out against the loosest column bound; rows that
 //               survive (rare) are appended to a global row list for the exact kernel
@@ -36,13 +38,15 @@
 
 #define KG_F_ROWS 128            // rows per block = UMMA M
 #define KG_F_CHUNK_COLS 128      // presence columns per A stage (two u64 words per row)
-#define KG_F_A_STAGE_BYTES (KG_F_ROWS * KG_F_CHUNK_COLS)
-#define KG_F_A_STAGES 3
-#define KG_F_RAW_STAGES 2
+#define KG_F_A_STAGE_TCOLS (KG_F_CHUNK_COLS / 4)   // TMEM columns of one A stage (4 u8 per 32-bit column)
+#define KG_F_A_STAGES 8          // A stages in tensor memory: 8 x 32 columns next to the 2 x 128 accumulator columns
+#define KG_F_TMEM_COLS 512
+#define KG_F_RAW_STAGES 4
 #define KG_F_EXPAND_WARP0 2
 #define KG_F_EXPAND_WARPS 8
 #define KG_F_EPI_WARP0 (KG_F_EXPAND_WARP0 + KG_F_EXPAND_WARPS)
-#define KG_F_THREADS ((KG_F_EPI_WARP0 + 4) * 32)
+#define KG_F_EPI_WARPS 8         // two sets of 4 (one warp per TMEM lane quarter); set s owns accumulator buffer s
+#define KG_F_THREADS ((KG_F_EPI_WARP0 + KG_F_EPI_WARPS) * 32)
 #define KG_F_ONE 128             // value of a set presence bit in the u8 A operand (0x80)
 
 // Per 16-column group: the loosest bound of its phenotype columns, in accumulator units (x KG_F_ONE).
@@ -80,8 +84,7 @@ struct KgFilterParams {
 
 __host__ __device__ inline uint32_t kg_filter_raw_stage_bytes(uint32_t w_file) { return KG_F_ROWS * 8u * (w_file + 1); }
 __host__ __device__ inline size_t kg_filter_smem_bytes(uint32_t w_file, uint32_t b_bytes, uint32_t p_pad) {
-	return 1024 /*alignment slack*/ + (size_t)b_bytes + (size_t)KG_F_A_STAGES * KG_F_A_STAGE_BYTES +
-	       (size_t)KG_F_RAW_STAGES * kg_filter_raw_stage_bytes(w_file) + (size_t)(p_pad / 16) * sizeof(KgFilterGroupConst) + 256;
+	return 1024 /*alignment slack*/ + (size_t)b_bytes + (size_t)KG_F_RAW_STAGES * kg_filter_raw_stage_bytes(w_file) + (size_t)(p_pad / 16) * sizeof(KgFilterGroupConst) + 256;
 }
 // K index (byte inside the A / B operands) of file column `col`: the expander's 64-bit multiply leaves bit i of
 // every presence byte in output byte 7 - i, so B is stored with the same permutation.
@@ -92,11 +95,14 @@ __host__ __device__ inline uint32_t kg_filter_k_of_column(uint32_t col) { return
 __device__ __forceinline__ uint64_t kg_spread8(uint32_t byte) {
 	return ((uint64_t)byte * 0x8040201008040201ull) & 0x8080808080808080ull;
 }
-__device__ __forceinline__ void kg_expand_u32(uint32_t w, uint32_t smem_dst) {
-	const uint64_t a = kg_spread8(__byte_perm(w, 0, 0x4440)), b = kg_spread8(__byte_perm(w, 0, 0x4441));
-	const uint64_t c = kg_spread8(__byte_perm(w, 0, 0x4442)), d = kg_spread8(__byte_perm(w, 0, 0x4443));
-	asm volatile("st.shared.v2.b64 [%0], {%1,%2};" ::"r"(smem_dst), "l"(a), "l"(b) : "memory");
-	asm volatile("st.shared.v2.b64 [%0], {%1,%2};" ::"r"(smem_dst + 128), "l"(c), "l"(d) : "memory");
+// 32 presence bits -> 32 u8 operand bytes in 8 registers
+__device__ __forceinline__ void kg_expand_u32(uint32_t w, uint32_t *out8) {
+#pragma unroll
+	for (int b = 0; b < 4; b++) {
+		const uint64_t v = kg_spread8(__byte_perm(w, 0, 0x4440 + b));
+		out8[2 * b] = (uint32_t)v;
+		out8[2 * b + 1] = (uint32_t)(v >> 32);
+	}
 }
 
 // alpha * g - kappa - slack(m), every step rounded towards -inf (a lower threshold only lists more rows)
@@ -113,9 +119,8 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 	// carve shared memory (1024-byte aligned base)
 	uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)kg_f_smem_raw + 1023) & ~(uintptr_t)1023);
 	uint8_t *sB = base;
-	uint8_t *sA = sB + prm.b_bytes;
 	const uint32_t raw_stage_bytes = kg_filter_raw_stage_bytes(prm.w_file);
-	uint8_t *sRaw = sA + KG_F_A_STAGES * KG_F_A_STAGE_BYTES;
+	uint8_t *sRaw = sB + prm.b_bytes;
 	KgFilterGroupConst *sConst = reinterpret_cast<KgFilterGroupConst *>(sRaw + KG_F_RAW_STAGES * raw_stage_bytes);
 	uint64_t *bars = reinterpret_cast<uint64_t *>(sConst + prm.p_pad / 16);
 	uint64_t *raw_full = bars, *raw_empty = bars + KG_F_RAW_STAGES;
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 		kg_fence_mbar_init();
 	}
 	for (uint32_t i = threadIdx.x; i < prm.p_pad / 16; i += blockDim.x) sConst[i] = prm.gconst[i];
-	if (warp == 1) kg_tmem_alloc(tmem_slot, 2 * prm.tcols);
+	if (warp == 1) kg_tmem_alloc(tmem_slot, KG_F_TMEM_COLS);
 	kg_tc_fence_before();
 	__syncthreads();
 	kg_tc_fence_after();
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 		// The whole warp runs the loop (so that descriptors and addresses live in uniform registers); one elected
 		// lane issues the tcgen05.mma / tcgen05.commit instructions.
 		const uint32_t idesc = kg_umma_idesc_i8(KG_F_ROWS, prm.p_pad, false, true, false, false);
-		const uint64_t a_desc0 = kg_umma_smem_desc(kg_smem_u32(sA), 128, 1024);        // stage 0, K offset 0
+		const uint32_t a_tmem0 = tmem_base + 2 * prm.tcols;                             // A stage 0, K offset 0
 		const uint64_t b_desc0 = kg_umma_smem_desc(kg_smem_u32(sB), 128, prm.sbo_b);   // column chunk 0
 		kg_mbar_wait(b_full, 0);
 		uint32_t it = 0, ait = 0;
@@ -185,12 +190,12 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 				kg_mbar_wait(&a_full[st], use & 1);
 				kg_tc_fence_after();
 				if (kg_elect_one()) {
-					// descriptor address fields are in 16-byte units: one stage = 1024 units, one K = 32 step = 16 units,
-					// one 128-column chunk of B = 64 units
-					const uint64_t ad = a_desc0 + (uint64_t)(st * (KG_F_A_STAGE_BYTES >> 4));
+					// A: 8 TMEM columns per K = 32 step.  B descriptor address field is in 16-byte units: one K = 32 step =
+					// 16 units, one 128-column chunk = 64 units
+					const uint32_t at = a_tmem0 + st * KG_F_A_STAGE_TCOLS;
 					const uint64_t bd = b_desc0 + (uint64_t)(c * 64);
 #pragma unroll
-					for (uint32_t kk = 0; kk < 4; kk++) kg_umma_i8(d_tmem, ad + kk * 16, bd + kk * 16, idesc, (c | kk) != 0);
+					for (uint32_t kk = 0; kk < 4; kk++) kg_umma_i8_ts(d_tmem, at + kk * 8, bd + kk * 16, idesc, (c | kk) != 0);
 					kg_umma_commit(&a_empty[st]);
 				}
 				__syncwarp();
@@ -199,11 +204,12 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 			__syncwarp();
 		}
 	} else if (warp < KG_F_EPI_WARP0) {
-		// ===================== expanders: bits -> u8 core matrices (thread = row x one u64 word per stage) ===========
-		const uint32_t t = threadIdx.x - KG_F_EXPAND_WARP0 * 32;
-		const uint32_t r = t & (KG_F_ROWS - 1), half = t >> 7;
-		const uint32_t dst_row = (r & 7) * 16 + (r >> 3) * 1024 + half * 512;
-		const uint32_t sA_addr = kg_smem_u32(sA);
+		// ===================== expanders: presence bits -> u8 A operand in tensor memory =====================
+		// thread = row (its TMEM lane) x one u64 word of the stage: 64 operand bytes = 16 TMEM columns
+		const uint32_t q4 = warp & 3;                                   // TMEM lane quarter of this warp
+		const uint32_t half = (warp - KG_F_EXPAND_WARP0) >> 2;          // which u64 word of the 128-column stage
+		const uint32_t r = q4 * 32 + lane;
+		const uint32_t a_taddr0 = tmem_base + 2 * prm.tcols + ((q4 * 32u) << 16) + half * 16;
 		uint32_t it = 0, ait = 0;
 		for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, it++) {
 			const uint32_t rst = it % KG_F_RAW_STAGES, ruse = it / KG_F_RAW_STAGES;
@@ -214,11 +220,14 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 				const uint32_t st = ait % KG_F_A_STAGES, use = ait / KG_F_A_STAGES;
 				const uint32_t nxt = 2 * (c + 1) + half;
 				const uint64_t w_next = (nxt < prm.w_file) ? row[nxt] : 0ull;   // prefetch before the wait
+				uint32_t v[16];
+				kg_expand_u32((uint32_t)w, v);
+				kg_expand_u32((uint32_t)(w >> 32), v + 8);
 				kg_mbar_wait(&a_empty[st], (use & 1) ^ 1);
-				const uint32_t dst = sA_addr + st * KG_F_A_STAGE_BYTES + dst_row;
-				kg_expand_u32((uint32_t)w, dst);
-				kg_expand_u32((uint32_t)(w >> 32), dst + 256);
-				kg_fence_proxy_async();
+				kg_tc_fence_after();
+				kg_tmem_st16(a_taddr0 + st * KG_F_A_STAGE_TCOLS, v);
+				kg_tmem_st_wait();
+				kg_tc_fence_before();
 				__syncwarp();
 				if (lane == 0) kg_mbar_arrive(&a_full[st]);
 				w = w_next;
@@ -230,12 +239,13 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 		// ===================== epilogue: MAC filter + bound test =====================
 		const uint32_t q4 = warp & 3;                       // TMEM lane quarter this warp may access
 		const uint32_t r = q4 * 32 + lane;                  // row of the block = TMEM lane
+		const uint32_t eset = (warp - KG_F_EPI_WARP0) >> 2; // this warp's set: it handles the blocks of accumulator buffer eset
 		const float Nf = (float)prm.n_used;
 		unsigned long long kept_local = 0;
-		uint32_t it = 0;
-		for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, it++) {
+		for (uint32_t it = eset; (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x < n_blocks; it += 2) {
+			const uint32_t blk = blockIdx.x + it * gridDim.x;
 			const uint64_t grow = (uint64_t)blk * KG_F_ROWS + r;
-			const uint32_t buf = it & 1;
+			const uint32_t buf = eset;
 			kg_mbar_wait(&tm_full[buf], (it >> 1) & 1);
 			kg_tc_fence_after();
 			const uint32_t taddr = tmem_base + buf * prm.tcols + ((q4 * 32u) << 16);
@@ -304,9 +314,11 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 					basep = __shfl_sync(0xffffffffu, basep, 0);
 					const uint32_t pos = (uint32_t)basep + __popc(mb & ((1u << lane) - 1u));
 					if (gmask) prm.row_list[pos] = (uint32_t)grow;
-					for (uint32_t k = 0; k < prm.p_pad / 16; k++) {
+					uint32_t gor = __reduce_or_sync(0xffffffffu, gmask);
+					while (gor) {
+						const uint32_t k = __ffs(gor) - 1;
+						gor &= gor - 1;
 						const uint32_t gb = __ballot_sync(0xffffffffu, (gmask >> k) & 1u);
-						if (!gb) continue;
 						unsigned long long gbase = 0;
 						if (lane == 0) gbase = atomicAdd(prm.group_count + k, (unsigned long long)__popc(gb));
 						gbase = __shfl_sync(0xffffffffu, gbase, 0);
@@ -326,5 +338,5 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 	// teardown: every role has drained its loop; the last tm_full wait of the epilogue implies all MMAs completed
 	kg_tc_fence_before();
 	__syncthreads();
-	if (warp == 1) kg_tmem_dealloc(tmem_base, 2 * prm.tcols);
+	if (warp == 1) kg_tmem_dealloc(tmem_base, KG_F_TMEM_COLS);
 }

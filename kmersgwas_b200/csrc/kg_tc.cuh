@@ -177,7 +177,8 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	tc.tcols = 32;
 	while (tc.tcols < tc.p_pad) tc.tcols *= 2;
 	if (c->min_count < 1) { tc.why_unavailable = "min_count = 0 (rows with an empty group have no finite bound)"; return KG_OK; }
-	if (tc.p_pad > 256) { tc.why_unavailable = "more than 255 phenotype columns per pass"; return KG_OK; }
+	// TMEM budget: 2 accumulator buffers of tcols columns + 8 A stages of 32 columns in 512 columns
+	if (tc.p_pad > 128) { tc.why_unavailable = "more than 127 phenotype columns per pass"; return KG_OK; }
 	if (tc.sbo_b > 0x3FFFu * 16) { tc.why_unavailable = "table too wide for the B descriptor stride"; return KG_OK; }
 	const size_t smem = kg_filter_smem_bytes(c->w_file, tc.b_bytes, tc.p_pad);
 	if (smem > 227u * 1024) {

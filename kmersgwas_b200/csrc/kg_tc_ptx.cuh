@@ -93,6 +93,24 @@ __device__ __forceinline__ void kg_umma_i8(uint32_t d_tmem, uint64_t a_desc, uin
 	    "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
 	    : "memory");
 }
+// Same with the A operand in tensor memory (lane = row, 4 one-byte K elements per 32-bit column).
+__device__ __forceinline__ void kg_umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+	    "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+	    "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+	    : "memory");
+}
+// registers -> TMEM: this warp's 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void kg_tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+	asm volatile(
+	    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+	    "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+	    "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+	    : "memory");
+}
+__device__ __forceinline__ void kg_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // mbarrier arrive once all tcgen05.mma issued so far by this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void kg_umma_commit(uint64_t *bar) {
