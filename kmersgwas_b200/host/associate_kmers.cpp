@@ -17,6 +17,8 @@
 #include "association_driver.h"
 #include "best_associations_heap.h"
 #include "cli_options.h"
+#include <cstdlib>
+
 #include "kmer_general.h"
 #include "kmers_multiple_databases.h"
 
@@ -134,7 +136,9 @@ int main(int argc, char *argv[]) {
 		// ---- pass 1: association scan ----------------------------------------------------------
 		vector<Shard> shards(n_gpus);
 		for (size_t g = 0; g < n_gpus; g++) {
-			MultipleKmersDataBases::set_device(device0 + (int)g);
+			// KMERSGWAS_SHARDS_ON_ONE_DEVICE=1 (tests): every shard gets its own context on the same GPU
+			const bool one_device = getenv("KMERSGWAS_SHARDS_ON_ONE_DEVICE") != nullptr;
+			MultipleKmersDataBases::set_device(one_device ? device0 : device0 + (int)g);
 			shards[g].db.reset(new MultipleKmersDataBases(table, p_list[0].first, kmer_length));
 			shards[g].db->set_scan_engine(engine);
 		}

@@ -1,0 +1,133 @@
+"""GPU tests of the two CLIs (kmersgwas_b200/bin/associate_kmers, emma_kinship_kmers): same flags, same input files
+and BYTE-IDENTICAL output files as the unmodified reference binaries (oracle/_ref, built from /root/reference by
+oracle/Makefile and shipped to the GPU box)."""
+import filecmp
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import support as S
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parent.parent
+BIN = ROOT / "kmersgwas_b200" / "bin"
+
+
+@pytest.fixture(scope="module")
+def bins(gpu_device):
+    if not S.have_ref():
+        pytest.skip("oracle/_ref not built")
+    for exe in ("associate_kmers", "emma_kinship_kmers"):
+        if not (BIN / exe).exists():
+            pytest.skip("CLI binaries not built")
+    return BIN
+
+
+def _run(exe, args, cwd=None):
+    return subprocess.run([str(exe)] + [str(a) for a in args], cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+
+
+def _same_dir(a: Path, b: Path):
+    fa, fb = sorted(p.name for p in a.iterdir()), sorted(p.name for p in b.iterdir())
+    assert fa == fb, (fa, fb)
+    for n in fa:
+        assert filecmp.cmp(a / n, b / n, shallow=False), f"{n} differs"
+    return fa
+
+
+@pytest.mark.parametrize("name,extra", [
+    ("plumbing_n64", []),
+    ("identity_n131", ["--k_mers_scores"]),
+    ("subset_n300", ["--k_mers_scores", "--pattern_counter"]),
+    ("ties_n96", ["--k_mers_scores"]),
+    ("thaliana_n1135", ["--k_mers_scores", "--engine", "2"]),
+])
+def test_associate_kmers_outputs_byte_identical(bins, tmp_path, name, extra):
+    g = S.Golden(name)
+    table, pheno = g.write_inputs(tmp_path)
+    outs = {}
+    for tag, exe in (("ref", S.REF_DIR / "associate_kmers"), ("ours", bins / "associate_kmers")):
+        out = tmp_path / tag
+        out.mkdir()
+        args = ["-p", pheno, "-b", "run", "-o", out, "--kmers_table", table, "-n", g.kbest, "--kmer_len", 31,
+                "--maf", g.maf, "--mac", g.mac, "--batch_size", g.batch, "--parallel", 2]
+        args += [a for a in extra if tag == "ours" or a not in ("--engine", "2")]
+        r = _run(exe, args)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[tag] = (out, r)
+    files = _same_dir(outs["ref"][0], outs["ours"][0])
+    assert any(f.endswith(".bed") for f in files) and "run.tested_kmers" in files
+    # the same progress vocabulary on stderr (timers differ)
+    for key in ("Effective minor allele count", "Load [0]", "Associations [0]"):
+        assert key in outs["ours"][1].stderr
+
+
+def test_associate_kmers_first_phenotype_best_and_small_batches(bins, tmp_path):
+    g = S.Golden("identity_n131")
+    table, pheno = g.write_inputs(tmp_path)
+    dirs = []
+    for tag, exe in (("ref", S.REF_DIR / "associate_kmers"), ("ours", bins / "associate_kmers")):
+        out = tmp_path / tag
+        out.mkdir()
+        r = _run(exe, ["-p", pheno, "-b", "x", "-o", out, "--kmers_table", table, "-n", 40, "--first_phenotype_best", 90,
+                       "--kmer_len", 31, "--maf", 0.1, "--mac", 3, "--batch_size", 777, "--k_mers_scores"])
+        assert r.returncode == 0, r.stderr[-2000:]
+        dirs.append(out)
+    _same_dir(*dirs)
+
+
+def test_associate_kmers_errors_like_reference(bins, tmp_path):
+    g = S.Golden("plumbing_n64")
+    table, pheno = g.write_inputs(tmp_path)
+    # --help: exit 0; unknown flag / missing required flag / bad k-mer length: non-zero exit, nothing written
+    assert _run(bins / "associate_kmers", ["--help"]).returncode == 0
+    assert _run(bins / "associate_kmers", ["--nonsense"]).returncode != 0
+    assert _run(bins / "associate_kmers", ["-p", pheno, "-b", "x", "--kmers_table", table]).returncode != 0
+    r = _run(bins / "associate_kmers", ["-p", pheno, "-b", "x", "-o", tmp_path, "--kmers_table", table, "--kmer_len", 9])
+    assert r.returncode == 1 and "kmer length has to be between 10-31" in r.stderr
+    # wrong k in the table header, unknown accession in the phenotype file
+    r = _run(bins / "associate_kmers", ["-p", pheno, "-b", "x", "-o", tmp_path, "--kmers_table", table, "--kmer_len", 25])
+    assert r.returncode != 0
+    bad = tmp_path / "bad.tsv"
+    bad.write_text(Path(pheno).read_text().replace("s3\t", "nobody\t"))
+    r = _run(bins / "associate_kmers", ["-p", bad, "-b", "x", "-o", tmp_path, "--kmers_table", table, "--kmer_len", 31])
+    assert r.returncode != 0
+
+
+@pytest.mark.parametrize("name,maf", [("plumbing_n64", 0.05), ("identity_n131", 0.1), ("thaliana_n1135", 0.05)])
+def test_emma_kinship_kmers_stdout_identical(bins, tmp_path, name, maf):
+    g = S.Golden(name)
+    table, _ = g.write_inputs(tmp_path)
+    args = ["-t", table, "-k", 31, "--maf", maf]
+    ref = _run(S.REF_DIR / "emma_kinship_kmers", args)
+    ours = _run(bins / "emma_kinship_kmers", args)
+    assert ref.returncode == 0 and ours.returncode == 0, ours.stderr[-2000:]
+    assert ours.stdout == ref.stdout
+    assert len(ours.stdout.splitlines()) == g.n_file
+
+
+def test_associate_kmers_two_shards_equal_one(bins, tmp_path):
+    """--gpus 2 on one device (two contexts): sharded scan + exact merge == single scan."""
+    import os
+    import torch
+    g = S.Golden("subset_n300")
+    table, pheno = g.write_inputs(tmp_path)
+    dirs = []
+    if torch.cuda.device_count() < 2:
+        os.environ["KMERSGWAS_SHARDS_ON_ONE_DEVICE"] = "1"
+    for tag, extra in (("one", []), ("two", ["--gpus", 2]), ("three", ["--gpus", 3])):
+        out = tmp_path / tag
+        out.mkdir()
+        if tag == "three":
+            os.environ["KMERSGWAS_SHARDS_ON_ONE_DEVICE"] = "1"
+        r = _run(bins / "associate_kmers", ["-p", pheno, "-b", "x", "-o", out, "--kmers_table", table, "-n", g.kbest,
+                                           "--kmer_len", 31, "--maf", g.maf, "--mac", g.mac, "--batch_size", 500,
+                                           "--k_mers_scores"] + extra)
+        assert r.returncode == 0, r.stderr[-2000:]
+        dirs.append(out)
+    os.environ.pop("KMERSGWAS_SHARDS_ON_ONE_DEVICE", None)
+    _same_dir(dirs[0], dirs[1])
+    _same_dir(dirs[0], dirs[2])
