@@ -856,6 +856,17 @@ extern "C" kg_status kg_kinship_submit(kg_ctx *c, const uint64_t *rows, uint64_t
 	const uint64_t *dev = nullptr;
 	kg_status st = acquire_tile(c, rows, n_rows, &dev);
 	if (st != KG_OK) return st;
+	bool use_tc = false;
+	if (c->kin_engine == 2) use_tc = true;
+	else if (c->kin_engine == 0) use_tc = kg_tc_kinship_available(c);
+	if (use_tc && !kg_tc_kinship_available(c))
+		KG_FAIL(c, KG_ERR_INVALID, "tensor kinship engine unavailable: %s", c->tc.why_unavailable.c_str());
+	if (use_tc) {
+		// raw rows straight to the tensor cores (file column order; MAC filter inside the kernel)
+		st = kg_tc_kinship_tile(c, dev, n_rows);
+		if (st != KG_OK) return st;
+		return release_tile(c);
+	}
 	KgRowView view;
 	st = memory_view(c, dev, n_rows, &view);
 	if (st != KG_OK) return st;
@@ -880,15 +891,7 @@ extern "C" kg_status kg_kinship_submit(kg_ctx *c, const uint64_t *rows, uint64_t
 		timing_end(c);
 		KG_LAUNCH_CHECK(c);
 	}
-	bool use_tc = false;
-	if (c->kin_engine == 2) use_tc = true;
-	else if (c->kin_engine == 0) use_tc = kg_tc_kinship_available(c);
-	if (use_tc && !kg_tc_kinship_available(c))
-		KG_FAIL(c, KG_ERR_INVALID, "tensor kinship engine unavailable: %s", c->tc.why_unavailable.c_str());
-	if (use_tc) {
-		st = kg_tc_kinship_tile(c, view);
-		if (st != KG_OK) return st;
-	} else {
+	{
 		const uint32_t t64 = (uint32_t)((c->n_used + 63) / 64);
 		const uint32_t pair_tiles = t64 * (t64 + 1) / 2;
 		const uint64_t n_chunks = (n_rows + KG_KIN_CHUNK_ROWS - 1) / KG_KIN_CHUNK_ROWS;

@@ -1,0 +1,257 @@
+// kg_kinship_tc.cuh -- kinship Gram accumulation on the int8 tensor cores (tcgen05.mma kind::i8, TMEM int32
+// accumulators).  KG_OPT_KINSHIP_ENGINE = 2.
+//
+// Reference: update_emma_kinshhip_calculation (/root/reference/src/kmers_multiple_databases.cpp:418-438):
+//   K[i][j] += 1 ^ g_i ^ g_j (j < i) over the rows load_kmers keeps.  With G = B^T B (co-presence counts over the
+//   kept rows, B = rows x samples 0/1), c_i = G[i][i] and M kept rows: K[i][j] = M - c_i - c_j + 2 G[i][j], exact.
+// This is the one dense contraction of the hot path: the contraction index is the ROW.
+//
+// Work split: the lower triangle of G (in FILE column order) is cut into tiles of 128 x 256 samples; a tile
+// group = one 128-sample block I with up to two 256-sample blocks J (2 x 256 int32 TMEM columns = the whole
+// tensor memory of an SM).  grid = (groups, row splits): CTA (g, s) streams the 128-row blocks s, s + splits, ...
+// of the tile and keeps its accumulators in TMEM for the whole kernel; at the end it adds them to a global
+// u64 delta matrix with atomics (int32 is enough inside a launch: a tile has < 2^31 rows).
+//
+// Per 128-row block:
+//   warp 0      bulk-copies the raw rows (contiguous bytes) into a 2-stage ring
+//   warps 2-9   MAC filter (masked popcount of every row, rows outside [mac, N - mac] contribute zeros), then expand
+//               the presence bits of the needed sample words to s8 bytes 0x00 / 0xFF (= -1; (-1)(-1) = 1) into
+//               MN-major core matrices (16 samples x 8 rows), 2 stages
+//   warp 1      one elected thread issues 4 (K = 32 rows each) x up to 2 tcgen05.mma  D_J += A_I^T-view * B_J
+//               (both operands MN-major: element (sample, row))
+#pragma once
+#include "kg_common.cuh"
+#include "kg_tc_ptx.cuh"
+
+#define KG_K_ROWS 128
+#define KG_K_THREADS 320
+#define KG_K_EXPAND_WARP0 2
+#define KG_K_EXPAND_THREADS 256
+#define KG_K_STAGES 2
+#define KG_K_RAW_STAGES 2
+#define KG_K_BT_BYTES (KG_K_ROWS * 256)   // one B tile stage: 128 rows x 256 samples
+#define KG_K_AT_BYTES (KG_K_ROWS * 128)   // separate A tile stage: 128 rows x 128 samples
+#define KG_K_STAGE_BYTES (2 * KG_K_BT_BYTES + KG_K_AT_BYTES)
+
+struct KgKinGroup {
+	int32_t i_blk;     // 128-sample block of the A operand (rows of G)
+	int32_t j2[2];     // 256-sample blocks of the B operands (columns of G); -1 = unused
+	int32_t a_in;      // B tile (0 / 1) that already contains the samples of block i_blk, or -1: expand A separately
+};
+
+struct KgKinTcParams {
+	const uint64_t *rows;       // raw tile, 16-byte aligned
+	uint64_t n_rows;
+	uint32_t w_file;
+	const uint64_t *file_mask;  // [w_file] used columns (MAC filter counts only these)
+	uint32_t n_used, min_count;
+	const KgKinGroup *groups;
+	unsigned long long *delta;  // [ld][ld] co-presence counts in FILE column order, entries (a, b <= a)
+	uint32_t ld;                // 64 * w_file
+	unsigned long long *kept_count;
+};
+
+__host__ __device__ inline size_t kg_kin_tc_smem_bytes(uint32_t w_file) {
+	return 1024 + (size_t)KG_K_STAGES * KG_K_STAGE_BYTES + (size_t)KG_K_RAW_STAGES * (KG_K_ROWS * 8u * (w_file + 1)) +
+	       (size_t)w_file * 8 + KG_K_RAW_STAGES * KG_K_ROWS + 256;
+}
+
+// 8 presence bits -> 8 bytes 0xFF / 0x00 (byte j <- bit 7 - j, see kg_scan_filter.cuh: both operands of the Gram use
+// the same permutation inside every 8 samples, so it is undone when the accumulators are written out)
+__device__ __forceinline__ uint2 kg_kin_spread8(uint32_t byte) {
+	const uint64_t v = (uint64_t)byte * 0x8040201008040201ull;
+	uint2 r;
+	// prmt selector nibble 8 + k: every bit of result byte k = the sign bit of source byte k  (0x00 / 0xFF)
+	asm("prmt.b32 %0, %1, 0, 0xba98;" : "=r"(r.x) : "r"((uint32_t)v));
+	asm("prmt.b32 %0, %1, 0, 0xba98;" : "=r"(r.y) : "r"((uint32_t)(v >> 32)));
+	return r;
+}
+
+__global__ void __launch_bounds__(KG_K_THREADS, 1) kg_kinship_tc_kernel(const KgKinTcParams prm) {
+	extern __shared__ uint8_t kg_k_smem_raw[];
+	uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)kg_k_smem_raw + 1023) & ~(uintptr_t)1023);
+	uint8_t *sStage = base;
+	const uint32_t raw_stage_bytes = KG_K_ROWS * 8u * (prm.w_file + 1);
+	uint8_t *sRaw = sStage + KG_K_STAGES * KG_K_STAGE_BYTES;
+	uint64_t *sMask = reinterpret_cast<uint64_t *>(sRaw + KG_K_RAW_STAGES * raw_stage_bytes);
+	uint8_t *sKeep = reinterpret_cast<uint8_t *>(sMask + prm.w_file);            // [raw stages][128]
+	uint64_t *bars = reinterpret_cast<uint64_t *>(sKeep + KG_K_RAW_STAGES * KG_K_ROWS);
+	uint64_t *raw_full = bars, *raw_empty = bars + KG_K_RAW_STAGES;
+	uint64_t *st_full = raw_empty + KG_K_RAW_STAGES, *st_empty = st_full + KG_K_STAGES;
+	uint64_t *done = st_empty + KG_K_STAGES;
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
+
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const KgKinGroup grp = prm.groups[blockIdx.x];
+	const uint32_t n_blocks = (uint32_t)((prm.n_rows + KG_K_ROWS - 1) / KG_K_ROWS);
+	const uint32_t row_bytes = 8u * (prm.w_file + 1);
+	const bool has2 = grp.j2[1] >= 0;
+
+	if (threadIdx.x == 0) {
+		for (int i = 0; i < KG_K_RAW_STAGES; i++) { kg_mbar_init(&raw_full[i], 1); kg_mbar_init(&raw_empty[i], KG_K_EXPAND_THREADS / 32); }
+		for (int i = 0; i < KG_K_STAGES; i++) { kg_mbar_init(&st_full[i], KG_K_EXPAND_THREADS / 32); kg_mbar_init(&st_empty[i], 1); }
+		kg_mbar_init(done, 1);
+		kg_fence_mbar_init();
+	}
+	for (uint32_t i = threadIdx.x; i < prm.w_file; i += blockDim.x) sMask[i] = prm.file_mask[i];
+	if (warp == 1) kg_tmem_alloc(tmem_slot, 512);
+	kg_tc_fence_before();
+	__syncthreads();
+	kg_tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot;
+
+	if (warp == 0) {
+		// ===================== producer =====================
+		if (lane == 0) {
+			uint32_t it = 0;
+			for (uint32_t blk = blockIdx.y; blk < n_blocks; blk += gridDim.y, it++) {
+				const uint32_t st = it % KG_K_RAW_STAGES, use = it / KG_K_RAW_STAGES;
+				kg_mbar_wait(&raw_empty[st], (use & 1) ^ 1);
+				const uint64_t r0 = (uint64_t)blk * KG_K_ROWS;
+				const uint32_t valid = (uint32_t)min((uint64_t)KG_K_ROWS, prm.n_rows - r0);
+				const uint32_t bytes = valid * row_bytes, bulk = bytes & ~15u;
+				const uint8_t *src = reinterpret_cast<const uint8_t *>(prm.rows) + r0 * row_bytes;
+				uint8_t *dst = sRaw + st * raw_stage_bytes;
+				if (bytes != bulk) *reinterpret_cast<uint64_t *>(dst + bulk) = *reinterpret_cast<const uint64_t *>(src + bulk);
+				kg_mbar_arrive_expect_tx(&raw_full[st], bulk);
+				if (bulk) kg_bulk_g2s(dst, src, bulk, &raw_full[st]);
+			}
+		}
+	} else if (warp == 1) {
+		// ===================== MMA issuer =====================
+		const uint32_t idesc = kg_umma_idesc_i8(128, 256, true, true, true, true);
+		const uint32_t s_addr = kg_smem_u32(sStage);
+		// MN-major, no swizzle: 16 samples contiguous, 8 rows 16 B apart; SBO = next 16 samples (128 B),
+		// LBO = next 8 rows (one row of core matrices = tile samples * 8 bytes)
+		const uint64_t b_desc0 = kg_umma_smem_desc(s_addr, 2048, 128);
+		const uint32_t a_off = grp.a_in >= 0 ? (uint32_t)grp.a_in * KG_K_BT_BYTES + (uint32_t)(grp.i_blk & 1) * 1024 : 2 * KG_K_BT_BYTES;
+		const uint64_t a_desc0 = kg_umma_smem_desc(s_addr + a_off, grp.a_in >= 0 ? 2048 : 1024, 128);
+		const uint32_t a_kstep = grp.a_in >= 0 ? (4 * 2048) >> 4 : (4 * 1024) >> 4;   // 32 rows = 4 row blocks, in 16-byte units
+		uint32_t it = 0;
+		for (uint32_t blk = blockIdx.y; blk < n_blocks; blk += gridDim.y, it++) {
+			const uint32_t st = it % KG_K_STAGES, use = it / KG_K_STAGES;
+			kg_mbar_wait(&st_full[st], use & 1);
+			kg_tc_fence_after();
+			if (kg_elect_one()) {
+				const uint64_t st_units = (uint64_t)(st * (KG_K_STAGE_BYTES >> 4));
+#pragma unroll
+				for (uint32_t ks = 0; ks < 4; ks++) {
+					const uint64_t ad = a_desc0 + st_units + ks * a_kstep;
+					kg_umma_i8(tmem_base, ad, b_desc0 + st_units + ks * 512, idesc, (it | ks) != 0);
+					if (has2) kg_umma_i8(tmem_base + 256, ad, b_desc0 + st_units + (KG_K_BT_BYTES >> 4) + ks * 512, idesc, (it | ks) != 0);
+				}
+				kg_umma_commit(&st_empty[st]);
+			}
+			__syncwarp();
+		}
+		if (kg_elect_one()) kg_umma_commit(done);
+		__syncwarp();
+	} else {
+		// ===================== expanders (and, at the end, the accumulator flush) =====================
+		const uint32_t t = threadIdx.x - KG_K_EXPAND_WARP0 * 32;
+		const uint32_t r = t & (KG_K_ROWS - 1), sub = t >> 7;
+		// work items of a stage: item i < 4 nb -> word (i % 4) of B tile (i / 4); then the 2 words of a separate A tile
+		const uint32_t nb = has2 ? 2u : 1u;
+		const uint32_t n_items = 4 * nb + (grp.a_in < 0 ? 2u : 0u);
+		const uint32_t s_addr = kg_smem_u32(sStage);
+		unsigned long long kept_local = 0;
+		uint32_t it = 0;
+		for (uint32_t blk = blockIdx.y; blk < n_blocks; blk += gridDim.y, it++) {
+			const uint32_t rst = it % KG_K_RAW_STAGES, ruse = it / KG_K_RAW_STAGES;
+			kg_mbar_wait(&raw_full[rst], ruse & 1);
+			const uint64_t *row = reinterpret_cast<const uint64_t *>(sRaw + rst * raw_stage_bytes + r * row_bytes) + 1;
+			// MAC filter of load_kmers (:117-121): one thread per row
+			if (sub == 0) {
+				const uint64_t grow = (uint64_t)blk * KG_K_ROWS + r;
+				uint32_t n1 = 0;
+				if (grow < prm.n_rows)
+					for (uint32_t k = 0; k < prm.w_file; k++) n1 += __popcll(row[k] & sMask[k]);
+				const bool keep = grow < prm.n_rows && n1 >= prm.min_count && n1 + prm.min_count <= prm.n_used;
+				sKeep[rst * KG_K_ROWS + r] = keep ? 1 : 0;
+				kept_local += __popc(__ballot_sync(0xffffffffu, keep));
+			}
+			asm volatile("bar.sync 1, %0;" ::"n"(KG_K_EXPAND_THREADS) : "memory");
+			const bool keep = sKeep[rst * KG_K_ROWS + r] != 0;
+
+			const uint32_t st = it % KG_K_STAGES, use = it / KG_K_STAGES;
+			kg_mbar_wait(&st_empty[st], (use & 1) ^ 1);
+			const uint32_t st_base = s_addr + st * KG_K_STAGE_BYTES + (r & 7) * 16;
+			for (uint32_t i = sub; i < n_items; i += 2) {
+				uint32_t fw, dst_off, lbo;   // file word, byte offset of its first sample chunk in the stage, row-block stride
+				if (i < 4 * nb) {
+					const uint32_t b = i >> 2, wt = i & 3;
+					fw = (uint32_t)grp.j2[b] * 4 + wt;
+					dst_off = b * KG_K_BT_BYTES + wt * 512;
+					lbo = 2048;
+				} else {
+					const uint32_t wt = i - 4 * nb;
+					fw = (uint32_t)grp.i_blk * 2 + wt;
+					dst_off = 2 * KG_K_BT_BYTES + wt * 512;
+					lbo = 1024;
+				}
+				const uint64_t w = (keep && fw < prm.w_file) ? row[fw] : 0ull;
+				const uint32_t dst = st_base + dst_off + (r >> 3) * lbo;
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					const uint32_t h = (uint32_t)(w >> (16 * q)) & 0xFFFFu;
+					const uint2 lo = kg_kin_spread8(h & 0xFFu), hi = kg_kin_spread8(h >> 8);
+					asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + q * 128), "r"(lo.x), "r"(lo.y), "r"(hi.x), "r"(hi.y)
+					             : "memory");
+				}
+			}
+			kg_fence_proxy_async();
+			__syncwarp();
+			if (lane == 0) {
+				kg_mbar_arrive(&st_full[st]);
+				kg_mbar_arrive(&raw_empty[rst]);
+			}
+		}
+		if (lane == 0 && kept_local && blockIdx.x == 0) atomicAdd(prm.kept_count, kept_local);
+
+		// ---- flush: TMEM accumulators -> global u64 delta (lower triangle, file column order)
+		if (warp < KG_K_EXPAND_WARP0 + 4 && n_blocks > blockIdx.y) {
+			kg_mbar_wait(done, 0);
+			kg_tc_fence_after();
+			const uint32_t q4 = warp & 3;
+			const uint32_t a = (uint32_t)grp.i_blk * 128 + q4 * 32 + lane;   // operand row index (permuted inside 8)
+			const uint32_t a_col = (a & ~7u) | (7u - (a & 7u));             // file column of that operand row
+			for (int b = 0; b < 2; b++) {
+				if (grp.j2[b] < 0) continue;
+				const uint32_t taddr = tmem_base + b * 256 + ((q4 * 32u) << 16);
+				for (uint32_t c0 = 0; c0 < 256; c0 += 16) {
+					uint32_t v[16];
+					kg_tmem_ld16(taddr + c0, v);
+					kg_tmem_ld_wait();
+#pragma unroll
+					for (int j = 0; j < 16; j++) {
+						const uint32_t bb = (uint32_t)grp.j2[b] * 256 + c0 + j;
+						const uint32_t b_col = (bb & ~7u) | (7u - (bb & 7u));
+						if (v[j] != 0 && b_col <= a_col && a_col < prm.ld)
+							atomicAdd(prm.delta + (size_t)a_col * prm.ld + b_col, (unsigned long long)v[j]);
+					}
+				}
+			}
+		}
+	}
+	kg_tc_fence_before();
+	__syncthreads();
+	if (warp == 1) kg_tmem_dealloc(tmem_base, 512);
+}
+
+// accum (memory order, see kg_kinship_begin) += delta (file order); then delta = 0 for the next tile
+__global__ void kg_kinship_fold_kernel(unsigned long long *__restrict__ delta, uint32_t ld, const uint32_t *__restrict__ map_mem,
+                                       uint32_t n_used, unsigned long long *__restrict__ accum,
+                                       unsigned long long *__restrict__ delta_kept) {
+	const uint64_t total = (uint64_t)n_used * n_used;
+	for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (uint64_t)gridDim.x * blockDim.x) {
+		const uint32_t i = (uint32_t)(idx / n_used), j = (uint32_t)(idx % n_used);
+		if (j > i) continue;
+		const uint32_t mi = map_mem[i], mj = map_mem[j];
+		const uint32_t a = (mi >> 6) * 64 + (mi & 63), b = (mj >> 6) * 64 + (mj & 63);
+		const unsigned long long v = delta[(size_t)max(a, b) * ld + min(a, b)];
+		if (v) accum[idx] += v;
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		accum[total] += *delta_kept;
+	}
+}

@@ -3,6 +3,7 @@
 #pragma once
 #include <cfloat>
 
+#include "kg_kinship_tc.cuh"
 #include "kg_scan_filter.cuh"
 
 static void kg_tc_free(KgTcState *tc) {
@@ -430,8 +431,75 @@ static kg_status kg_tc_filter_debug(kg_ctx *c, const uint64_t *dev_in, uint64_t 
 	return KG_OK;
 }
 
-static kg_status kg_tc_prepare_kinship(kg_ctx *c) { (void)c; return KG_OK; }
-static kg_status kg_tc_kinship_tile(kg_ctx *c, const KgRowView &view) {
-	(void)view;
-	KG_FAIL(c, KG_ERR_INVALID, "tensor kinship engine not built");
+// ------------------------------------------------------------------------------------- kinship (tensor engine)
+static kg_status kg_tc_prepare_kinship(kg_ctx *c) {
+	KgTcState &tc = c->tc;
+	tc.kin_ready = false;
+	const uint32_t ld = 64 * c->w_file;
+	const size_t smem = kg_kin_tc_smem_bytes(c->w_file);
+	if (smem > 227u * 1024) { tc.why_unavailable = "row block does not fit shared memory next to the operand stages"; return KG_OK; }
+	// tile groups over the lower triangle in file column order
+	std::vector<KgKinGroup> groups;
+	const uint32_t n_i = (ld + 127) / 128;
+	for (uint32_t I = 0; I < n_i; I++) {
+		const uint32_t n_j = I / 2 + 1;   // 256-sample blocks 0 .. I/2 intersect the columns <= the rows of block I
+		for (uint32_t j = 0; j < n_j; j += 2) {
+			KgKinGroup g;
+			g.i_blk = (int32_t)I;
+			g.j2[0] = (int32_t)j;
+			g.j2[1] = j + 1 < n_j ? (int32_t)(j + 1) : -1;
+			g.a_in = g.j2[0] == (int32_t)(I / 2) ? 0 : (g.j2[1] == (int32_t)(I / 2) ? 1 : -1);
+			groups.push_back(g);
+		}
+	}
+	if (groups.size() > 4096) { tc.why_unavailable = "too many sample tiles"; return KG_OK; }
+	cudaFree(tc.d_kin_groups); cudaFree(tc.d_kin_delta);
+	tc.d_kin_groups = nullptr; tc.d_kin_delta = nullptr;
+	cudaError_t e = cudaMalloc((void **)&tc.d_kin_groups, groups.size() * sizeof(KgKinGroup));
+	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc kinship groups: %s", cudaGetErrorString(e));
+	KG_CUDA(c, cudaMemcpy(tc.d_kin_groups, groups.data(), groups.size() * sizeof(KgKinGroup), cudaMemcpyHostToDevice));
+	e = cudaMalloc((void **)&tc.d_kin_delta, ((size_t)ld * ld + 1) * sizeof(unsigned long long));
+	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc kinship delta: %s", cudaGetErrorString(e));
+	KG_CUDA(c, cudaFuncSetAttribute(kg_kinship_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	tc.kin_groups = (uint32_t)groups.size();
+	tc.kin_smem = smem;
+	tc.kin_ready = true;
+	return KG_OK;
+}
+
+// G (file order) of one raw tile on the tensor cores, folded into the caller-visible accumulator (memory order)
+static kg_status kg_tc_kinship_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_rows) {
+	KgTcState &tc = c->tc;
+	const uint64_t *dev = nullptr;
+	kg_status st = kg_tc_aligned_tile(c, dev_in, n_rows, &dev);
+	if (st != KG_OK) return st;
+	const uint32_t ld = 64 * c->w_file;
+	KG_CUDA(c, cudaMemsetAsync(tc.d_kin_delta, 0, ((size_t)ld * ld + 1) * sizeof(unsigned long long), c->stream));
+	KgKinTcParams k;
+	memset(&k, 0, sizeof k);
+	k.rows = dev;
+	k.n_rows = n_rows;
+	k.w_file = c->w_file;
+	k.file_mask = c->d_file_mask;
+	k.n_used = (uint32_t)c->n_used;
+	k.min_count = (uint32_t)std::min<uint64_t>(c->kin_min_count, 0xFFFFFFFFull);
+	k.groups = tc.d_kin_groups;
+	k.delta = tc.d_kin_delta;
+	k.ld = ld;
+	k.kept_count = tc.d_kin_delta + (size_t)ld * ld;
+	const uint32_t n_blocks = (uint32_t)((n_rows + KG_K_ROWS - 1) / KG_K_ROWS);
+	const uint32_t splits = std::max(1u, std::min<uint32_t>(n_blocks, (uint32_t)c->sm_count / std::max(1u, tc.kin_groups)));
+	dim3 grid(tc.kin_groups, splits);
+	timing_begin(c, KG_KERNEL_KINSHIP, n_rows);
+	kg_kinship_tc_kernel<<<grid, KG_K_THREADS, tc.kin_smem, c->stream>>>(k);
+	timing_end(c);
+	KG_LAUNCH_CHECK(c);
+	const uint64_t n2 = (uint64_t)c->n_used * c->n_used;
+	const unsigned fg = (unsigned)std::min<uint64_t>((n2 + 255) / 256, (uint64_t)c->sm_count * 8);
+	timing_begin(c, KG_KERNEL_AUX, 0);
+	kg_kinship_fold_kernel<<<std::max(fg, 1u), 256, 0, c->stream>>>(tc.d_kin_delta, ld, c->d_map_mem, (uint32_t)c->n_used,
+	                                                                 c->d_accum, tc.d_kin_delta + (size_t)ld * ld);
+	timing_end(c);
+	KG_LAUNCH_CHECK(c);
+	return KG_OK;
 }

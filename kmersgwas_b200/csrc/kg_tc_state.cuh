@@ -34,6 +34,10 @@ struct KgTcState {
 	size_t smem_bytes = 0;
 	uint64_t *d_aligned = nullptr;         // realigned copy of a tile whose device pointer is not 16-byte aligned
 	size_t aligned_cap = 0;
-	// kinship: int32 partial Gram flush scratch
+	// kinship tensor engine: tile groups, per-tile co-presence delta in file column order (+ kept-row counter)
+	struct KgKinGroup *d_kin_groups = nullptr;
+	unsigned long long *d_kin_delta = nullptr;
+	uint32_t kin_groups = 0;
+	size_t kin_smem = 0;
 	void *d_scratch = nullptr;
 };

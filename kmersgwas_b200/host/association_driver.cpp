@@ -10,6 +10,7 @@
 #include "association_driver.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -23,6 +24,23 @@ void check(kg_ctx *ctx, kg_status st, const char *what) {
 	if (st != KG_OK) throw std::runtime_error(std::string(what) + ": " + kg_last_error(ctx));
 }
 }  // namespace
+
+// Host threads for the per-phenotype replay tasks: KMERSGWAS_HOST_THREADS if set, else the cores of the box
+// divided by the ranks sharing it (torchrun's LOCAL_WORLD_SIZE), at most 32.
+unsigned kgh_host_threads() {
+	if (const char *e = getenv("KMERSGWAS_HOST_THREADS")) {
+		const int v = atoi(e);
+		if (v > 0) return (unsigned)v;
+	}
+	unsigned hw = std::thread::hardware_concurrency();
+	if (hw == 0) hw = 4;
+	unsigned ranks = 1;
+	if (const char *e = getenv("LOCAL_WORLD_SIZE")) {
+		const int v = atoi(e);
+		if (v > 0) ranks = (unsigned)v;
+	}
+	return std::max(1u, std::min(hw / ranks, 32u));
+}
 
 // ------------------------------------------------------------------------------------------ pool
 KghTaskPool::KghTaskPool(unsigned n_threads) {
@@ -131,11 +149,7 @@ static bool replay_in_flight(kg_ctx *ctx, BestAssociationsHeap *const *heaps, st
 		std::vector<std::size_t> at(S.bucket_off.begin(), S.bucket_off.end() - 1);
 		for (std::size_t i = 0; i < n_hits; i++) S.bucketed[at[S.hit_buf[i].pheno]++] = S.hit_buf[i];
 	}
-	if (!S.pool) {
-		unsigned hw = std::thread::hardware_concurrency();
-		if (hw == 0) hw = 4;
-		S.pool = new KghTaskPool(std::max(1u, std::min<unsigned>(std::min<unsigned>(hw, 32u), (unsigned)P)));
-	}
+	if (!S.pool) S.pool = new KghTaskPool(std::min<unsigned>(kgh_host_threads(), (unsigned)P));
 	kg_hit *const base = S.bucketed.data();
 	const std::vector<std::size_t> &off = S.bucket_off;
 	S.pool->run(P, [&](std::size_t j) {
@@ -233,17 +247,27 @@ void kgh_associate_rows(kg_ctx *ctx, BestAssociationsHeap *const *heaps, std::si
 }
 
 void kgh_merge_hit_log(std::vector<kg_hit> &all, uint64_t kept, BestAssociationsHeap *const *final_heaps, std::size_t P) {
-	std::sort(all.begin(), all.end(), [](const kg_hit &a, const kg_hit &b) {
-		return a.pheno != b.pheno ? a.pheno < b.pheno : a.row < b.row;
-	});
-	std::size_t i = 0;
-	for (std::size_t j = 0; j < P; j++) {
-		std::size_t e = i;
-		while (e < all.size() && all[e].pheno == j) e++;
-		final_heaps[j]->add_hits(all.data() + i, e - i);
-		final_heaps[j]->note_tested_rows((std::size_t)(kept - (e - i)));
-		i = e;
+	// group by phenotype (stable counting sort), then one task per phenotype: order by row (shard logs are already
+	// row-sorted, so this is usually a no-op check) and replay through the final heap
+	std::vector<std::size_t> off(P + 1, 0);
+	for (const kg_hit &h : all)
+		if (h.pheno < P) off[h.pheno + 1]++;
+	for (std::size_t j = 0; j < P; j++) off[j + 1] += off[j];
+	std::vector<kg_hit> grouped(off[P]);
+	{
+		std::vector<std::size_t> at(off.begin(), off.end() - 1);
+		for (const kg_hit &h : all)
+			if (h.pheno < P) grouped[at[h.pheno]++] = h;
 	}
+	std::vector<kg_hit>().swap(all);
+	KghTaskPool pool(std::min<unsigned>(kgh_host_threads(), (unsigned)std::max<std::size_t>(P, 1)));
+	pool.run(P, [&](std::size_t j) {
+		kg_hit *b = grouped.data() + off[j], *e = grouped.data() + off[j + 1];
+		auto by_row = [](const kg_hit &x, const kg_hit &y) { return x.row < y.row; };
+		if (!std::is_sorted(b, e, by_row)) std::sort(b, e, by_row);
+		final_heaps[j]->add_hits(b, (std::size_t)(e - b));
+		final_heaps[j]->note_tested_rows((std::size_t)(kept - (uint64_t)(e - b)));
+	});
 }
 
 void kgh_merge_shards(std::vector<AssociationDriverState *> &shards, BestAssociationsHeap *const *final_heaps,

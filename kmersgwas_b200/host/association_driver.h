@@ -20,6 +20,8 @@
 #include "best_associations_heap.h"
 #include "kmersgwas_b200.h"
 
+unsigned kgh_host_threads();
+
 // Minimal fork-join pool: run(n, fn) calls fn(i) for i in [0, n) on the workers and the calling thread.
 class KghTaskPool {
 	public:

@@ -216,8 +216,9 @@ def test_hit_overflow_is_reported_and_recoverable(kg):
 
 
 # ------------------------------------------------------------------------------ kinship
-@pytest.mark.parametrize("n_file", [64, 65, 129, 241])
-def test_kinship_matches_oracle(kg, n_file):
+@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("n_file", [64, 65, 129, 241, 300, 1135])
+def test_kinship_matches_oracle(kg, n_file, engine):
     import math
     n_rows = 5000
     table = S.synth_table(50 + n_file, n_rows, n_file)
@@ -225,6 +226,7 @@ def test_kinship_matches_oracle(kg, n_file):
     mc = int(math.ceil(n_file * 0.05))
     K_o, cnt_o = S.oracle_kinship(table, n_file, idx // 64, idx % 64, mc)
     ctx = kg.Context.identity(n_file)
+    ctx.set_option(kg.OPT_KINSHIP_ENGINE, engine)
     ctx.kinship_begin(mc)
     for r0 in range(0, n_rows, 1700):   # several tiles accumulate
         n = min(1700, n_rows - r0)
@@ -235,11 +237,13 @@ def test_kinship_matches_oracle(kg, n_file):
     ctx.close()
 
 
+@pytest.mark.parametrize("engine", [1, 2])
 @pytest.mark.parametrize("name", ["identity_n131", "plumbing_n64", "ties_n96", "thaliana_n1135"])
-def test_kinship_matches_reference_golden(kg, name):
+def test_kinship_matches_reference_golden(kg, name, engine):
     import hashlib
     g = S.Golden(name)
     ctx = kg.Context.identity(g.n_file)
+    ctx.set_option(kg.OPT_KINSHIP_ENGINE, engine)
     ctx.kinship_begin(int(g.z["kin_min_count"]))
     ctx.kinship_submit(g.table, g.n_rows)
     K, cnt = ctx.kinship_fetch()
@@ -251,7 +255,8 @@ def test_kinship_matches_reference_golden(kg, name):
     ctx.close()
 
 
-def test_kinship_subset_columns(kg):
+@pytest.mark.parametrize("engine", [1, 2])
+def test_kinship_subset_columns(kg, engine):
     n_file, n_used = 300, 150
     rng = np.random.default_rng(2)
     names = [f"s{i}" for i in range(n_file)]
@@ -260,6 +265,7 @@ def test_kinship_subset_columns(kg):
     table = S.synth_table(61, 3000, n_file)
     K_o, cnt_o = S.oracle_kinship(table, n_file, mw, mb, 8)
     ctx = kg.Context(n_file, mw, mb)
+    ctx.set_option(kg.OPT_KINSHIP_ENGINE, engine)
     ctx.kinship_begin(8)
     ctx.kinship_submit(table, 3000)
     K, cnt = ctx.kinship_fetch()
