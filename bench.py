@@ -404,6 +404,7 @@ def our_arm(args):
                 "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "launches": dom_launches, "avg_launch_ms": dom_ms / max(dom_launches, 1),
                 "kernel_ms_share_of_step": {k_: v[0] / ms_dev for k_, v in kt.items() if v[1]},
+                "kernels": {k_: {"ms_per_launch": v[0] / v[1], "launches": v[1], "rows_per_launch": v[2] / v[1]} for k_, v in kt.items() if v[1]},
                 "note": (f"algorithmic bytes = {row_bytes} B/row; at P={p} the exact fp32-order kernel is bound by the FP32 add pipe "
                          f"({t_fp32_row * 1e9:.2f} ns/row lower bound = {1 / t_fp32_row / 1e9:.2f} G rows/s), not by HBM"),
             },

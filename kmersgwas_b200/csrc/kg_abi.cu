@@ -637,6 +637,18 @@ static KgScanParams scan_params(kg_ctx *c, const KgRowView &view, uint64_t first
 	return prm;
 }
 
+static bool is_device_pointer(const void *p) {
+	cudaPointerAttributes attr;
+	if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+static kg_status scan_submit_one(kg_ctx *c, const uint64_t *rows, uint64_t n_rows, uint64_t first_row_id);
+
+// Host tiles are cut into sub-tiles so that the H2D copy of sub-tile i+1 runs under the kernels of sub-tile i
+// (two device slots); device tiles are scanned in place, in one launch.
+static const uint64_t kHostSubTileRows = 1ull << 20;
+
 extern "C" kg_status kg_scan_submit(kg_ctx *c, const uint64_t *rows, uint64_t n_rows, uint64_t first_row_id) {
 	if (!c) return KG_ERR_INVALID;
 	if (!c->d_y_lane) KG_FAIL(c, KG_ERR_STATE, "kg_scan_submit: call kg_scan_set_phenotypes first");
@@ -644,6 +656,17 @@ extern "C" kg_status kg_scan_submit(kg_ctx *c, const uint64_t *rows, uint64_t n_
 	if (!rows) KG_FAIL(c, KG_ERR_INVALID, "kg_scan_submit: null rows");
 	if (n_rows >= (1ull << 31)) KG_FAIL(c, KG_ERR_INVALID, "kg_scan_submit: tile of %llu rows too large (max 2^31-1)", (unsigned long long)n_rows);
 	KG_CUDA(c, cudaSetDevice(c->device));
+	if (n_rows <= kHostSubTileRows || is_device_pointer(rows)) return scan_submit_one(c, rows, n_rows, first_row_id);
+	const size_t stride = (size_t)c->w_file + 1;
+	for (uint64_t off = 0; off < n_rows; off += kHostSubTileRows) {
+		const uint64_t n = std::min<uint64_t>(kHostSubTileRows, n_rows - off);
+		kg_status st = scan_submit_one(c, rows + off * stride, n, first_row_id + off);
+		if (st != KG_OK) return st;
+	}
+	return KG_OK;
+}
+
+static kg_status scan_submit_one(kg_ctx *c, const uint64_t *rows, uint64_t n_rows, uint64_t first_row_id) {
 	const uint64_t *dev = nullptr;
 	kg_status st = acquire_tile(c, rows, n_rows, &dev);
 	if (st != KG_OK) return st;

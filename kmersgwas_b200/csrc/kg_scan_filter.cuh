@@ -22,13 +22,15 @@
 //
 // Kernel: persistent, one CTA per SM, 128-row blocks, warp-specialised:
 //   warp 0      bulk-async-copies raw 128-row blocks (contiguous 128 * 8(1+W) bytes) into a 2-stage ring
-//   warps 2-9   expand presence bits -> u8 {0,0x80} with one 64-bit multiply per presence byte and store them with
-//               tcgen05.st straight into TENSOR MEMORY (A operand from TMEM: lane = row, 4 bytes of K per column),
-//               8 stages of 128 columns; no shared-memory round trip and no proxy fence for A
+//   warps 2-13  expand presence bits -> u8 {0,0x80} with one 64-bit multiply per presence byte and store them with
+//               tcgen05.st straight into TENSOR MEMORY (A operand from TMEM: lane = row, 4 bytes of K per column);
+//               TMEM holds the two accumulator buffers (2 x P_pad columns) and the A stages: at N = 1135, P = 101 that
+//               is 2 x 112 + 2 x 144 columns = two stages of half a row block each (every stage hand-off costs a
+//               barrier round trip of ~1.5 k cycles, so few large stages beat many small ones)
 //   warp 1      one elected thread issues tcgen05.mma kind::i8 (M = 128, N = P_pad, K = 32 per instruction, A from
 //               TMEM, B from shared memory) into a double-buffered TMEM accumulator; B (quantised phenotypes,
 //               P_pad x K_pad s8, K-major core matrices, no swizzle) stays resident in shared memory
-//   warps 10-17 epilogue (two sets of 4 warps alternate blocks, one accumulator buffer each): tcgen05.ld of the 128 x P_pad accumulators; column 0 of B is all-ones over the used
+//   warps 14-21 epilogue (two sets of 4 warps alternate blocks, one accumulator buffer each): tcgen05.ld of the 128 x P_pad accumulators; column 0 of B is all-ones over the used
 //               columns, so its accumulator is the row popcount (MAC filter) for free; pass 1 takes max |Q| over the
 //               row with 3-input min/max and rules the whole row out against the loosest column bound; rows that
 //               survive (rare) are appended to a global row list for the exact kernel
@@ -37,13 +39,14 @@
 #include "kg_tc_ptx.cuh"
 
 #define KG_F_ROWS 128            // rows per block = UMMA M
-#define KG_F_CHUNK_COLS 128      // presence columns per A stage (two u64 words per row)
-#define KG_F_A_STAGE_TCOLS (KG_F_CHUNK_COLS / 4)   // TMEM columns of one A stage (4 u8 per 32-bit column)
-#define KG_F_A_STAGES 8          // A stages in tensor memory: 8 x 32 columns next to the 2 x 128 accumulator columns
-#define KG_F_TMEM_COLS 512
+#define KG_F_MAX_A_STAGES 8      // A stages live in tensor memory next to the two accumulator buffers:
+#define KG_F_TMEM_COLS 512       //   2 x p_pad accumulator columns + a_stages x 16 a_words columns <= 512
 #define KG_F_RAW_STAGES 4
 #define KG_F_EXPAND_WARP0 2
-#define KG_F_EXPAND_WARPS 8
+#ifndef KG_F_EXPAND_WARPS
+#define KG_F_EXPAND_WARPS 12        // KG_F_EXPAND_WARPS / 4 per TMEM lane quarter share a stage's words
+#endif
+#define KG_F_NSUB (KG_F_EXPAND_WARPS / 4)
 #define KG_F_EPI_WARP0 (KG_F_EXPAND_WARP0 + KG_F_EXPAND_WARPS)
 #define KG_F_EPI_WARPS 8         // two sets of 4 (one warp per TMEM lane quarter); set s owns accumulator buffer s
 #define KG_F_THREADS ((KG_F_EPI_WARP0 + KG_F_EPI_WARPS) * 32)
@@ -64,13 +67,16 @@ struct KgFilterParams {
 	const uint64_t *rows;      // raw tile, 16-byte aligned
 	uint64_t n_rows;
 	uint32_t w_file;           // presence words per row
-	uint32_t nc;               // A stages per block = ceil(w_file / 2)
+	uint32_t a_words;          // u64 presence words per A stage (16 TMEM columns, 2 MMAs of K = 32 each); as many as
+	                           // fit: every stage hand-off costs a barrier round trip, so few large stages win
+	uint32_t a_stages;         // 2 .. KG_F_MAX_A_STAGES
+	uint32_t nc;               // A stages per row block = ceil(w_file / a_words)
 	uint32_t p_pad;            // UMMA N (multiple of 16, <= 256): column 0 = all-ones (row popcount), the phenotypes follow
 	                           // sorted by their alpha so that the 16 columns of a group have similar bounds
-	uint32_t tcols;            // TMEM columns per accumulator buffer (power of two >= p_pad, >= 32)
+	uint32_t tcols;            // TMEM columns per accumulator buffer (= p_pad)
 	const int8_t *yq_image;    // B operand in its shared-memory byte order, b_bytes long
 	uint32_t b_bytes;          // (p_pad / 8) * sbo_b
-	uint32_t sbo_b;            // nc * 1024
+	uint32_t sbo_b;            // ceil(w_file / 2) * 1024: K_pad = 128 * ceil(w_file / 2) columns
 	const KgFilterGroupConst *gconst;   // [p_pad / 16]; groups without phenotype columns hold alpha = +inf
 	uint32_t n_used, min_count;
 	uint32_t *row_list;        // out: rows of the tile (index inside the tile) that could not be ruled out, any order
@@ -80,6 +86,7 @@ struct KgFilterParams {
 	uint64_t group_cap;        // = capacity of row_list (n_rows)
 	unsigned long long *kept_count;
 	int32_t *q_out;            // debug mode: [n_rows][p_pad] accumulators
+	uint32_t dbg;              // perf experiments only (env KG_FILTER_DEBUG): 1 skip expansion, 2 skip epilogue work, 4 skip MMAs
 };
 
 __host__ __device__ inline uint32_t kg_filter_raw_stage_bytes(uint32_t w_file) { return KG_F_ROWS * 8u * (w_file + 1); }
@@ -124,8 +131,8 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 	KgFilterGroupConst *sConst = reinterpret_cast<KgFilterGroupConst *>(sRaw + KG_F_RAW_STAGES * raw_stage_bytes);
 	uint64_t *bars = reinterpret_cast<uint64_t *>(sConst + prm.p_pad / 16);
 	uint64_t *raw_full = bars, *raw_empty = bars + KG_F_RAW_STAGES;
-	uint64_t *a_full = bars + 2 * KG_F_RAW_STAGES, *a_empty = a_full + KG_F_A_STAGES;
-	uint64_t *tm_full = a_empty + KG_F_A_STAGES, *tm_empty = tm_full + 2;
+	uint64_t *a_full = bars + 2 * KG_F_RAW_STAGES, *a_empty = a_full + KG_F_MAX_A_STAGES;
+	uint64_t *tm_full = a_empty + KG_F_MAX_A_STAGES, *tm_empty = tm_full + 2;
 	uint64_t *b_full = tm_empty + 2;
 	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_full + 1);
 
@@ -135,7 +142,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 
 	if (threadIdx.x == 0) {
 		for (int i = 0; i < KG_F_RAW_STAGES; i++) { kg_mbar_init(&raw_full[i], 1); kg_mbar_init(&raw_empty[i], KG_F_EXPAND_WARPS); }
-		for (int i = 0; i < KG_F_A_STAGES; i++) { kg_mbar_init(&a_full[i], KG_F_EXPAND_WARPS); kg_mbar_init(&a_empty[i], 1); }
+		for (int i = 0; i < KG_F_MAX_A_STAGES; i++) { kg_mbar_init(&a_full[i], KG_F_EXPAND_WARPS); kg_mbar_init(&a_empty[i], 1); }
 		for (int i = 0; i < 2; i++) { kg_mbar_init(&tm_full[i], 1); kg_mbar_init(&tm_empty[i], 4); }
 		kg_mbar_init(b_full, 1);
 		kg_fence_mbar_init();
@@ -167,6 +174,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 				uint8_t *dst = sRaw + st * raw_stage_bytes;
 				if (bytes != bulk)  // 8 trailing bytes of a ragged last block
 					*reinterpret_cast<uint64_t *>(dst + bulk) = *reinterpret_cast<const uint64_t *>(src + bulk);
+				if (prm.dbg & 8) { kg_mbar_arrive(&raw_full[st]); continue; }
 				kg_mbar_arrive_expect_tx(&raw_full[st], bulk);
 				if (bulk) kg_bulk_g2s(dst, src, bulk, &raw_full[st]);
 			}
@@ -177,63 +185,86 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 		// lane issues the tcgen05.mma / tcgen05.commit instructions.
 		const uint32_t idesc = kg_umma_idesc_i8(KG_F_ROWS, prm.p_pad, false, true, false, false);
 		const uint32_t a_tmem0 = tmem_base + 2 * prm.tcols;                             // A stage 0, K offset 0
+		const uint32_t a_stage_cols = 16 * prm.a_words;
 		const uint64_t b_desc0 = kg_umma_smem_desc(kg_smem_u32(sB), 128, prm.sbo_b);   // column chunk 0
 		kg_mbar_wait(b_full, 0);
-		uint32_t it = 0, ait = 0;
+		const uint32_t words_last = prm.w_file - (prm.nc - 1) * prm.a_words;   // words in the last stage of a row block
+		uint32_t it = 0, st = 0, st_par = 0;                                   // A stage ring position / parity
 		for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, it++) {
 			const uint32_t buf = it & 1;
 			kg_mbar_wait(&tm_empty[buf], ((it >> 1) & 1) ^ 1);
 			kg_tc_fence_after();
 			const uint32_t d_tmem = tmem_base + buf * prm.tcols;
-			for (uint32_t c = 0; c < prm.nc; c++, ait++) {
-				const uint32_t st = ait % KG_F_A_STAGES, use = ait / KG_F_A_STAGES;
-				kg_mbar_wait(&a_full[st], use & 1);
+			uint64_t bd = b_desc0;
+			for (uint32_t c = 0; c < prm.nc; c++) {
+				kg_mbar_wait(&a_full[st], st_par);
 				kg_tc_fence_after();
 				if (kg_elect_one()) {
-					// A: 8 TMEM columns per K = 32 step.  B descriptor address field is in 16-byte units: one K = 32 step =
-					// 16 units, one 128-column chunk = 64 units
-					const uint32_t at = a_tmem0 + st * KG_F_A_STAGE_TCOLS;
-					const uint64_t bd = b_desc0 + (uint64_t)(c * 64);
-#pragma unroll
-					for (uint32_t kk = 0; kk < 4; kk++) kg_umma_i8_ts(d_tmem, at + kk * 8, bd + kk * 16, idesc, (c | kk) != 0);
-					kg_umma_commit(&a_empty[st]);
+					// A: 8 TMEM columns per K = 32 step, 16 per presence word.  B descriptor address field is in 16-byte
+					// units: one K = 32 step = 16 units, one presence word = 32 units.
+					const uint32_t at = a_tmem0 + st * a_stage_cols;
+					const uint32_t ksteps = 2 * (c + 1 == prm.nc ? words_last : prm.a_words);
+					if (!(prm.dbg & 4))
+						for (uint32_t kk = 0; kk < ksteps; kk++) kg_umma_i8_ts(d_tmem, at + kk * 8, bd + kk * 16, idesc, (c | kk) != 0);
+					if (prm.dbg & 16) kg_mbar_arrive(&a_empty[st]); else kg_umma_commit(&a_empty[st]);
 				}
 				__syncwarp();
+				bd += (uint64_t)prm.a_words * 32;
+				if (++st == prm.a_stages) { st = 0; st_par ^= 1; }
 			}
 			if (kg_elect_one()) kg_umma_commit(&tm_full[buf]);
 			__syncwarp();
 		}
 	} else if (warp < KG_F_EPI_WARP0) {
 		// ===================== expanders: presence bits -> u8 A operand in tensor memory =====================
-		// thread = row (its TMEM lane) x one u64 word of the stage: 64 operand bytes = 16 TMEM columns
+		// thread = row (its TMEM lane) x two u64 words of the stage: 128 operand bytes = 32 TMEM columns
 		const uint32_t q4 = warp & 3;                                   // TMEM lane quarter of this warp
-		const uint32_t half = (warp - KG_F_EXPAND_WARP0) >> 2;          // which u64 word of the 128-column stage
+		const uint32_t sub = (warp - KG_F_EXPAND_WARP0) >> 2;           // the KG_F_NSUB warps of a lane quarter split a stage's words
 		const uint32_t r = q4 * 32 + lane;
-		const uint32_t a_taddr0 = tmem_base + 2 * prm.tcols + ((q4 * 32u) << 16) + half * 16;
-		uint32_t it = 0, ait = 0;
+		const uint32_t a_stage_cols = 16 * prm.a_words;
+		const uint32_t words_last = prm.w_file - (prm.nc - 1) * prm.a_words;
+		// my words [lo, hi) of a full stage / of the last (possibly shorter) stage of a row block
+		const uint32_t per_f = (prm.a_words + KG_F_NSUB - 1) / KG_F_NSUB, lo_f = min(sub * per_f, prm.a_words), hi_f = min(lo_f + per_f, prm.a_words);
+		const uint32_t per_l = (words_last + KG_F_NSUB - 1) / KG_F_NSUB, lo_l = min(sub * per_l, words_last), hi_l = min(lo_l + per_l, words_last);
+		const uint32_t a_taddr0 = tmem_base + 2 * prm.tcols + ((q4 * 32u) << 16);
+		uint32_t it = 0, st = 0, st_par = 1;                            // a_empty parity: the first pass finds every stage free
+		uint32_t rst = 0, r_par = 0;
 		for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, it++) {
-			const uint32_t rst = it % KG_F_RAW_STAGES, ruse = it / KG_F_RAW_STAGES;
-			kg_mbar_wait(&raw_full[rst], ruse & 1);
+			kg_mbar_wait(&raw_full[rst], r_par);
 			const uint64_t *row = reinterpret_cast<const uint64_t *>(sRaw + rst * raw_stage_bytes + r * row_bytes) + 1;
-			uint64_t w = (half < prm.w_file) ? row[half] : 0ull;
-			for (uint32_t c = 0; c < prm.nc; c++, ait++) {
-				const uint32_t st = ait % KG_F_A_STAGES, use = ait / KG_F_A_STAGES;
-				const uint32_t nxt = 2 * (c + 1) + half;
-				const uint64_t w_next = (nxt < prm.w_file) ? row[nxt] : 0ull;   // prefetch before the wait
+			for (uint32_t c = 0; c < prm.nc; c++) {
+				const bool last = c + 1 == prm.nc;
+				const uint32_t lo = last ? lo_l : lo_f, hi = last ? hi_l : hi_f;
+				const uint64_t *wp = row + c * prm.a_words;
+				// first word before the wait (its expansion overlaps the hand-off latency), the rest after it
 				uint32_t v[16];
-				kg_expand_u32((uint32_t)w, v);
-				kg_expand_u32((uint32_t)(w >> 32), v + 8);
-				kg_mbar_wait(&a_empty[st], (use & 1) ^ 1);
+				if (lo < hi && !(prm.dbg & 1)) {
+					const uint64_t w = wp[lo];
+					kg_expand_u32((uint32_t)w, v);
+					kg_expand_u32((uint32_t)(w >> 32), v + 8);
+				}
+				kg_mbar_wait(&a_empty[st], st_par);
 				kg_tc_fence_after();
-				kg_tmem_st16(a_taddr0 + st * KG_F_A_STAGE_TCOLS, v);
-				kg_tmem_st_wait();
+				const uint32_t taddr = a_taddr0 + st * a_stage_cols;
+				if (!(prm.dbg & 1)) {
+					for (uint32_t k = lo; k < hi; k++) {
+						if (k > lo) {
+							const uint64_t w = wp[k];
+							kg_expand_u32((uint32_t)w, v);
+							kg_expand_u32((uint32_t)(w >> 32), v + 8);
+						}
+						kg_tmem_st16(taddr + 16 * k, v);
+					}
+					kg_tmem_st_wait();
+				}
 				kg_tc_fence_before();
 				__syncwarp();
 				if (lane == 0) kg_mbar_arrive(&a_full[st]);
-				w = w_next;
+				if (++st == prm.a_stages) { st = 0; st_par ^= 1; }
 			}
 			__syncwarp();
 			if (lane == 0) kg_mbar_arrive(&raw_empty[rst]);
+			if (++rst == KG_F_RAW_STAGES) { rst = 0; r_par ^= 1; }
 		}
 	} else {
 		// ===================== epilogue: MAC filter + bound test =====================
@@ -264,7 +295,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 				uint32_t n1 = 0;
 				float g = 0.f, hm = 0.f;
 				uint32_t gmask = 0;   // bit k: group k could not be ruled out for this row
-				for (uint32_t c0 = 0; c0 < prm.p_pad; c0 += 32) {
+				for (uint32_t c0 = 0; c0 < ((prm.dbg & 2) ? 0u : prm.p_pad); c0 += 32) {
 					uint32_t v[16], u[16];
 					kg_tmem_ld16(taddr + c0, v);
 					const bool second = c0 + 16 < prm.p_pad;   // warp-uniform

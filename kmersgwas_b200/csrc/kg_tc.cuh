@@ -172,11 +172,20 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	}
 	const uint32_t P = c->n_pheno, N = (uint32_t)c->n_used;
 	tc.p_pad = (P + 1 + 15) / 16 * 16;  // + the all-ones column
-	tc.nc = (c->w_file + 1) / 2;
-	tc.sbo_b = tc.nc * 1024;
+	tc.sbo_b = ((c->w_file + 1) / 2) * 1024;       // K_pad = 128 * ceil(w_file / 2) bytes per B column, 1024 B per 128
 	tc.b_bytes = (tc.p_pad / 8) * tc.sbo_b;
-	tc.tcols = 32;
-	while (tc.tcols < tc.p_pad) tc.tcols *= 2;
+	tc.tcols = tc.p_pad;
+	// tensor memory: 2 accumulator buffers + the A stages (16 columns per presence word); as few, as large stages as fit
+	if (tc.p_pad <= 128) {
+		const uint32_t a_cols = KG_F_TMEM_COLS - 2 * tc.p_pad;
+		tc.a_words = std::max(1u, std::min<uint32_t>(c->w_file, a_cols / 32));           // at least two stages
+		if (const char *e = getenv("KG_FILTER_A_WORDS")) {                                // perf experiments
+			const uint32_t v = (uint32_t)atoi(e);
+			if (v >= 1 && v <= tc.a_words) tc.a_words = v;
+		}
+		tc.a_stages = std::max(2u, std::min<uint32_t>(KG_F_MAX_A_STAGES, a_cols / (16 * tc.a_words)));
+		tc.nc = (c->w_file + tc.a_words - 1) / tc.a_words;
+	}
 	if (c->min_count < 1) { tc.why_unavailable = "min_count = 0 (rows with an empty group have no finite bound)"; return KG_OK; }
 	// TMEM budget: 2 accumulator buffers of tcols columns + 8 A stages of 32 columns in 512 columns
 	if (tc.p_pad > 128) { tc.why_unavailable = "more than 127 phenotype columns per pass"; return KG_OK; }
@@ -296,6 +305,8 @@ static KgFilterParams kg_tc_filter_params(kg_ctx *c, const uint64_t *dev, uint64
 	f.n_rows = n_rows;
 	f.w_file = c->w_file;
 	f.nc = tc.nc;
+	f.a_words = tc.a_words;
+	f.a_stages = tc.a_stages;
 	f.p_pad = tc.p_pad;
 	f.tcols = tc.tcols;
 	f.yq_image = tc.d_yq;
@@ -310,6 +321,7 @@ static KgFilterParams kg_tc_filter_params(kg_ctx *c, const uint64_t *dev, uint64
 	f.group_count = tc.d_group_count;
 	f.group_cap = tc.row_list_cap;
 	f.kept_count = c->d_counters + 1;
+	if (const char *e = getenv("KG_FILTER_DEBUG")) f.dbg = (uint32_t)atoi(e);   // perf experiments only (results are wrong)
 	return f;
 }
 

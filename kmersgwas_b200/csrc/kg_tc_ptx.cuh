@@ -33,10 +33,28 @@ __device__ __forceinline__ void kg_mbar_wait(uint64_t *bar, uint32_t parity) {
 	asm volatile(
 	    "{\n\t.reg .pred p;\n\t"
 	    "KG_WAIT_%=:\n\t"
+#ifdef KG_MBAR_TEST_WAIT
+	    "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+#else
 	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+#endif
 	    "@p bra KG_DONE_%=;\n\t"
 	    "bra KG_WAIT_%=;\n\t"
 	    "KG_DONE_%=:\n\t}" ::"r"(kg_smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// for waiters that are far from the critical path: poll with a back-off so that they do not steal issue slots
+__device__ __forceinline__ void kg_mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+	uint32_t done = 0;
+	for (;;) {
+		asm volatile(
+		    "{\n\t.reg .pred p;\n\t"
+		    "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		    "selp.u32 %0, 1, 0, p;\n\t}"
+		    : "=r"(done) : "r"(kg_smem_u32(bar)), "r"(parity) : "memory");
+		if (done) return;
+		__nanosleep(200);
+	}
 }
 
 // ---- bulk async copy global -> shared (1-D TMA), completion on an mbarrier -----------------------

@@ -30,7 +30,7 @@ struct KgTcState {
 	std::vector<double> scale;             // [P] quantisation step s_p
 	std::vector<float> kappa;              // [P]
 	std::vector<uint8_t> degenerate;       // [P] phenotype column the bound cannot handle: always a candidate
-	uint32_t p_pad = 0, nc = 0, sbo_b = 0, b_bytes = 0, tcols = 0;
+	uint32_t p_pad = 0, nc = 0, sbo_b = 0, b_bytes = 0, tcols = 0, a_words = 0, a_stages = 0;
 	size_t smem_bytes = 0;
 	uint64_t *d_aligned = nullptr;         // realigned copy of a tile whose device pointer is not 16-byte aligned
 	size_t aligned_cap = 0;

@@ -15,7 +15,6 @@
 #include <string>
 
 namespace {
-const uint64_t kSubTileRows = 1ull << 20;   // rows per device submit: the H2D copy of sub-tile i+1 overlaps the kernels of i
 const uint64_t kMaxRoundRows = 1ull << 21;  // rows per round once the heaps are warm
 const uint64_t kMinWarmRound = 1ull << 16;
 const uint64_t kHitBudget = 1ull << 21;     // expected hits per round (the device buffer holds 1 << 22 by default)
@@ -212,10 +211,8 @@ void kgh_associate_rows(kg_ctx *ctx, BestAssociationsHeap *const *heaps, std::si
 
 		check(ctx, kg_scan_set_thresholds(ctx, S.thr.data(), (uint32_t)P), "kg_scan_set_thresholds");
 		S.h2d_small_bytes += (uint64_t)P * sizeof(double);
-		for (uint64_t off = 0; off < round; off += kSubTileRows) {
-			const uint64_t n = std::min<uint64_t>(kSubTileRows, round - off);
-			check(ctx, kg_scan_submit(ctx, rows + (done + off) * stride, n, first_row_id + done + off), "kg_scan_submit");
-		}
+		// one submit per round: the library scans device rows in place and cuts host rows into sub-tiles itself
+		check(ctx, kg_scan_submit(ctx, rows + done * stride, round, first_row_id + done), "kg_scan_submit");
 		// the device now works on this round; meanwhile replay the previous one
 		if (!replay_in_flight(ctx, heaps, P, S)) {
 			// overflow in the previous round: drop everything not replayed, redo from that round in smaller pieces
