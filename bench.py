@@ -7,7 +7,8 @@
 Workload (config.workload): the shape of BASELINE.json configs[1] -- 1135 samples, 1 phenotype + 100
 permutations (P = 101), best K = 10001, maf 0.05 / mac 5 -- on synthetic rows of the counter-based
 generator documented in oracle/oracle.c.  The full 2.3e9-row table (350 GB) does not fit one GPU's HBM, so a
-"step" is one batch of --rows-per-step rows (default 2^22 = 637 MB, larger than the 126 MB L2) pushed through
+"step" is one batch of --rows-per-step rows (default 2^23 = 1.27 GB, larger than the 126 MB L2; the reference's default
+--batch_size is 10^7 rows) pushed through
 the product's associate loop (kmersgwas_b200/host/association_driver.cpp: device scan -> candidate hits ->
 exact replay through BestAssociationsHeap); every step scans rows no earlier step saw, and the heaps carry over.
 
@@ -380,6 +381,17 @@ def our_arm(args):
         dom_ms, dom_launches, dom_rows = kt[dom]
         achieved = (dom_rows * row_bytes) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         t_fp32_row = (128 * ((n + 127) // 128)) * p / (148 * 128 * 1.965e9)
+        traffic = None
+        try:
+            tr = json.loads((ROOT / "profiles" / "r01_ncu_traffic.json").read_text())
+            if dom in tr and (n, p) == (N_SAMPLES, N_PHENO):
+                traffic = tr[dom]["dram_bytes_per_row"] * dom_rows / max(dom_launches, 1)
+        except Exception:
+            pass
+        n_pad_cols = 128 * ((64 * w_file + 127) // 128)
+        p_pad = 16 * ((p + 1 + 15) // 16)
+        tensor_ops = 2.0 * n_pad_cols * p_pad * kt["scan_filter"][2]          # int8 MACs x 2 issued by the filter
+        tensor_tops = tensor_ops / (kt["scan_filter"][0] * 1e-3) / 1e12 if kt["scan_filter"][0] > 0 else 0.0
         line = {
             "metric": "k-mers scored/sec", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -401,12 +413,15 @@ def our_arm(args):
             },
             "roofline": {
                 "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "tensor": {"achieved_int8_tops": tensor_tops, "nominal_dense_int8_tops": 4500.0, "frac_of_nominal": tensor_tops / 4500.0,
+                           "note": f"filter MMA shape per 128-row block: M=128, N={p_pad}, K={n_pad_cols}; at P={p} the int8 tensor pipe, not HBM, is "
+                                   f"the binding roofline of the scan (SURVEY 7, hard part 2)"},
                 "launches": dom_launches, "avg_launch_ms": dom_ms / max(dom_launches, 1),
                 "kernel_ms_share_of_step": {k_: v[0] / ms_dev for k_, v in kt.items() if v[1]},
                 "kernels": {k_: {"ms_per_launch": v[0] / v[1], "launches": v[1], "rows_per_launch": v[2] / v[1]} for k_, v in kt.items() if v[1]},
-                "note": (f"algorithmic bytes = {row_bytes} B/row; at P={p} the exact fp32-order kernel is bound by the FP32 add pipe "
-                         f"({t_fp32_row * 1e9:.2f} ns/row lower bound = {1 / t_fp32_row / 1e9:.2f} G rows/s), not by HBM"),
+                "note": (f"achieved = {row_bytes} algorithmic B/row x rows of the launch / CUDA-event time of the launch; the exact fp32-order "
+                         f"kernel (scan_exact / scan_refine) is bound by the FP32 add pipe ({t_fp32_row * 1e9:.2f} ns/row at P={p}), not by HBM"),
             },
             "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": R * row_bytes + (io3[0] - io2[0]) // K,
                     "d2h_bytes_per_step": (io3[1] - io2[1]) // K, "ms_per_step": ms_e2e / K,
@@ -507,7 +522,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rows-per-step", type=int, default=1 << 22)
+    ap.add_argument("--rows-per-step", type=int, default=1 << 23)
     ap.add_argument("--samples", type=int, default=N_SAMPLES)
     ap.add_argument("--phenos", type=int, default=N_PHENO)
     ap.add_argument("--kbest", type=int, default=K_BEST)

@@ -590,12 +590,15 @@ static kg_status launch_exact(kg_ctx *c, const KgScanParams &prm) {
 	return KG_OK;
 }
 
+#ifndef KG_LIST_R
+#define KG_LIST_R 4
+#endif
 // list mode (MODE 2): one grid column per tile of 8 filter columns; the lists' lengths are only known on the device,
 // so the grid is one full wave and every CTA loops over its tile's list
 static kg_status launch_exact_list(kg_ctx *c, const KgScanParams &prm, uint32_t n_tiles) {
 	constexpr int GS = kg_ys_group_stride<8>();
 	const size_t smem = (size_t)c->nb * 4 * GS * sizeof(float);
-	auto kern = kg_scan_exact_kernel<2, 8, 2>;
+	auto kern = kg_scan_exact_kernel<KG_LIST_R, 8, 2>;
 	KG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int occ = 1;
 	KG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));

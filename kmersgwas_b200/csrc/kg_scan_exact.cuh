@@ -42,6 +42,7 @@ struct KgScanParams {
 	const unsigned long long *group_count;   // [n_groups]
 	uint64_t group_cap;
 	const int32_t *tile_pheno;
+	unsigned int *tile_chunk_counter;   // [tiles] zeroed before the launch: CTAs of a tile pull chunks of its list dynamically
 	uint32_t list_compact;   // 1: the view holds the listed rows back to back (squeezed copies), indexed by pos
 };
 
@@ -133,7 +134,16 @@ __global__ void __launch_bounds__(256) kg_scan_exact_kernel(const KgScanParams p
 	const uint32_t w32_in = prm.view.w_in * 2;
 
 	const uint32_t *glist = (MODE == 2) ? prm.group_list + (size_t)(blockIdx.y >> 1) * prm.group_cap : nullptr;
-	for (uint64_t chunk = blockIdx.x; chunk * ROWS_PER_CTA < n_work; chunk += gridDim.x) {
+	__shared__ unsigned int s_next_chunk;
+	for (uint64_t chunk = blockIdx.x;; chunk += gridDim.x) {
+		if (MODE == 2) {
+			// list lengths differ per tile and are short: dynamic chunk scheduling keeps the CTAs of a tile balanced
+			__syncthreads();
+			if (threadIdx.x == 0) s_next_chunk = atomicAdd(prm.tile_chunk_counter + blockIdx.y, 1u);
+			__syncthreads();
+			chunk = s_next_chunk;
+		}
+		if (chunk * ROWS_PER_CTA >= n_work) break;
 		const uint64_t row0 = chunk * ROWS_PER_CTA + (uint64_t)warp * (8 * R) + row_sub;
 		uint64_t rows_of[R];   // view row of work item row0 + 8 r
 		uint64_t ids_of[R];    // row id inside the submitted tile (differs from rows_of for compacted lists)

@@ -263,7 +263,7 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	tc.d_tile_pheno = nullptr; tc.d_group_count = nullptr;
 	e = cudaMalloc((void **)&tc.d_tile_pheno, tc.p_pad * sizeof(int32_t));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc tile table: %s", cudaGetErrorString(e));
-	e = cudaMalloc((void **)&tc.d_group_count, 16 * sizeof(unsigned long long));
+	e = cudaMalloc((void **)&tc.d_group_count, (16 + 16) * sizeof(unsigned long long));   // + 32 u32 tile chunk counters
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc group counters: %s", cudaGetErrorString(e));
 	e = cudaMalloc((void **)&tc.d_gconst, (tc.p_pad / 16) * sizeof(KgFilterGroupConst));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc filter constants: %s", cudaGetErrorString(e));
@@ -363,7 +363,7 @@ static kg_status kg_tc_scan_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_r
 		if (st != KG_OK) return st;
 	}
 	KG_CUDA(c, cudaMemsetAsync(c->d_counters + 2, 0, sizeof(unsigned long long), c->stream));
-	KG_CUDA(c, cudaMemsetAsync(tc.d_group_count, 0, 16 * sizeof(unsigned long long), c->stream));
+	KG_CUDA(c, cudaMemsetAsync(tc.d_group_count, 0, (16 + 16) * sizeof(unsigned long long), c->stream));
 	KgFilterParams f = kg_tc_filter_params(c, dev, n_rows);
 	const uint32_t n_blocks = (uint32_t)((n_rows + KG_F_ROWS - 1) / KG_F_ROWS);
 	const unsigned grid = std::max(1u, std::min<uint32_t>(n_blocks, (uint32_t)c->sm_count));
@@ -391,6 +391,7 @@ static kg_status kg_tc_scan_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_r
 	prm.group_count = tc.d_group_count;
 	prm.group_cap = tc.row_list_cap;
 	prm.tile_pheno = tc.d_tile_pheno;
+	prm.tile_chunk_counter = reinterpret_cast<unsigned int *>(tc.d_group_count + 16);
 	prm.list_compact = compact;
 	timing_begin(c, KG_KERNEL_SCAN_REFINE, 0);
 	st = launch_exact_list(c, prm, tc.p_pad / 8);

@@ -15,7 +15,7 @@
 #include <string>
 
 namespace {
-const uint64_t kMaxRoundRows = 1ull << 21;  // rows per round once the heaps are warm
+const uint64_t kMaxRoundRows = 1ull << 23;  // rows per round once the heaps are warm
 const uint64_t kMinWarmRound = 1ull << 16;
 const uint64_t kHitBudget = 1ull << 21;     // expected hits per round (the device buffer holds 1 << 22 by default)
 
