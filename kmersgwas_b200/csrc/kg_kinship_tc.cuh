@@ -8,13 +8,13 @@
 //
 // Work split: the lower triangle of G (in FILE column order) is cut into tiles of 128 x 256 samples; a tile
 // group = one 128-sample block I with up to two 256-sample blocks J (2 x 256 int32 TMEM columns = the whole
-// tensor memory of an SM).  grid = (groups, row splits): CTA (g, s) streams the 128-row blocks s, s + splits, ...
-// of the tile and keeps its accumulators in TMEM for the whole kernel; at the end it adds them to a global
+// tensor memory of an SM).  One CTA = (group, split): it streams the 128-row blocks split, split + n_splits, ... of the
+// tile (a group gets row splits in proportion to its number of sample tiles) and keeps its accumulators in TMEM for the whole kernel; at the end it adds them to a global
 // u64 delta matrix with atomics (int32 is enough inside a launch: a tile has < 2^31 rows).
 //
 // Per 128-row block:
 //   warp 0      bulk-copies the raw rows (contiguous bytes) into a 2-stage ring
-//   warps 2-9   MAC filter (masked popcount of every row, rows outside [mac, N - mac] contribute zeros), then expand
+//   warps 2-17  MAC filter (masked popcount of every row, rows outside [mac, N - mac] contribute zeros), then expand
 //               the presence bits of the needed sample words to s8 bytes 0x00 / 0xFF (= -1; (-1)(-1) = 1) into
 //               MN-major core matrices (16 samples x 8 rows), 2 stages
 //   warp 1      one elected thread issues 4 (K = 32 rows each) x up to 2 tcgen05.mma  D_J += A_I^T-view * B_J
@@ -24,9 +24,10 @@
 #include "kg_tc_ptx.cuh"
 
 #define KG_K_ROWS 128
-#define KG_K_THREADS 320
 #define KG_K_EXPAND_WARP0 2
-#define KG_K_EXPAND_THREADS 256
+#define KG_K_EXPAND_THREADS 512
+#define KG_K_EXPAND_SUBS (KG_K_EXPAND_THREADS / KG_K_ROWS)   // threads per row
+#define KG_K_THREADS (KG_K_EXPAND_WARP0 * 32 + KG_K_EXPAND_THREADS)
 #define KG_K_STAGES 2
 #define KG_K_RAW_STAGES 2
 #define KG_K_BT_BYTES (KG_K_ROWS * 256)   // one B tile stage: 128 rows x 256 samples
@@ -39,6 +40,11 @@ struct KgKinGroup {
 	int32_t a_in;      // B tile (0 / 1) that already contains the samples of block i_blk, or -1: expand A separately
 };
 
+// one CTA: row blocks split, split + n_splits, ... of tile group `group` (splits are proportional to the group's tiles)
+struct KgKinCta {
+	uint32_t group, split, n_splits, pad_;
+};
+
 struct KgKinTcParams {
 	const uint64_t *rows;       // raw tile, 16-byte aligned
 	uint64_t n_rows;
@@ -46,6 +52,7 @@ struct KgKinTcParams {
 	const uint64_t *file_mask;  // [w_file] used columns (MAC filter counts only these)
 	uint32_t n_used, min_count;
 	const KgKinGroup *groups;
+	const KgKinCta *ctas;       // [gridDim.x]
 	unsigned long long *delta;  // [ld][ld] co-presence counts in FILE column order, entries (a, b <= a)
 	uint32_t ld;                // 64 * w_file
 	unsigned long long *kept_count;
@@ -82,7 +89,8 @@ __global__ void __launch_bounds__(KG_K_THREADS, 1) kg_kinship_tc_kernel(const Kg
 	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
 
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const KgKinGroup grp = prm.groups[blockIdx.x];
+	const KgKinCta me = prm.ctas[blockIdx.x];
+	const KgKinGroup grp = prm.groups[me.group];
 	const uint32_t n_blocks = (uint32_t)((prm.n_rows + KG_K_ROWS - 1) / KG_K_ROWS);
 	const uint32_t row_bytes = 8u * (prm.w_file + 1);
 	const bool has2 = grp.j2[1] >= 0;
@@ -104,7 +112,7 @@ __global__ void __launch_bounds__(KG_K_THREADS, 1) kg_kinship_tc_kernel(const Kg
 		// ===================== producer =====================
 		if (lane == 0) {
 			uint32_t it = 0;
-			for (uint32_t blk = blockIdx.y; blk < n_blocks; blk += gridDim.y, it++) {
+			for (uint32_t blk = me.split; blk < n_blocks; blk += me.n_splits, it++) {
 				const uint32_t st = it % KG_K_RAW_STAGES, use = it / KG_K_RAW_STAGES;
 				kg_mbar_wait(&raw_empty[st], (use & 1) ^ 1);
 				const uint64_t r0 = (uint64_t)blk * KG_K_ROWS;
@@ -128,7 +136,7 @@ __global__ void __launch_bounds__(KG_K_THREADS, 1) kg_kinship_tc_kernel(const Kg
 		const uint64_t a_desc0 = kg_umma_smem_desc(s_addr + a_off, grp.a_in >= 0 ? 2048 : 1024, 128);
 		const uint32_t a_kstep = grp.a_in >= 0 ? (4 * 2048) >> 4 : (4 * 1024) >> 4;   // 32 rows = 4 row blocks, in 16-byte units
 		uint32_t it = 0;
-		for (uint32_t blk = blockIdx.y; blk < n_blocks; blk += gridDim.y, it++) {
+		for (uint32_t blk = me.split; blk < n_blocks; blk += me.n_splits, it++) {
 			const uint32_t st = it % KG_K_STAGES, use = it / KG_K_STAGES;
 			kg_mbar_wait(&st_full[st], use & 1);
 			kg_tc_fence_after();
@@ -149,14 +157,14 @@ __global__ void __launch_bounds__(KG_K_THREADS, 1) kg_kinship_tc_kernel(const Kg
 	} else {
 		// ===================== expanders (and, at the end, the accumulator flush) =====================
 		const uint32_t t = threadIdx.x - KG_K_EXPAND_WARP0 * 32;
-		const uint32_t r = t & (KG_K_ROWS - 1), sub = t >> 7;
+		const uint32_t r = t & (KG_K_ROWS - 1), sub = t >> 7;   // sub in [0, KG_K_EXPAND_SUBS)
 		// work items of a stage: item i < 4 nb -> word (i % 4) of B tile (i / 4); then the 2 words of a separate A tile
 		const uint32_t nb = has2 ? 2u : 1u;
 		const uint32_t n_items = 4 * nb + (grp.a_in < 0 ? 2u : 0u);
 		const uint32_t s_addr = kg_smem_u32(sStage);
 		unsigned long long kept_local = 0;
 		uint32_t it = 0;
-		for (uint32_t blk = blockIdx.y; blk < n_blocks; blk += gridDim.y, it++) {
+		for (uint32_t blk = me.split; blk < n_blocks; blk += me.n_splits, it++) {
 			const uint32_t rst = it % KG_K_RAW_STAGES, ruse = it / KG_K_RAW_STAGES;
 			kg_mbar_wait(&raw_full[rst], ruse & 1);
 			const uint64_t *row = reinterpret_cast<const uint64_t *>(sRaw + rst * raw_stage_bytes + r * row_bytes) + 1;
@@ -176,7 +184,7 @@ __global__ void __launch_bounds__(KG_K_THREADS, 1) kg_kinship_tc_kernel(const Kg
 			const uint32_t st = it % KG_K_STAGES, use = it / KG_K_STAGES;
 			kg_mbar_wait(&st_empty[st], (use & 1) ^ 1);
 			const uint32_t st_base = s_addr + st * KG_K_STAGE_BYTES + (r & 7) * 16;
-			for (uint32_t i = sub; i < n_items; i += 2) {
+			for (uint32_t i = sub; i < n_items; i += KG_K_EXPAND_SUBS) {
 				uint32_t fw, dst_off, lbo;   // file word, byte offset of its first sample chunk in the stage, row-block stride
 				if (i < 4 * nb) {
 					const uint32_t b = i >> 2, wt = i & 3;
@@ -206,10 +214,10 @@ __global__ void __launch_bounds__(KG_K_THREADS, 1) kg_kinship_tc_kernel(const Kg
 				kg_mbar_arrive(&raw_empty[rst]);
 			}
 		}
-		if (lane == 0 && kept_local && blockIdx.x == 0) atomicAdd(prm.kept_count, kept_local);
+		if (lane == 0 && kept_local && me.group == 0) atomicAdd(prm.kept_count, kept_local);
 
 		// ---- flush: TMEM accumulators -> global u64 delta (lower triangle, file column order)
-		if (warp < KG_K_EXPAND_WARP0 + 4 && n_blocks > blockIdx.y) {
+		if (warp < KG_K_EXPAND_WARP0 + 4 && n_blocks > me.split) {
 			kg_mbar_wait(done, 0);
 			kg_tc_fence_after();
 			const uint32_t q4 = warp & 3;

@@ -9,7 +9,8 @@
 static void kg_tc_free(KgTcState *tc) {
 	cudaFree(tc->d_row_list); cudaFree(tc->d_group_list); cudaFree(tc->d_group_count); cudaFree(tc->d_tile_pheno);
 	tc->d_group_list = nullptr; tc->d_group_count = nullptr; tc->d_tile_pheno = nullptr;
-	cudaFree(tc->d_yq); cudaFree(tc->d_gconst); cudaFree(tc->d_scratch); cudaFree(tc->d_aligned);
+	cudaFree(tc->d_yq); cudaFree(tc->d_gconst); cudaFree(tc->d_kin_groups); cudaFree(tc->d_kin_delta); cudaFree(tc->d_kin_ctas);
+	tc->d_kin_groups = nullptr; tc->d_kin_delta = nullptr; tc->d_kin_ctas = nullptr; cudaFree(tc->d_scratch); cudaFree(tc->d_aligned);
 	tc->d_row_list = nullptr; tc->d_yq = nullptr; tc->d_gconst = nullptr; tc->d_scratch = nullptr; tc->d_aligned = nullptr;
 	tc->aligned_cap = 0;
 	tc->row_list_cap = 0;
@@ -465,9 +466,29 @@ static kg_status kg_tc_prepare_kinship(kg_ctx *c) {
 			groups.push_back(g);
 		}
 	}
-	if (groups.size() > 4096) { tc.why_unavailable = "too many sample tiles"; return KG_OK; }
-	cudaFree(tc.d_kin_groups); cudaFree(tc.d_kin_delta);
-	tc.d_kin_groups = nullptr; tc.d_kin_delta = nullptr;
+	if (groups.size() > (size_t)c->sm_count) { tc.why_unavailable = "more sample tile groups than SMs"; return KG_OK; }
+	// CTA table: one wave, row splits per group in proportion to its tiles (a 2-tile group does twice the MMAs)
+	std::vector<KgKinCta> ctas;
+	{
+		uint32_t total_tiles = 0;
+		for (const KgKinGroup &g : groups) total_tiles += g.j2[1] >= 0 ? 2 : 1;
+		uint32_t left = (uint32_t)c->sm_count, tiles_left = total_tiles;
+		for (uint32_t gi = 0; gi < groups.size(); gi++) {
+			const uint32_t t = groups[gi].j2[1] >= 0 ? 2 : 1;
+			const uint32_t groups_after = (uint32_t)groups.size() - gi - 1;
+			uint32_t n = std::max(1u, (left * t + tiles_left / 2) / tiles_left);
+			n = std::min(n, left - groups_after);   // every later group still gets a CTA
+			for (uint32_t s_ = 0; s_ < n; s_++) ctas.push_back(KgKinCta{gi, s_, n, 0});
+			left -= n;
+			tiles_left -= t;
+		}
+	}
+	cudaFree(tc.d_kin_groups); cudaFree(tc.d_kin_delta); cudaFree(tc.d_kin_ctas);
+	tc.d_kin_groups = nullptr; tc.d_kin_delta = nullptr; tc.d_kin_ctas = nullptr;
+	cudaError_t e0 = cudaMalloc((void **)&tc.d_kin_ctas, ctas.size() * sizeof(KgKinCta));
+	if (e0 != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc kinship CTA table: %s", cudaGetErrorString(e0));
+	KG_CUDA(c, cudaMemcpy(tc.d_kin_ctas, ctas.data(), ctas.size() * sizeof(KgKinCta), cudaMemcpyHostToDevice));
+	tc.kin_ctas = (uint32_t)ctas.size();
 	cudaError_t e = cudaMalloc((void **)&tc.d_kin_groups, groups.size() * sizeof(KgKinGroup));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc kinship groups: %s", cudaGetErrorString(e));
 	KG_CUDA(c, cudaMemcpy(tc.d_kin_groups, groups.data(), groups.size() * sizeof(KgKinGroup), cudaMemcpyHostToDevice));
@@ -497,14 +518,12 @@ static kg_status kg_tc_kinship_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t 
 	k.n_used = (uint32_t)c->n_used;
 	k.min_count = (uint32_t)std::min<uint64_t>(c->kin_min_count, 0xFFFFFFFFull);
 	k.groups = tc.d_kin_groups;
+	k.ctas = tc.d_kin_ctas;
 	k.delta = tc.d_kin_delta;
 	k.ld = ld;
 	k.kept_count = tc.d_kin_delta + (size_t)ld * ld;
-	const uint32_t n_blocks = (uint32_t)((n_rows + KG_K_ROWS - 1) / KG_K_ROWS);
-	const uint32_t splits = std::max(1u, std::min<uint32_t>(n_blocks, (uint32_t)c->sm_count / std::max(1u, tc.kin_groups)));
-	dim3 grid(tc.kin_groups, splits);
 	timing_begin(c, KG_KERNEL_KINSHIP, n_rows);
-	kg_kinship_tc_kernel<<<grid, KG_K_THREADS, tc.kin_smem, c->stream>>>(k);
+	kg_kinship_tc_kernel<<<tc.kin_ctas, KG_K_THREADS, tc.kin_smem, c->stream>>>(k);
 	timing_end(c);
 	KG_LAUNCH_CHECK(c);
 	const uint64_t n2 = (uint64_t)c->n_used * c->n_used;

@@ -37,7 +37,8 @@ struct KgTcState {
 	// kinship tensor engine: tile groups, per-tile co-presence delta in file column order (+ kept-row counter)
 	struct KgKinGroup *d_kin_groups = nullptr;
 	unsigned long long *d_kin_delta = nullptr;
-	uint32_t kin_groups = 0;
+	struct KgKinCta *d_kin_ctas = nullptr;
+	uint32_t kin_groups = 0, kin_ctas = 0;
 	size_t kin_smem = 0;
 	void *d_scratch = nullptr;
 };

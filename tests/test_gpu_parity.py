@@ -294,3 +294,84 @@ def test_kinship_external_accumulator(kg):
     K, cnt = ctx.kinship_fetch()
     assert cnt == cnt_o and np.array_equal(K, K_o)
     ctx.close()
+
+
+# ------------------------------------------------------------------------------ shapes beyond the tensor engines
+def test_wide_table_falls_back_to_exact_and_popc_engines(kg):
+    """BASELINE config 5 shape (4096 samples): the phenotype tile of the int8 filter and the kinship operand stages do
+    not fit shared memory, so the auto engines must pick the exact score kernel / the popcount Gram and stay exact."""
+    n_file, n_rows, n_pheno = 4096, 700, 3
+    table = S.synth_table(91, n_rows, n_file)
+    y = S.synth_phenotypes(92, n_file, n_pheno)
+    mc = S.min_count_of(n_file, 0.05, 5)
+    idx = np.arange(n_file)
+    mw, mb = idx // 64, idx % 64
+    keep_o, scores_o, kept_o = S.oracle_scan(table, n_file, mw, mb, y, mc)
+    sess = kg.Session(n_file, mw, mb, y, mc, 50)
+    sess.associate(table, n_rows, 0)
+    assert sess.tested(0) == kept_o
+    for j in range(n_pheno):
+        h = S.oracle_topk(table, keep_o, scores_o[j], 50)
+        ko, so, ro = h.dump()
+        k, s, r = sess.heap(j)
+        assert np.array_equal(k, ko) and np.array_equal(_bits(s), _bits(so)) and np.array_equal(r, ro)
+    sess.close()
+    ctx = kg.Context.identity(n_file)
+    with pytest.raises(kg.KgError):          # forcing the tensor engines on this shape is refused, not emulated
+        ctx.set_option(kg.OPT_SCAN_ENGINE, 2)
+        ctx.set_phenotypes(y, mc)
+        ctx.scan_submit(table, n_rows)
+    ctx.close()
+    ctx = kg.Context.identity(n_file)
+    ctx.kinship_begin(mc)
+    ctx.kinship_submit(np.ascontiguousarray(table[:200]), 200)
+    K, cnt = ctx.kinship_fetch()
+    K_o, cnt_o = S.oracle_kinship(table[:200], n_file, mw, mb, mc)
+    assert cnt == cnt_o and np.array_equal(K, K_o)
+    ctx.close()
+
+
+def test_many_phenotypes_auto_engine(kg):
+    """P = 140 > 127 columns: the filter is unavailable, the auto engine scores everything exactly."""
+    n_file, n_rows, n_pheno, kbest = 241, 6000, 140, 30
+    table = S.synth_table(93, n_rows, n_file)
+    y = S.synth_phenotypes(94, n_file, n_pheno)
+    mc = S.min_count_of(n_file, 0.05, 5)
+    idx = np.arange(n_file)
+    keep_o, scores_o, kept_o = S.oracle_scan(table, n_file, idx // 64, idx % 64, y, mc)
+    sess = kg.Session(n_file, idx // 64, idx % 64, y, mc, kbest)
+    for r0 in range(0, n_rows, 2500):
+        n = min(2500, n_rows - r0)
+        sess.associate(np.ascontiguousarray(table[r0:r0 + n]), n, r0)
+    assert sess.tested(0) == kept_o
+    for j in (0, 69, 139):
+        h = S.oracle_topk(table, keep_o, scores_o[j], kbest)
+        ko, so, ro = h.dump()
+        k, s, r = sess.heap(j)
+        assert np.array_equal(k, ko) and np.array_equal(_bits(s), _bits(so)) and np.array_equal(r, ro)
+    sess.close()
+
+
+def test_ecoli_shape_through_the_pipeline(kg):
+    """BASELINE config 4 shape (241 samples, 101 phenotypes): auto engine, several batches, device-resident rows."""
+    n_file, n_rows, n_pheno, kbest = 241, 60000, 101, 100
+    table = S.synth_table(95, n_rows, n_file)
+    y = S.synth_phenotypes(96, n_file, n_pheno)
+    mc = S.min_count_of(n_file, 0.05, 5)
+    idx = np.arange(n_file)
+    keep_o, scores_o, kept_o = S.oracle_scan(table, n_file, idx // 64, idx % 64, y, mc)
+    dev = _torch_rows(table)
+    sess = kg.Session(n_file, idx // 64, idx % 64, y, mc, kbest)
+    stride = table.shape[1]
+    for r0 in range(0, n_rows, 17000):
+        n = min(17000, n_rows - r0)
+        sess.associate(dev.data_ptr() + r0 * stride * 8, n, r0)
+    assert sess.tested(0) == kept_o
+    st = sess.stats()
+    assert st["rows_scored"] == n_rows
+    for j in (0, 50, 100):
+        h = S.oracle_topk(table, keep_o, scores_o[j], kbest)
+        ko, so, ro = h.dump()
+        k, s, r = sess.heap(j)
+        assert np.array_equal(k, ko) and np.array_equal(_bits(s), _bits(so)) and np.array_equal(r, ro)
+    sess.close()
