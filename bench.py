@@ -179,7 +179,7 @@ def reference_arm(args):
         return 0
     exe, _ = _ref_paths()
     if not exe.exists():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/associate_kmers not built"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/associate_kmers not built"})
         return 0
     threads = os.cpu_count() or 1
     n_rows = args.ref_rows
@@ -206,7 +206,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -223,6 +223,7 @@ def our_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -291,6 +292,7 @@ def our_arm(args):
         launches0 = sess.launches()
         io0 = sess.io_bytes()
         stats0 = sess.stats()
+        hostms0 = sess.host_ms()
         sampler = ClockSampler(local)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -308,6 +310,7 @@ def our_arm(args):
         launches_timed = sess.launches() - launches0
         io1 = sess.io_bytes()
         stats1 = sess.stats()
+        hostms1 = sess.host_ms()
 
         # ---- e2e: same loop from pinned host memory (H2D of the rows + D2H of the hits inside the timing)
         host = [torch.empty(R * stride, dtype=torch.int64).pin_memory() for _ in range(n_e2e)]
@@ -409,6 +412,7 @@ def our_arm(args):
                 "hits_replayed_per_step": (stats1["hits_replayed"] - stats0["hits_replayed"]) / K,
                 "threshold_rounds_per_step": (stats1["rounds"] - stats0["rounds"]) / K,
                 "filter_listed_rows_per_step": kt["scan_refine"][2] / K,
+                "host_ms_per_step": {k_: (hostms1[k_] - hostms0[k_]) / K for k_ in hostms1},
                 "rows_per_step_by_engine": {"exact": kt["scan_exact"][2] / K, "tensor_filter": kt["scan_filter"][2] / K},
             },
             "roofline": {
@@ -434,7 +438,7 @@ def our_arm(args):
             line["merge_ms"] = merge_ms
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
-        print(json.dumps(line))
+        emit(line)
     sess.close()
     if world > 1:
         dist.destroy_process_group()
@@ -516,6 +520,28 @@ def cpu_baseline(args):
             "associate_rows_per_s": args.cpu_rows / assoc_s if assoc_s > 0 else None}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL banner, torchrun children) may write to fd 1; the driver wants exactly ONE JSON line there.
+    Route fd 1 to stderr for the run and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -536,6 +562,7 @@ def main():
     ap.add_argument("--warmup-ref", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    quiet_stdout()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

@@ -40,6 +40,8 @@ def load():
     lib.kgh_session_heap_dump.restype = None
     lib.kgh_session_stats.argtypes = [vp, vp, vp, vp, vp]
     lib.kgh_session_stats.restype = None
+    lib.kgh_session_host_ns.argtypes = [vp, vp]
+    lib.kgh_session_host_ns.restype = None
     lib.kgh_session_io_bytes.argtypes = [vp, vp, vp]
     lib.kgh_session_io_bytes.restype = None
     lib.kgh_session_log_size.argtypes = [vp]
@@ -133,6 +135,12 @@ class Session:
         a, b, c, d = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._lib.kgh_session_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
         return dict(rounds=a.value, hits_replayed=b.value, rows_scored=c.value, rows_kept=d.value)
+
+    def host_ms(self):
+        """Host wall time per driver phase so far (ms): wait for the device, copy hits, group, replay, thresholds + submit."""
+        a = (C.c_uint64 * 5)()
+        self._lib.kgh_session_host_ns(self._h, a)
+        return dict(zip(("wait_device", "copy_hits", "group", "replay", "thresholds_submit"), (x / 1e6 for x in a)))
 
     def io_bytes(self):
         """(small host->device bytes: thresholds, device->host bytes: hits + counters) so far."""

@@ -10,6 +10,7 @@
 #include "association_driver.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
@@ -18,6 +19,10 @@ namespace {
 const uint64_t kMaxRoundRows = 1ull << 23;  // rows per round once the heaps are warm
 const uint64_t kMinWarmRound = 1ull << 16;
 const uint64_t kHitBudget = 1ull << 21;     // expected hits per round (the device buffer holds 1 << 22 by default)
+
+uint64_t now_ns() {
+	return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 void check(kg_ctx *ctx, kg_status st, const char *what) {
 	if (st != KG_OK) throw std::runtime_error(std::string(what) + ": " + kg_last_error(ctx));
@@ -116,7 +121,10 @@ static bool replay_in_flight(kg_ctx *ctx, BestAssociationsHeap *const *heaps, st
 	if (!S.in_flight) return true;
 	std::size_t n_hits = 0;
 	uint64_t seen = 0, kept_now = 0;
+	uint64_t t0 = now_ns();
 	kg_status st = kg_scan_fetch(ctx, nullptr, 0, &n_hits, &seen, &kept_now);
+	S.ns_wait += now_ns() - t0;
+	t0 = now_ns();
 	if (st == KG_ERR_HITS_OVERFLOW) {
 		S.in_flight = false;
 		return false;
@@ -138,6 +146,8 @@ static bool replay_in_flight(kg_ctx *ctx, BestAssociationsHeap *const *heaps, st
 	}
 	const uint64_t kept_round = kept_now - S.kept_seen;
 	S.kept_seen = kept_now;
+	S.ns_copy += now_ns() - t0;
+	t0 = now_ns();
 
 	// group by phenotype (counting sort), then one task per phenotype: sort by row + replay through its heap
 	S.bucket_off.assign(P + 1, 0);
@@ -149,6 +159,8 @@ static bool replay_in_flight(kg_ctx *ctx, BestAssociationsHeap *const *heaps, st
 		for (std::size_t i = 0; i < n_hits; i++) S.bucketed[at[S.hit_buf[i].pheno]++] = S.hit_buf[i];
 	}
 	if (!S.pool) S.pool = new KghTaskPool(std::min<unsigned>(kgh_host_threads(), (unsigned)P));
+	S.ns_group += now_ns() - t0;
+	t0 = now_ns();
 	kg_hit *const base = S.bucketed.data();
 	const std::vector<std::size_t> &off = S.bucket_off;
 	S.pool->run(P, [&](std::size_t j) {
@@ -158,6 +170,7 @@ static bool replay_in_flight(kg_ctx *ctx, BestAssociationsHeap *const *heaps, st
 		heaps[j]->note_tested_rows((std::size_t)(kept_round - (uint64_t)(e - b)));
 	});
 	if (S.log_hits) S.hit_log.insert(S.hit_log.end(), S.bucketed.begin(), S.bucketed.end());
+	S.ns_replay += now_ns() - t0;
 	S.rows_kept += kept_round;
 	S.rows_scored += S.in_flight_rows;
 	S.hits_replayed += n_hits;
@@ -209,10 +222,12 @@ void kgh_associate_rows(kg_ctx *ctx, BestAssociationsHeap *const *heaps, std::si
 		round = std::max<uint64_t>(round / shrink, 1);
 		round = std::min<uint64_t>(round, n_rows - done);
 
+		const uint64_t t_sub = now_ns();
 		check(ctx, kg_scan_set_thresholds(ctx, S.thr.data(), (uint32_t)P), "kg_scan_set_thresholds");
 		S.h2d_small_bytes += (uint64_t)P * sizeof(double);
 		// one submit per round: the library scans device rows in place and cuts host rows into sub-tiles itself
 		check(ctx, kg_scan_submit(ctx, rows + done * stride, round, first_row_id + done), "kg_scan_submit");
+		S.ns_submit += now_ns() - t_sub;
 		// the device now works on this round; meanwhile replay the previous one
 		if (!replay_in_flight(ctx, heaps, P, S)) {
 			// overflow in the previous round: drop everything not replayed, redo from that round in smaller pieces

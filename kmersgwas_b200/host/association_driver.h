@@ -58,6 +58,8 @@ struct AssociationDriverState {
 	uint64_t rows_kept = 0;          // rows that passed the MAC filter (replayed intervals)
 	uint64_t d2h_bytes = 0;          // hits + counters copied back from the device
 	uint64_t h2d_small_bytes = 0;    // thresholds sent to the device (the tiles themselves are counted by the caller)
+	// host wall time per phase (ns): waiting for the device, copying hits, grouping, replaying, thresholds + submit
+	uint64_t ns_wait = 0, ns_copy = 0, ns_group = 0, ns_replay = 0, ns_submit = 0;
 	std::vector<double> thr;
 	// Multi-GPU shards: keep every replayed candidate so that the shards' logs can be merged and
 	// replayed once more, in global row order, through the final heaps (kgh_merge_shards).

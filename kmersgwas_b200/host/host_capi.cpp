@@ -98,6 +98,12 @@ void kgh_session_stats(kgh_session *s, uint64_t *rounds, uint64_t *hits_replayed
 	if (rows_kept) *rows_kept = s->state.rows_kept;
 }
 
+// host wall time per driver phase so far, ns: wait for device, copy hits, group, replay, thresholds + submit
+void kgh_session_host_ns(kgh_session *s, uint64_t *out5) {
+	out5[0] = s->state.ns_wait; out5[1] = s->state.ns_copy; out5[2] = s->state.ns_group;
+	out5[3] = s->state.ns_replay; out5[4] = s->state.ns_submit;
+}
+
 void kgh_session_io_bytes(kgh_session *s, uint64_t *h2d_small, uint64_t *d2h) {
 	if (h2d_small) *h2d_small = s->state.h2d_small_bytes;
 	if (d2h) *d2h = s->state.d2h_bytes;
