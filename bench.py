@@ -15,7 +15,8 @@ exact replay through BestAssociationsHeap); every step scans rows no earlier ste
   value  : rows/s with the batches already resident in HBM (device pointers handed to the C ABI)
   e2e    : rows/s with the batches in pinned HOST memory; H2D of the rows and D2H of the hits inside the timing
   N > 1  : rows sharded by k-mer block across ranks ("weak": every rank scans --rows-per-step rows per step), no
-           data-path collective; the per-rank hit logs are merged on rank 0 after the timed steps (merge_ms).
+           data-path collective; after the timed steps the per-rank hit logs are exchanged (one all-to-all by
+           phenotype) and merged exactly, every rank merging its share of the phenotypes (merge_ms).
 """
 from __future__ import annotations
 
@@ -351,26 +352,35 @@ def our_arm(args):
     ms_dev = max_over_ranks(ms_dev)
     ms_e2e = max_over_ranks(ms_e2e)
 
-    # ---- N > 1: exact merge of the shards' hit logs on rank 0 (host side, once per job)
+    # ---- N > 1: exact merge of the shards' hit logs (host side, once per job).  Phenotypes are independent, so rank r
+    # merges the phenotypes p = r (mod N): one all-to-all of the logs, then every rank replays its phenotypes' hits
+    # in global row order through fresh heaps (kgh_merge_hit_log) -- the sequential reference heap state, ties included.
     merge_ms = None
     if world > 1:
         t0 = time.perf_counter()
         log = sess.hit_log()
         kept = sess.stats()["rows_kept"]
-        sizes = [None] * world
-        dist.all_gather_object(sizes, (len(log), kept))
-        cap = max(s[0] for s in sizes)
-        mine = torch.zeros(max(cap, 1) * kg.HIT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
-        if len(log):
-            mine[: len(log) * kg.HIT_DTYPE.itemsize] = torch.from_numpy(log.view(np.uint8).copy()).cuda()
-        gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-        dist.gather(mine, gathered, dst=0)
-        if rank == 0:
-            parts = [g[: sizes[i][0] * kg.HIT_DTYPE.itemsize].cpu().numpy().view(kg.HIT_DTYPE) for i, g in enumerate(gathered)]
-            hs = kg.HeapSet(args.kbest, p)
-            hs.merge(np.concatenate(parts), sum(s[1] for s in sizes))
-            assert hs.tested(0) == sum(s[1] for s in sizes)
-        merge_ms = 1e3 * (time.perf_counter() - t0)
+        dest = (log["pheno"] % world).astype(np.int64)
+        order = np.argsort(dest, kind="stable")
+        send_counts = np.bincount(dest, minlength=world).astype(np.int64)
+        send = torch.from_numpy(log[order].view(np.uint8).reshape(-1).copy()).cuda()
+        counts_all = torch.zeros(world * world, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(counts_all, torch.from_numpy(send_counts).cuda())
+        counts_all = counts_all.cpu().numpy().reshape(world, world)          # [src][dst]
+        recv_counts = counts_all[:, rank]
+        isz = kg.HIT_DTYPE.itemsize
+        recv = torch.empty(int(recv_counts.sum()) * isz, dtype=torch.uint8, device="cuda")
+        dist.all_to_all_single(recv, send, output_split_sizes=[int(c) * isz for c in recv_counts],
+                               input_split_sizes=[int(c) * isz for c in send_counts])
+        kept_all = torch.tensor([kept], dtype=torch.int64, device="cuda")
+        dist.all_reduce(kept_all)
+        mine = recv.cpu().numpy().view(kg.HIT_DTYPE)
+        hs = kg.HeapSet(args.kbest, p)
+        hs.merge(mine, int(kept_all.item()))
+        my_phenos = [j for j in range(p) if j % world == rank]
+        assert all(hs.tested(j) == int(kept_all.item()) for j in my_phenos)
+        merge_local = 1e3 * (time.perf_counter() - t0)
+        merge_ms = max_over_ranks(merge_local)
 
     # ---- kinship leg (config 3 shape, bounded rows): GB/s of table consumed
     kin = kinship_leg(args, kg, torch, dist, rank, world, local, n, stride, row_bytes)

@@ -9,9 +9,13 @@
 // reproduces the reference heap state, ties included.
 #include "association_driver.h"
 
+#include <sys/mman.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <cstring>
+#include <new>
 #include <stdexcept>
 #include <string>
 
@@ -111,7 +115,26 @@ AssociationDriverState::AssociationDriverState() {}
 
 AssociationDriverState::~AssociationDriverState() {
 	if (hit_buf && pinned_owner) kg_host_free(pinned_owner, hit_buf);
+	for (LogChunk &c : hit_log) free(c.p);
 	delete pool;
+}
+
+void AssociationDriverState::log_append(const kg_hit *hits, std::size_t n) {
+	while (n) {
+		if (hit_log.empty() || hit_log.back().n == hit_log.back().cap) {
+			const std::size_t cap = 1u << 22;   // 4 M hits = 128 MB
+			void *p = nullptr;
+			if (posix_memalign(&p, 2u << 20, cap * sizeof(kg_hit)) != 0) throw std::bad_alloc();
+			madvise(p, cap * sizeof(kg_hit), MADV_HUGEPAGE);
+			hit_log.push_back(LogChunk{static_cast<kg_hit *>(p), 0, cap});
+		}
+		LogChunk &c = hit_log.back();
+		const std::size_t m = std::min(n, c.cap - c.n);
+		memcpy(c.p + c.n, hits, m * sizeof(kg_hit));
+		c.n += m;
+		hits += m;
+		n -= m;
+	}
 }
 
 // ------------------------------------------------------------------------------------------ replay
@@ -149,27 +172,51 @@ static bool replay_in_flight(kg_ctx *ctx, BestAssociationsHeap *const *heaps, st
 	S.ns_copy += now_ns() - t0;
 	t0 = now_ns();
 
-	// group by phenotype (counting sort), then one task per phenotype: sort by row + replay through its heap
-	S.bucket_off.assign(P + 1, 0);
-	for (std::size_t i = 0; i < n_hits; i++) S.bucket_off[S.hit_buf[i].pheno + 1]++;
-	for (std::size_t j = 0; j < P; j++) S.bucket_off[j + 1] += S.bucket_off[j];
-	S.bucketed.resize(n_hits);
-	{
-		std::vector<std::size_t> at(S.bucket_off.begin(), S.bucket_off.end() - 1);
-		for (std::size_t i = 0; i < n_hits; i++) S.bucketed[at[S.hit_buf[i].pheno]++] = S.hit_buf[i];
-	}
+	// group by phenotype (counting sort, parallel over slices of the hit buffer), then one task per phenotype:
+	// sort by row + replay through its heap
 	if (!S.pool) S.pool = new KghTaskPool(std::min<unsigned>(kgh_host_threads(), (unsigned)P));
+	const std::size_t T = n_hits >= 8192 ? S.pool->threads() : 1;
+	const std::size_t slice = (n_hits + T - 1) / std::max<std::size_t>(T, 1);
+	S.slice_count.assign(T * P, 0);
+	const kg_hit *const raw = S.hit_buf;
+	S.pool->run(T, [&](std::size_t t) {
+		std::size_t *cnt = S.slice_count.data() + t * P;
+		const std::size_t b = t * slice, e = std::min(n_hits, b + slice);
+		for (std::size_t i = b; i < e; i++) cnt[raw[i].pheno]++;
+	});
+	S.bucket_off.assign(P + 1, 0);
+	{
+		std::size_t run = 0;   // slice_count[t][j] becomes the write position of slice t inside bucket j
+		for (std::size_t j = 0; j < P; j++) {
+			S.bucket_off[j] = run;
+			for (std::size_t t = 0; t < T; t++) {
+				const std::size_t c = S.slice_count[t * P + j];
+				S.slice_count[t * P + j] = run;
+				run += c;
+			}
+		}
+		S.bucket_off[P] = run;
+	}
+	S.bucketed.resize(n_hits);
+	kg_hit *const base = S.bucketed.data();
+	S.pool->run(T, [&](std::size_t t) {
+		std::size_t *at = S.slice_count.data() + t * P;
+		const std::size_t b = t * slice, e = std::min(n_hits, b + slice);
+		for (std::size_t i = b; i < e; i++) base[at[raw[i].pheno]++] = raw[i];
+	});
 	S.ns_group += now_ns() - t0;
 	t0 = now_ns();
-	kg_hit *const base = S.bucketed.data();
 	const std::vector<std::size_t> &off = S.bucket_off;
-	S.pool->run(P, [&](std::size_t j) {
+	// one task per phenotype; in sharded runs task 0 appends the round's hits to the shard log meanwhile
+	const std::size_t log_task = (S.log_hits && n_hits) ? 1 : 0;
+	S.pool->run(P + log_task, [&](std::size_t task) {
+		if (task < log_task) { S.log_append(raw, n_hits); return; }
+		const std::size_t j = task - log_task;
 		kg_hit *b = base + off[j], *e = base + off[j + 1];
 		std::sort(b, e, [](const kg_hit &x, const kg_hit &y) { return x.row < y.row; });
 		heaps[j]->add_hits(b, (std::size_t)(e - b));
 		heaps[j]->note_tested_rows((std::size_t)(kept_round - (uint64_t)(e - b)));
 	});
-	if (S.log_hits) S.hit_log.insert(S.hit_log.end(), S.bucketed.begin(), S.bucketed.end());
 	S.ns_replay += now_ns() - t0;
 	S.rows_kept += kept_round;
 	S.rows_scored += S.in_flight_rows;
@@ -286,8 +333,11 @@ void kgh_merge_shards(std::vector<AssociationDriverState *> &shards, BestAssocia
                       std::size_t P) {
 	std::vector<kg_hit> all;
 	uint64_t kept = 0;
+	std::size_t total = 0;
+	for (AssociationDriverState *s : shards) total += s->hit_log_size();
+	all.reserve(total);
 	for (AssociationDriverState *s : shards) {
-		all.insert(all.end(), s->hit_log.begin(), s->hit_log.end());
+		for (const auto &chunk : s->hit_log) all.insert(all.end(), chunk.p, chunk.p + chunk.n);
 		kept += s->rows_kept;
 	}
 	kgh_merge_hit_log(all, kept, final_heaps, P);

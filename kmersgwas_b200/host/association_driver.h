@@ -64,7 +64,16 @@ struct AssociationDriverState {
 	// Multi-GPU shards: keep every replayed candidate so that the shards' logs can be merged and
 	// replayed once more, in global row order, through the final heaps (kgh_merge_shards).
 	bool log_hits = false;
-	std::vector<kg_hit> hit_log;
+	// Append-only chunks of 128 MB on transparent huge pages: appending a round's hits must not re-copy a 100+ MB
+	// vector nor take a 4 KB page fault per 128 hits.
+	struct LogChunk { kg_hit *p; std::size_t n, cap; };
+	std::vector<LogChunk> hit_log;
+	void log_append(const kg_hit *hits, std::size_t n);
+	std::size_t hit_log_size() const {
+		std::size_t n = 0;
+		for (const auto &c : hit_log) n += c.n;
+		return n;
+	}
 
 	// ---- pipeline state
 	bool in_flight = false;          // the open device interval holds submitted rows whose hits are not replayed yet
@@ -75,6 +84,7 @@ struct AssociationDriverState {
 	std::size_t hit_cap = 0;
 	std::vector<kg_hit> bucketed;    // hits of the current interval grouped by phenotype
 	std::vector<std::size_t> bucket_off;
+	std::vector<std::size_t> slice_count;   // [threads][P] scratch of the parallel counting sort
 	KghTaskPool *pool = nullptr;
 };
 

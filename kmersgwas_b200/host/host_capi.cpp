@@ -111,9 +111,12 @@ void kgh_session_io_bytes(kgh_session *s, uint64_t *h2d_small, uint64_t *d2h) {
 
 // Multi-shard merge: replay the shards' hit logs, in global row order, into shard 0's heaps
 // (which are reset first).  Used by the world_size > 1 tests and the multi-GPU bench.
-uint64_t kgh_session_log_size(kgh_session *s) { kgh_session_finish(s); return s->state.hit_log.size(); }
+uint64_t kgh_session_log_size(kgh_session *s) { kgh_session_finish(s); return s->state.hit_log_size(); }
 void kgh_session_log_copy(kgh_session *s, kg_hit *out) {
-	if (!s->state.hit_log.empty()) memcpy(out, s->state.hit_log.data(), s->state.hit_log.size() * sizeof(kg_hit));
+	for (const auto &chunk : s->state.hit_log) {
+		memcpy(out, chunk.p, chunk.n * sizeof(kg_hit));
+		out += chunk.n;
+	}
 }
 
 // Standalone heap object for merging gathered logs on rank 0.
