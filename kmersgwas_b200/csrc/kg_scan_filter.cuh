@@ -42,15 +42,20 @@
 #define KG_F_MAX_A_STAGES 8      // A stages live in tensor memory next to the two accumulator buffers:
 #define KG_F_TMEM_COLS 512       //   2 x p_pad accumulator columns + a_stages x 16 a_words columns <= 512
 #define KG_F_RAW_STAGES 4
-#define KG_F_EXPAND_WARP0 2
+#define KG_F_EXPAND_WARP0 1
 #ifndef KG_F_EXPAND_WARPS
 #define KG_F_EXPAND_WARPS 12        // KG_F_EXPAND_WARPS / 4 per TMEM lane quarter share a stage's words
 #endif
 #define KG_F_NSUB (KG_F_EXPAND_WARPS / 4)
+#define KG_F_MAX_WPT 3           // presence words per expander thread and stage: a_words <= KG_F_MAX_WPT * KG_F_NSUB
 #define KG_F_EPI_WARP0 (KG_F_EXPAND_WARP0 + KG_F_EXPAND_WARPS)
 #define KG_F_EPI_WARPS 8         // two sets of 4 (one warp per TMEM lane quarter); set s owns accumulator buffer s
-#define KG_F_THREADS ((KG_F_EPI_WARP0 + KG_F_EPI_WARPS) * 32)
-#define KG_F_ONE 128             // value of a set presence bit in the u8 A operand (0x80)
+#define KG_F_MMA_WARP0 (KG_F_EPI_WARP0 + KG_F_EPI_WARPS)
+#ifndef KG_F_MMA_WARPS
+#define KG_F_MMA_WARPS 2         // issuers that take turns with the A-stage batches of the MMA stream (see the MMA role below)
+#endif
+#define KG_F_THREADS ((KG_F_MMA_WARP0 + KG_F_MMA_WARPS) * 32)
+#define KG_F_ONE 1               // accumulator units per presence bit: A holds -1 (0xFF, s8), B holds the NEGATED phenotype column
 
 // Per 16-column group: the loosest bound of its phenotype columns, in accumulator units (x KG_F_ONE).
 //   a row is ruled out for the group iff  max |Q| < alpha * sqrt(den) - kappa - slack(m),
@@ -86,30 +91,40 @@ struct KgFilterParams {
 	uint64_t group_cap;        // = capacity of row_list (n_rows)
 	unsigned long long *kept_count;
 	int32_t *q_out;            // debug mode: [n_rows][p_pad] accumulators
-	uint32_t dbg;              // perf experiments only (env KG_FILTER_DEBUG): 1 skip expansion, 2 skip epilogue work, 4 skip MMAs
+	uint32_t n_issuers;        // MMA issuer warps in use, 1 .. KG_F_MMA_WARPS
+	uint32_t dbg;              // perf experiments only (env KG_FILTER_DEBUG): 1 skip expansion, 2 skip epilogue work, 4 skip MMAs, 8 skip loads, 16 plain a_empty arrive, 32 SS-mode MMAs on garbage A
 };
 
 __host__ __device__ inline uint32_t kg_filter_raw_stage_bytes(uint32_t w_file) { return KG_F_ROWS * 8u * (w_file + 1); }
 __host__ __device__ inline size_t kg_filter_smem_bytes(uint32_t w_file, uint32_t b_bytes, uint32_t p_pad) {
-	return 1024 /*alignment slack*/ + (size_t)b_bytes + (size_t)KG_F_RAW_STAGES * kg_filter_raw_stage_bytes(w_file) + (size_t)(p_pad / 16) * sizeof(KgFilterGroupConst) + 256;
+	return 1024 /*alignment slack*/ + (size_t)b_bytes + (size_t)KG_F_RAW_STAGES * kg_filter_raw_stage_bytes(w_file) + (size_t)(p_pad / 16) * sizeof(KgFilterGroupConst) + 320;
 }
-// K index (byte inside the A / B operands) of file column `col`: the expander's 64-bit multiply leaves bit i of
-// every presence byte in output byte 7 - i, so B is stored with the same permutation.
-__host__ __device__ inline uint32_t kg_filter_k_of_column(uint32_t col) { return (col & ~7u) | (7u - (col & 7u)); }
+// K index (byte inside the A / B operands) of file column `col`.  The expander (below) turns 16 presence bits into
+// 4 registers with 4 PRMTs: register b holds the samples 4 n + b (n = byte inside the register), i.e. inside every
+// 16 columns the two 2-bit fields of the column index are swapped; B is stored with the same permutation.
+__host__ __device__ inline uint32_t kg_filter_k_of_column(uint32_t col) { return (col & ~15u) | ((col & 3u) << 2) | ((col >> 2) & 3u); }
 
-// 8 presence bits -> 8 bytes of 0x80 / 0x00.  x * sum_j 2^(9j): bit i lands on positions i + 9j, all distinct
-// (no carries); position 8j + 7 (the top bit of byte j) receives bit 7 - j.
-__device__ __forceinline__ uint64_t kg_spread8(uint32_t byte) {
-	return ((uint64_t)byte * 0x8040201008040201ull) & 0x8080808080808080ull;
+__device__ __forceinline__ uint32_t kg_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+	uint32_t d;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+	return d;
 }
-// 32 presence bits -> 32 u8 operand bytes in 8 registers
-__device__ __forceinline__ void kg_expand_u32(uint32_t w, uint32_t *out8) {
-#pragma unroll
-	for (int b = 0; b < 4; b++) {
-		const uint64_t v = kg_spread8(__byte_perm(w, 0, 0x4440 + b));
-		out8[2 * b] = (uint32_t)v;
-		out8[2 * b + 1] = (uint32_t)(v >> 32);
-	}
+// 32 presence bits -> 32 s8 operand bytes (0xFF = -1 for a set bit, 0x00) in 8 registers: 8 PRMTs + 3 shifts, ALU
+// pipe only (the former 64-bit multiply per presence byte paid 2 IMADs + 3 ALU operations per 8 bits).
+// PRMT picks result byte n from the 8 bytes {b, a} with selector nibble n (its low 16 bits = 16 presence bits); a
+// table whose byte i is 0xFF iff bit j of i is set therefore yields bit j of every nibble as a full byte.  Bit 3 of a
+// selector nibble means "replicate the sign of the selected byte", which maps 0xFF / 0x00 onto themselves, so the
+// other bits of a nibble never disturb the result; bit 3 itself is read as bit 2 of (x >> 1).
+__device__ __forceinline__ void kg_expand_u32(uint32_t x, uint32_t *out8) {
+	const uint32_t x1 = x >> 1, y = x >> 16, y1 = x >> 17;
+	out8[0] = kg_prmt(0xFF00FF00u, 0xFF00FF00u, x);
+	out8[1] = kg_prmt(0xFFFF0000u, 0xFFFF0000u, x);
+	out8[2] = kg_prmt(0x00000000u, 0xFFFFFFFFu, x);
+	out8[3] = kg_prmt(0x00000000u, 0xFFFFFFFFu, x1);
+	out8[4] = kg_prmt(0xFF00FF00u, 0xFF00FF00u, y);
+	out8[5] = kg_prmt(0xFFFF0000u, 0xFFFF0000u, y);
+	out8[6] = kg_prmt(0x00000000u, 0xFFFFFFFFu, y);
+	out8[7] = kg_prmt(0x00000000u, 0xFFFFFFFFu, y1);
 }
 
 // alpha * g - kappa - slack(m), every step rounded towards -inf (a lower threshold only lists more rows)
@@ -134,7 +149,8 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 	uint64_t *a_full = bars + 2 * KG_F_RAW_STAGES, *a_empty = a_full + KG_F_MAX_A_STAGES;
 	uint64_t *tm_full = a_empty + KG_F_MAX_A_STAGES, *tm_empty = tm_full + 2;
 	uint64_t *b_full = tm_empty + 2;
-	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_full + 1);
+	uint64_t *turn = b_full + 1;   // [KG_F_MMA_WARPS] issue-order token passed round the MMA issuers
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(turn + KG_F_MMA_WARPS);
 
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t n_blocks = (uint32_t)((prm.n_rows + KG_F_ROWS - 1) / KG_F_ROWS);
@@ -143,12 +159,14 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 	if (threadIdx.x == 0) {
 		for (int i = 0; i < KG_F_RAW_STAGES; i++) { kg_mbar_init(&raw_full[i], 1); kg_mbar_init(&raw_empty[i], KG_F_EXPAND_WARPS); }
 		for (int i = 0; i < KG_F_MAX_A_STAGES; i++) { kg_mbar_init(&a_full[i], KG_F_EXPAND_WARPS); kg_mbar_init(&a_empty[i], 1); }
-		for (int i = 0; i < 2; i++) { kg_mbar_init(&tm_full[i], 1); kg_mbar_init(&tm_empty[i], 4); }
+		// tm_full: one tcgen05.commit from each issuer that has MMAs in the block (a commit tracks the issuing thread only)
+		for (int i = 0; i < 2; i++) { kg_mbar_init(&tm_full[i], min(prm.nc, prm.n_issuers)); kg_mbar_init(&tm_empty[i], 4); }
+		for (int i = 0; i < KG_F_MMA_WARPS; i++) kg_mbar_init(&turn[i], 1);
 		kg_mbar_init(b_full, 1);
 		kg_fence_mbar_init();
 	}
 	for (uint32_t i = threadIdx.x; i < prm.p_pad / 16; i += blockDim.x) sConst[i] = prm.gconst[i];
-	if (warp == 1) kg_tmem_alloc(tmem_slot, KG_F_TMEM_COLS);
+	if (warp == KG_F_MMA_WARP0) kg_tmem_alloc(tmem_slot, KG_F_TMEM_COLS);
 	kg_tc_fence_before();
 	__syncthreads();
 	kg_tc_fence_after();
@@ -179,41 +197,75 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 				if (bulk) kg_bulk_g2s(dst, src, bulk, &raw_full[st]);
 			}
 		}
-	} else if (warp == 1) {
-		// ===================== MMA issuer =====================
-		// The whole warp runs the loop (so that descriptors and addresses live in uniform registers); one elected
-		// lane issues the tcgen05.mma / tcgen05.commit instructions.
-		const uint32_t idesc = kg_umma_idesc_i8(KG_F_ROWS, prm.p_pad, false, true, false, false);
+	} else if (warp >= KG_F_MMA_WARP0) {
+		if (warp - KG_F_MMA_WARP0 < prm.n_issuers) {
+		// ===================== MMA issuers =====================
+		// Measured on B200 (profiles/probes/umma_rate.cu): a tcgen05.commit holds its issuing thread for ~670 cycles, and
+		// with N = 112 (58 cycles per MMA) the few MMAs queued behind it cannot cover that -- one issuer loses ~450
+		// tensor cycles per commit (80 instead of 58 cycles per MMA at 18 MMAs per batch).  Two issuers that alternate the
+		// batches of the stream hide each other's commit (57 cycles per MMA).  Batch j (A stage j mod a_stages) belongs to
+		// issuer j mod n_issuers; a token barrier passed round the issuers orders their barrier waits (below).  Whole warps
+		// run the loop (descriptors in uniform registers); one elected lane issues.
+		const uint32_t k = warp - KG_F_MMA_WARP0;
+		const uint32_t idesc = kg_umma_idesc_i8(KG_F_ROWS, prm.p_pad, true, true, false, false);
 		const uint32_t a_tmem0 = tmem_base + 2 * prm.tcols;                             // A stage 0, K offset 0
 		const uint32_t a_stage_cols = 16 * prm.a_words;
 		const uint64_t b_desc0 = kg_umma_smem_desc(kg_smem_u32(sB), 128, prm.sbo_b);   // column chunk 0
 		kg_mbar_wait(b_full, 0);
 		const uint32_t words_last = prm.w_file - (prm.nc - 1) * prm.a_words;   // words in the last stage of a row block
-		uint32_t it = 0, st = 0, st_par = 0;                                   // A stage ring position / parity
-		for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, it++) {
+		const uint32_t n_it = n_blocks > blockIdx.x ? (n_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+		const uint32_t NI = prm.n_issuers;
+		const uint32_t tail = min(prm.nc, NI);           // the last `tail` batches of a block (one per issuer) commit tm_full
+		uint32_t it = k / prm.nc, c = k % prm.nc;                              // row block (of this CTA) and stage inside it of batch j = k
+		uint32_t st = k % prm.a_stages, st_par = (k / prm.a_stages) & 1;       // A stage ring position / parity of batch j
+		uint32_t turn_par = 0;
+		bool first = k == 0;
+		while (it < n_it) {
 			const uint32_t buf = it & 1;
-			kg_mbar_wait(&tm_empty[buf], ((it >> 1) & 1) ^ 1);
-			kg_tc_fence_after();
 			const uint32_t d_tmem = tmem_base + buf * prm.tcols;
-			uint64_t bd = b_desc0;
-			for (uint32_t c = 0; c < prm.nc; c++) {
-				kg_mbar_wait(&a_full[st], st_par);
-				kg_tc_fence_after();
-				if (kg_elect_one()) {
-					// A: 8 TMEM columns per K = 32 step, 16 per presence word.  B descriptor address field is in 16-byte
-					// units: one K = 32 step = 16 units, one presence word = 32 units.
-					const uint32_t at = a_tmem0 + st * a_stage_cols;
-					const uint32_t ksteps = 2 * (c + 1 == prm.nc ? words_last : prm.a_words);
-					if (!(prm.dbg & 4))
-						for (uint32_t kk = 0; kk < ksteps; kk++) kg_umma_i8_ts(d_tmem, at + kk * 8, bd + kk * 16, idesc, (c | kk) != 0);
-					if (prm.dbg & 16) kg_mbar_arrive(&a_empty[st]); else kg_umma_commit(&a_empty[st]);
-				}
-				__syncwarp();
-				bd += (uint64_t)prm.a_words * 32;
-				if (++st == prm.a_stages) { st = 0; st_par ^= 1; }
+			// The token comes FIRST: once every earlier batch has been issued, the previous user of this A stage (and of
+			// this accumulator buffer) has passed its own wait, so the barriers below are in the phase this batch waits
+			// for -- an issuer running ahead of the token could otherwise match the parity of a phase two uses back.
+			if (!first) {
+				kg_mbar_wait(&turn[k], turn_par);
+				turn_par ^= 1;
 			}
-			if (kg_elect_one()) kg_umma_commit(&tm_full[buf]);
+			first = false;
+			if (c == 0) {
+				kg_mbar_wait(&tm_empty[buf], ((it >> 1) & 1) ^ 1);
+				kg_tc_fence_after();
+			}
+			kg_mbar_wait(&a_full[st], st_par);
+			kg_tc_fence_after();
+			// Integer accumulation commutes, so the only ordering the MMAs of a block need is that its FIRST one (which
+			// overwrites the accumulator) is issued before the others: the issuer of stage 0 passes the token after that
+			// MMA, every other batch passes it before issuing anything -- the issue of a batch and the ~670-cycle stall
+			// of its commits then overlap with the next issuers' batches.
+			const uint32_t at = a_tmem0 + st * a_stage_cols;
+			const uint64_t bd = b_desc0 + (uint64_t)c * prm.a_words * 32;
+			const uint32_t ksteps = (prm.dbg & 4) ? 0u : 2 * (c + 1 == prm.nc ? words_last : prm.a_words);
+			uint32_t kk0 = 0;
+			if (c == 0 && ksteps) {
+				// A: 8 TMEM columns per K = 32 step, 16 per presence word.  B descriptor address field is in 16-byte
+				// units: one K = 32 step = 16 units, one presence word = 32 units.
+				if (kg_elect_one()) kg_umma_i8_ts(d_tmem, at, bd, idesc, 0);
+				kk0 = 1;
+				__syncwarp();
+			}
+			if (lane == 0) kg_mbar_arrive(&turn[k + 1 == NI ? 0 : k + 1]);
 			__syncwarp();
+			if (kg_elect_one()) {
+				for (uint32_t kk = kk0; kk < ksteps; kk++) kg_umma_i8_ts(d_tmem, at + kk * 8, bd + kk * 16, idesc, 1);
+				kg_umma_commit(&a_empty[st]);
+				if (c + tail >= prm.nc) kg_umma_commit(&tm_full[buf]);
+			}
+			__syncwarp();
+			// batch j + KG_F_MMA_WARPS
+			c += NI;
+			while (c >= prm.nc) { c -= prm.nc; it++; }
+			st += NI;
+			while (st >= prm.a_stages) { st -= prm.a_stages; st_par ^= 1; }
+		}
 		}
 	} else if (warp < KG_F_EPI_WARP0) {
 		// ===================== expanders: presence bits -> u8 A operand in tensor memory =====================
@@ -236,25 +288,27 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 				const bool last = c + 1 == prm.nc;
 				const uint32_t lo = last ? lo_l : lo_f, hi = last ? hi_l : hi_f;
 				const uint64_t *wp = row + c * prm.a_words;
-				// first word before the wait (its expansion overlaps the hand-off latency), the rest after it
-				uint32_t v[16];
-				if (lo < hi && !(prm.dbg & 1)) {
-					const uint64_t w = wp[lo];
-					kg_expand_u32((uint32_t)w, v);
-					kg_expand_u32((uint32_t)(w >> 32), v + 8);
+				// Everything that does not need the stage happens BEFORE the wait: this thread's words of the stage
+				// (at most KG_F_MAX_WPT) are loaded and expanded into registers, so that the stage is held only for
+				// the tcgen05.st instructions themselves.
+				uint32_t v[KG_F_MAX_WPT][16];
+				if (!(prm.dbg & 1)) {
+#pragma unroll
+					for (uint32_t i = 0; i < KG_F_MAX_WPT; i++) {
+						if (lo + i < hi) {
+							const uint64_t w = wp[lo + i];
+							kg_expand_u32((uint32_t)w, v[i]);
+							kg_expand_u32((uint32_t)(w >> 32), v[i] + 8);
+						}
+					}
 				}
 				kg_mbar_wait(&a_empty[st], st_par);
 				kg_tc_fence_after();
 				const uint32_t taddr = a_taddr0 + st * a_stage_cols;
 				if (!(prm.dbg & 1)) {
-					for (uint32_t k = lo; k < hi; k++) {
-						if (k > lo) {
-							const uint64_t w = wp[k];
-							kg_expand_u32((uint32_t)w, v);
-							kg_expand_u32((uint32_t)(w >> 32), v + 8);
-						}
-						kg_tmem_st16(taddr + 16 * k, v);
-					}
+#pragma unroll
+					for (uint32_t i = 0; i < KG_F_MAX_WPT; i++)
+						if (lo + i < hi) kg_tmem_st16(taddr + 16 * (lo + i), v[i]);
 					kg_tmem_st_wait();
 				}
 				kg_tc_fence_before();
@@ -369,5 +423,5 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 	// teardown: every role has drained its loop; the last tm_full wait of the epilogue implies all MMAs completed
 	kg_tc_fence_before();
 	__syncthreads();
-	if (warp == 1) kg_tmem_dealloc(tmem_base, KG_F_TMEM_COLS);
+	if (warp == KG_F_MMA_WARP0) kg_tmem_dealloc(tmem_base, KG_F_TMEM_COLS);
 }

@@ -139,12 +139,14 @@ static kg_status kg_tc_update_thresholds(kg_ctx *c, KgFilterGroupConst *gc_pinne
 		KG_CUDA(c, cudaEventSynchronize(tc.img_ev[slot]));
 		int8_t *img = tc.h_img_pinned[slot];
 		memset(img, 0, tc.b_bytes);
-		for (uint32_t i = 0; i < N; i++)  // column 0: 1 on every used file column -> accumulator = KG_F_ONE * popcount
-			img[kg_tc_b_offset(tc, 0, kg_filter_k_of_column(c->map_word[i] * 64 + c->map_bit[i]))] = 1;
+		// The A operand holds -1 (0xFF) for a set presence bit (kg_scan_filter.cuh), so B is stored NEGATED:
+		// (-1) * (-q) = q.  Column 0: -1 on every used file column -> accumulator = row popcount.
+		for (uint32_t i = 0; i < N; i++)
+			img[kg_tc_b_offset(tc, 0, kg_filter_k_of_column(c->map_word[i] * 64 + c->map_bit[i]))] = -1;
 		for (uint32_t p = 0; p < P; p++) {
 			const int8_t *q = tc.h_q.data() + (size_t)p * N;
 			for (uint32_t i = 0; i < N; i++)
-				img[kg_tc_b_offset(tc, col_of[p], kg_filter_k_of_column(c->map_word[i] * 64 + c->map_bit[i]))] = q[i];
+				img[kg_tc_b_offset(tc, col_of[p], kg_filter_k_of_column(c->map_word[i] * 64 + c->map_bit[i]))] = (int8_t)-q[i];   // |q| <= 127
 		}
 		tc.col_of = col_of;
 		// exact-kernel tiles of 8 filter columns -> phenotype index (staged at the tail of the pinned image slot)
@@ -179,10 +181,11 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	// tensor memory: 2 accumulator buffers + the A stages (16 columns per presence word); as few, as large stages as fit
 	if (tc.p_pad <= 128) {
 		const uint32_t a_cols = KG_F_TMEM_COLS - 2 * tc.p_pad;
-		tc.a_words = std::max(1u, std::min<uint32_t>(c->w_file, a_cols / 32));           // at least two stages
+		tc.a_words = std::max(1u, std::min<uint32_t>(c->w_file, a_cols / 32));           // at least two stages (few large stages measured best)
+		tc.a_words = std::min<uint32_t>(tc.a_words, KG_F_MAX_WPT * KG_F_NSUB);            // register budget of the expanders
 		if (const char *e = getenv("KG_FILTER_A_WORDS")) {                                // perf experiments
 			const uint32_t v = (uint32_t)atoi(e);
-			if (v >= 1 && v <= tc.a_words) tc.a_words = v;
+			if (v >= 1 && v <= c->w_file && v <= a_cols / 32 && v <= KG_F_MAX_WPT * KG_F_NSUB) tc.a_words = v;
 		}
 		tc.a_stages = std::max(2u, std::min<uint32_t>(KG_F_MAX_A_STAGES, a_cols / (16 * tc.a_words)));
 		tc.nc = (c->w_file + tc.a_words - 1) / tc.a_words;
@@ -322,6 +325,8 @@ static KgFilterParams kg_tc_filter_params(kg_ctx *c, const uint64_t *dev, uint64
 	f.group_count = tc.d_group_count;
 	f.group_cap = tc.row_list_cap;
 	f.kept_count = c->d_counters + 1;
+	f.n_issuers = KG_F_MMA_WARPS;
+	if (const char *e = getenv("KG_FILTER_ISSUERS")) f.n_issuers = (uint32_t)std::max(1, std::min(KG_F_MMA_WARPS, atoi(e)));   // perf experiments
 	if (const char *e = getenv("KG_FILTER_DEBUG")) f.dbg = (uint32_t)atoi(e);   // perf experiments only (results are wrong)
 	return f;
 }
@@ -440,7 +445,7 @@ static kg_status kg_tc_filter_debug(kg_ctx *c, const uint64_t *dev_in, uint64_t 
 		const uint32_t kpad = 64 * c->w_file;
 		for (uint32_t p = 0; p < c->n_pheno; p++)
 			for (uint32_t col = 0; col < kpad; col++)
-				yq_host[(size_t)p * kpad + col] = tc.h_yq_image[kg_tc_b_offset(tc, tc.col_of[p], kg_filter_k_of_column(col))];
+				yq_host[(size_t)p * kpad + col] = (int8_t)-tc.h_yq_image[kg_tc_b_offset(tc, tc.col_of[p], kg_filter_k_of_column(col))];
 	}
 	return KG_OK;
 }
