@@ -39,6 +39,7 @@ struct kg_ctx {
 	uint32_t n_pheno = 0, p_alloc = 0, pt = 8;
 	uint64_t min_count = 0;
 	float *d_y_lane = nullptr;
+	float *d_y_pair = nullptr;   // the same values in the order kg_scan_pair_kernel reads them (see kg_scan_exact.cuh)
 	float *d_sums = nullptr;
 	double *d_thr = nullptr;
 	std::vector<float> h_y;      // [P][n_used] as given (tensor filter quantises from it)
@@ -289,7 +290,7 @@ extern "C" void kg_ctx_destroy(kg_ctx *c) {
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
 	cudaFree(c->d_map_mem); cudaFree(c->d_map_lane); cudaFree(c->d_file_mask); cudaFree(c->d_mem_mask);
-	cudaFree(c->d_mask32); cudaFree(c->d_y_lane); cudaFree(c->d_sums); cudaFree(c->d_thr);
+	cudaFree(c->d_mask32); cudaFree(c->d_y_lane); cudaFree(c->d_y_pair); cudaFree(c->d_sums); cudaFree(c->d_thr);
 	for (int i = 0; i < 2; i++) {
 		cudaFree(c->iv[i].d_hits); cudaFree(c->iv[i].d_cnt);
 		if (c->iv[i].h_cnt) cudaFreeHost(c->iv[i].h_cnt);
@@ -517,9 +518,22 @@ extern "C" kg_status kg_scan_set_phenotypes(kg_ctx *c, const float *y, uint32_t 
 				for (uint32_t L = 0; L < 4; L++) sum = sum + yl[(size_t)(blk * 4 + L) * 32 + t];
 		c->h_sums[p] = sum;
 	}
-	cudaFree(c->d_y_lane); cudaFree(c->d_sums); cudaFree(c->d_thr);
-	c->d_y_lane = nullptr; c->d_sums = nullptr; c->d_thr = nullptr;
+	cudaFree(c->d_y_lane); cudaFree(c->d_y_pair); cudaFree(c->d_sums); cudaFree(c->d_thr);
+	c->d_y_lane = nullptr; c->d_y_pair = nullptr; c->d_sums = nullptr; c->d_thr = nullptr;
 	KG_CUDA(c, dev_alloc_copy(&c->d_y_lane, y_lane));
+	{
+		// pair mode: y_pair[p][((b * 8 + t4) * 4 + L) * 4 + k] = y_lane[p][(4 b + L) * 32 + 4 t4 + k]: the four lanes of a
+		// pair read 64 contiguous bytes per load instead of four different 128-byte lines
+		std::vector<float> y_pair(y_lane.size());
+		for (uint32_t p = 0; p < c->p_alloc; p++)
+			for (uint32_t b = 0; b < c->nb; b++)
+				for (uint32_t t4 = 0; t4 < 8; t4++)
+					for (uint32_t L = 0; L < 4; L++)
+						for (uint32_t k = 0; k < 4; k++)
+							y_pair[(size_t)p * lane_len + ((size_t)(b * 8 + t4) * 4 + L) * 4 + k] =
+							    y_lane[(size_t)p * lane_len + (size_t)(4 * b + L) * 32 + 4 * t4 + k];
+		KG_CUDA(c, dev_alloc_copy(&c->d_y_pair, y_pair));
+	}
 	KG_CUDA(c, dev_alloc_copy(&c->d_sums, c->h_sums));
 	c->h_thr.assign(c->p_alloc, -1.0);
 	KG_CUDA(c, dev_alloc_copy(&c->d_thr, c->h_thr));
@@ -545,7 +559,7 @@ extern "C" kg_status kg_scan_set_phenotypes(kg_ctx *c, const float *y, uint32_t 
 		c->thr_stage[i].h_thr = nullptr;
 		c->thr_stage[i].h_gc = nullptr;
 		KG_CUDA(c, cudaMallocHost((void **)&c->thr_stage[i].h_thr, (size_t)c->p_alloc * sizeof(double)));
-		KG_CUDA(c, cudaMallocHost((void **)&c->thr_stage[i].h_gc, 16 * 48));
+		KG_CUDA(c, cudaMallocHost((void **)&c->thr_stage[i].h_gc, 16 * 48 + 2 * (size_t)c->p_alloc * sizeof(float)));   // group slots + per-phenotype (alpha, kappa)
 	}
 	kg_status st = kg_tc_prepare_scan(c);
 	return st;
@@ -629,6 +643,7 @@ static KgScanParams scan_params(kg_ctx *c, const KgRowView &view, uint64_t first
 	prm.n_pheno = c->n_pheno;
 	prm.min_count = (uint32_t)std::min<uint64_t>(c->min_count, 0xFFFFFFFFull);
 	prm.y_lane = c->d_y_lane;
+	prm.y_pair = c->d_y_pair;
 	prm.sums = c->d_sums;
 	prm.mask32 = c->d_mask32;
 	prm.thr = c->d_thr;

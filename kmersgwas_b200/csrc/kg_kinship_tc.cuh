@@ -14,9 +14,9 @@
 //
 // Per 128-row block:
 //   warp 0      bulk-copies the raw rows (contiguous bytes) into a 2-stage ring
-//   warps 2-17  MAC filter (masked popcount of every row, rows outside [mac, N - mac] contribute zeros), then expand
-//               the presence bits of the needed sample words to s8 bytes 0x00 / 0xFF (= -1; (-1)(-1) = 1) into
-//               MN-major core matrices (16 samples x 8 rows), 2 stages
+//   warps 2-17  expand the presence bits of the needed sample words to s8 bytes 0x00 / 0xFF (= -1; (-1)(-1) = 1) with
+//               4 PRMTs per 16 samples into MN-major core matrices (16 samples x 8 rows), 2 stages; rows that fail the MAC
+//               filter (keep bits from kg_prefilter_kernel, once per tile) contribute zeros
 //   warp 1      one elected thread issues 4 (K = 32 rows each) x up to 2 tcgen05.mma  D_J += A_I^T-view * B_J
 //               (both operands MN-major: element (sample, row))
 #pragma once
@@ -49,30 +49,30 @@ struct KgKinTcParams {
 	const uint64_t *rows;       // raw tile, 16-byte aligned
 	uint64_t n_rows;
 	uint32_t w_file;
-	const uint64_t *file_mask;  // [w_file] used columns (MAC filter counts only these)
-	uint32_t n_used, min_count;
+	const uint32_t *keep_bits;  // [ceil(n_rows / 32)] MAC filter of load_kmers, one bit per row (kg_prefilter_kernel)
 	const KgKinGroup *groups;
 	const KgKinCta *ctas;       // [gridDim.x]
 	unsigned long long *delta;  // [ld][ld] co-presence counts in FILE column order, entries (a, b <= a)
 	uint32_t ld;                // 64 * w_file
-	unsigned long long *kept_count;
 };
 
 __host__ __device__ inline size_t kg_kin_tc_smem_bytes(uint32_t w_file) {
-	return 1024 + (size_t)KG_K_STAGES * KG_K_STAGE_BYTES + (size_t)KG_K_RAW_STAGES * (KG_K_ROWS * 8u * (w_file + 1)) +
-	       (size_t)w_file * 8 + KG_K_RAW_STAGES * KG_K_ROWS + 256;
+	return 1024 + (size_t)KG_K_STAGES * KG_K_STAGE_BYTES + (size_t)KG_K_RAW_STAGES * (KG_K_ROWS * 8u * (w_file + 1)) + 256;
 }
 
-// 8 presence bits -> 8 bytes 0xFF / 0x00 (byte j <- bit 7 - j, see kg_scan_filter.cuh: both operands of the Gram use
-// the same permutation inside every 8 samples, so it is undone when the accumulators are written out)
-__device__ __forceinline__ uint2 kg_kin_spread8(uint32_t byte) {
-	const uint64_t v = (uint64_t)byte * 0x8040201008040201ull;
-	uint2 r;
-	// prmt selector nibble 8 + k: every bit of result byte k = the sign bit of source byte k  (0x00 / 0xFF)
-	asm("prmt.b32 %0, %1, 0, 0xba98;" : "=r"(r.x) : "r"((uint32_t)v));
-	asm("prmt.b32 %0, %1, 0, 0xba98;" : "=r"(r.y) : "r"((uint32_t)(v >> 32)));
+// 16 presence bits -> 16 operand bytes 0xFF (= -1) / 0x00 with 4 PRMTs (kg_expand_u32 in kg_scan_filter.cuh has the
+// derivation): register b holds the samples 4 n + b of the 16 (n = byte inside the register), i.e. operand index o and
+// file column are related by swapping the two 2-bit fields of the low nibble.  Both operands of the Gram use the same
+// permutation, so it is undone when the accumulators are written out (kg_kin_col_of_operand).
+__device__ __forceinline__ uint4 kg_kin_spread16(uint32_t h) {
+	uint4 r;
+	r.x = kg_prmt(0xFF00FF00u, 0xFF00FF00u, h);
+	r.y = kg_prmt(0xFFFF0000u, 0xFFFF0000u, h);
+	r.z = kg_prmt(0x00000000u, 0xFFFFFFFFu, h);
+	r.w = kg_prmt(0x00000000u, 0xFFFFFFFFu, h >> 1);
 	return r;
 }
+__host__ __device__ inline uint32_t kg_kin_col_of_operand(uint32_t o) { return (o & ~15u) | ((o & 3u) << 2) | ((o >> 2) & 3u); }
 
 __global__ void __launch_bounds__(KG_K_THREADS, 1) kg_kinship_tc_kernel(const KgKinTcParams prm) {
 	extern __shared__ uint8_t kg_k_smem_raw[];
@@ -80,9 +80,7 @@ __global__ void __launch_bounds__(KG_K_THREADS, 1) kg_kinship_tc_kernel(const Kg
 	uint8_t *sStage = base;
 	const uint32_t raw_stage_bytes = KG_K_ROWS * 8u * (prm.w_file + 1);
 	uint8_t *sRaw = sStage + KG_K_STAGES * KG_K_STAGE_BYTES;
-	uint64_t *sMask = reinterpret_cast<uint64_t *>(sRaw + KG_K_RAW_STAGES * raw_stage_bytes);
-	uint8_t *sKeep = reinterpret_cast<uint8_t *>(sMask + prm.w_file);            // [raw stages][128]
-	uint64_t *bars = reinterpret_cast<uint64_t *>(sKeep + KG_K_RAW_STAGES * KG_K_ROWS);
+	uint64_t *bars = reinterpret_cast<uint64_t *>(sRaw + KG_K_RAW_STAGES * raw_stage_bytes);
 	uint64_t *raw_full = bars, *raw_empty = bars + KG_K_RAW_STAGES;
 	uint64_t *st_full = raw_empty + KG_K_RAW_STAGES, *st_empty = st_full + KG_K_STAGES;
 	uint64_t *done = st_empty + KG_K_STAGES;
@@ -101,7 +99,6 @@ __global__ void __launch_bounds__(KG_K_THREADS, 1) kg_kinship_tc_kernel(const Kg
 		kg_mbar_init(done, 1);
 		kg_fence_mbar_init();
 	}
-	for (uint32_t i = threadIdx.x; i < prm.w_file; i += blockDim.x) sMask[i] = prm.file_mask[i];
 	if (warp == 1) kg_tmem_alloc(tmem_slot, 512);
 	kg_tc_fence_before();
 	__syncthreads();
@@ -162,29 +159,22 @@ __global__ void __launch_bounds__(KG_K_THREADS, 1) kg_kinship_tc_kernel(const Kg
 		const uint32_t nb = has2 ? 2u : 1u;
 		const uint32_t n_items = 4 * nb + (grp.a_in < 0 ? 2u : 0u);
 		const uint32_t s_addr = kg_smem_u32(sStage);
-		unsigned long long kept_local = 0;
 		uint32_t it = 0;
 		for (uint32_t blk = me.split; blk < n_blocks; blk += me.n_splits, it++) {
 			const uint32_t rst = it % KG_K_RAW_STAGES, ruse = it / KG_K_RAW_STAGES;
 			kg_mbar_wait(&raw_full[rst], ruse & 1);
 			const uint64_t *row = reinterpret_cast<const uint64_t *>(sRaw + rst * raw_stage_bytes + r * row_bytes) + 1;
-			// MAC filter of load_kmers (:117-121): one thread per row
-			if (sub == 0) {
-				const uint64_t grow = (uint64_t)blk * KG_K_ROWS + r;
-				uint32_t n1 = 0;
-				if (grow < prm.n_rows)
-					for (uint32_t k = 0; k < prm.w_file; k++) n1 += __popcll(row[k] & sMask[k]);
-				const bool keep = grow < prm.n_rows && n1 >= prm.min_count && n1 + prm.min_count <= prm.n_used;
-				sKeep[rst * KG_K_ROWS + r] = keep ? 1 : 0;
-				kept_local += __popc(__ballot_sync(0xffffffffu, keep));
-			}
-			asm volatile("bar.sync 1, %0;" ::"n"(KG_K_EXPAND_THREADS) : "memory");
-			const bool keep = sKeep[rst * KG_K_ROWS + r] != 0;
+			// MAC filter of load_kmers (:117-121): computed once per tile by kg_prefilter_kernel (every tile group reads the
+			// same rows); rows outside [mac, N - mac] contribute zeros
+			const uint64_t grow = (uint64_t)blk * KG_K_ROWS + r;
+			const bool keep = grow < prm.n_rows && ((__ldg(prm.keep_bits + (grow >> 5)) >> (grow & 31)) & 1u);
 
 			const uint32_t st = it % KG_K_STAGES, use = it / KG_K_STAGES;
 			kg_mbar_wait(&st_empty[st], (use & 1) ^ 1);
 			const uint32_t st_base = s_addr + st * KG_K_STAGE_BYTES + (r & 7) * 16;
-			for (uint32_t i = sub; i < n_items; i += KG_K_EXPAND_SUBS) {
+			// items are 32-sample halves of the words (2 n_items of them: 8 .. 20, a multiple of the 4 threads of a row)
+			for (uint32_t hi = sub; hi < 2 * n_items; hi += KG_K_EXPAND_SUBS) {
+				const uint32_t i = hi >> 1, half = hi & 1;
 				uint32_t fw, dst_off, lbo;   // file word, byte offset of its first sample chunk in the stage, row-block stride
 				if (i < 4 * nb) {
 					const uint32_t b = i >> 2, wt = i & 3;
@@ -197,15 +187,11 @@ __global__ void __launch_bounds__(KG_K_THREADS, 1) kg_kinship_tc_kernel(const Kg
 					dst_off = 2 * KG_K_BT_BYTES + wt * 512;
 					lbo = 1024;
 				}
-				const uint64_t w = (keep && fw < prm.w_file) ? row[fw] : 0ull;
-				const uint32_t dst = st_base + dst_off + (r >> 3) * lbo;
-#pragma unroll
-				for (int q = 0; q < 4; q++) {
-					const uint32_t h = (uint32_t)(w >> (16 * q)) & 0xFFFFu;
-					const uint2 lo = kg_kin_spread8(h & 0xFFu), hi = kg_kin_spread8(h >> 8);
-					asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + q * 128), "r"(lo.x), "r"(lo.y), "r"(hi.x), "r"(hi.y)
-					             : "memory");
-				}
+				const uint32_t w = (keep && fw < prm.w_file) ? reinterpret_cast<const uint32_t *>(row + fw)[half] : 0u;
+				const uint32_t dst = st_base + dst_off + (r >> 3) * lbo + half * 256;
+				const uint4 e0 = kg_kin_spread16(w), e1 = kg_kin_spread16(w >> 16);
+				asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(e0.x), "r"(e0.y), "r"(e0.z), "r"(e0.w) : "memory");
+				asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 128), "r"(e1.x), "r"(e1.y), "r"(e1.z), "r"(e1.w) : "memory");
 			}
 			kg_fence_proxy_async();
 			__syncwarp();
@@ -214,7 +200,6 @@ __global__ void __launch_bounds__(KG_K_THREADS, 1) kg_kinship_tc_kernel(const Kg
 				kg_mbar_arrive(&raw_empty[rst]);
 			}
 		}
-		if (lane == 0 && kept_local && me.group == 0) atomicAdd(prm.kept_count, kept_local);
 
 		// ---- flush: TMEM accumulators -> global u64 delta (lower triangle, file column order)
 		if (warp < KG_K_EXPAND_WARP0 + 4 && n_blocks > me.split) {
@@ -222,7 +207,7 @@ __global__ void __launch_bounds__(KG_K_THREADS, 1) kg_kinship_tc_kernel(const Kg
 			kg_tc_fence_after();
 			const uint32_t q4 = warp & 3;
 			const uint32_t a = (uint32_t)grp.i_blk * 128 + q4 * 32 + lane;   // operand row index (permuted inside 8)
-			const uint32_t a_col = (a & ~7u) | (7u - (a & 7u));             // file column of that operand row
+			const uint32_t a_col = kg_kin_col_of_operand(a);                // file column of that operand row
 			for (int b = 0; b < 2; b++) {
 				if (grp.j2[b] < 0) continue;
 				const uint32_t taddr = tmem_base + b * 256 + ((q4 * 32u) << 16);
@@ -233,7 +218,7 @@ __global__ void __launch_bounds__(KG_K_THREADS, 1) kg_kinship_tc_kernel(const Kg
 #pragma unroll
 					for (int j = 0; j < 16; j++) {
 						const uint32_t bb = (uint32_t)grp.j2[b] * 256 + c0 + j;
-						const uint32_t b_col = (bb & ~7u) | (7u - (bb & 7u));
+						const uint32_t b_col = kg_kin_col_of_operand(bb);
 						if (v[j] != 0 && b_col <= a_col && a_col < prm.ld)
 							atomicAdd(prm.delta + (size_t)a_col * prm.ld + b_col, (unsigned long long)v[j]);
 					}

@@ -22,6 +22,7 @@ struct KgScanParams {
 	uint32_t n_pheno;        // P
 	uint32_t min_count;
 	const float *y_lane;     // [P_pad][nb*128]  y_lane[p][(4b+L)*32 + t] = y[p][128b + 32L + 31 - t]
+	const float *y_pair;     // [P_pad][nb*128]  y_pair[p][((8b+t4)*4+L)*4+k] = y_lane[p][(4b+L)*32 + 4 t4 + k]  (pair mode)
 	const float *sums;       // [P_pad] sequential fp32 sum of the permuted padded vector (:288-295)
 	const uint32_t *mask32;  // [nb*4] valid-sample mask of u32 word 4b+L
 	const double *thr;       // [P_pad]
@@ -44,6 +45,10 @@ struct KgScanParams {
 	const int32_t *tile_pheno;
 	unsigned int *tile_chunk_counter;   // [tiles] zeroed before the launch: CTAs of a tile pull chunks of its list dynamically
 	uint32_t list_compact;   // 1: the view holds the listed rows back to back (squeezed copies), indexed by pos
+	uint64_t dense_limit;    // list mode: groups with at most this many entries are left to kg_scan_pair_kernel (0: none)
+	// pair mode (kg_scan_pair_kernel): (position in row_list, phenotype) pairs from kg_pair_select_kernel
+	const uint2 *pairs;
+	const unsigned long long *pair_count;
 };
 
 __device__ __forceinline__ double kg_score_epilogue(float l0, float l1, float l2, float l3, double Nd,
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(256) kg_scan_exact_kernel(const KgScanParams p
 	const uint32_t ng = prm.nb * 4;
 	const uint32_t p0 = blockIdx.y * PT;
 	const uint64_t n_work = (MODE == 2) ? (uint64_t)prm.group_count[blockIdx.y >> 1] : prm.view.n_rows;
-	if (MODE == 2 && n_work == 0) return;   // nothing survived in this tile's group
+	if (MODE == 2 && (n_work == 0 || n_work <= prm.dense_limit)) return;   // nothing survived in this tile's group, or few: pair mode
 
 	// stage this CTA's y tile:  ys[g*GS + t*PT + q] = y_lane[phenotype of slot q][g*32 + t]
 	for (uint32_t i = threadIdx.x; i < ng * 32 * PT; i += blockDim.x) {
@@ -248,6 +253,81 @@ __global__ void __launch_bounds__(256) kg_scan_exact_kernel(const KgScanParams p
 							}
 						}
 					}
+				}
+			}
+		}
+	}
+}
+
+// ---- pair mode: ONE phenotype per listed row ------------------------------------------------------------------
+// Four adjacent lanes (L = 0..3, the reference's SSE lanes) re-score one (row, phenotype) pair: lane L walks the
+// 32-sample quarters 4 b + L of every 128-sample block in the reference's order (kg_scan_exact_kernel has the
+// derivation) with y read straight from global memory (y_pair: L2 / L1 resident, P x N_pad floats, laid out so that
+// the four lanes of a pair read 64 contiguous bytes per load).  Work per pair is N_pad predicated
+// adds instead of the 16 N_pad of the two 8-phenotype tiles a listed (row, group) costs in list mode.
+__global__ void __launch_bounds__(256) kg_scan_pair_kernel(const KgScanParams prm) {
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t L = lane & 3;
+	const uint32_t grp_base = lane & ~3u;
+	const uint64_t n_pairs = *prm.pair_count;
+	const uint32_t *row32 = reinterpret_cast<const uint32_t *>(prm.view.base);
+	const uint32_t stride32 = prm.view.stride * 2;
+	const uint32_t w32_in = prm.view.w_in * 2;
+	const uint32_t ng = prm.nb * 4;
+	const double Nd = (double)prm.n_used;
+	const uint64_t per_pass = ((uint64_t)gridDim.x * blockDim.x) >> 2;
+	// whole warps stay in the loop (shuffles below): the bound is rounded up to the 8 pairs of a warp
+	for (uint64_t item0 = 0; item0 < n_pairs; item0 += per_pass) {
+		const uint64_t item = item0 + ((((uint64_t)blockIdx.x * blockDim.x + threadIdx.x)) >> 2);
+		const bool valid = item < n_pairs;
+		uint32_t pos = 0, p = 0;
+		if (valid) { const uint2 pr = prm.pairs[item]; pos = pr.x; p = pr.y; }
+		const uint64_t id = valid ? (uint64_t)prm.row_list[pos] : 0ull;
+		const uint64_t row = prm.list_compact ? (uint64_t)pos : id;
+		const float4 *yp = reinterpret_cast<const float4 *>(prm.y_pair + (size_t)p * (ng * 32)) + L;
+		float acc = 0.0f;
+		uint32_t n1 = 0;
+		for (uint32_t b = 0; b < prm.nb; b++) {
+			const uint32_t g = b * 4 + L;
+			uint32_t w = 0;
+			if (valid && g < w32_in) w = __ldg(row32 + row * stride32 + 2 + g);
+			w &= prm.mask32[g];
+			n1 += __popc(w);
+#pragma unroll
+			for (int t4 = 0; t4 < 8; t4++) {
+				const float4 f = __ldg(yp + (b * 8 + t4) * 4);
+				const float yv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					float a1[1] = {acc};
+					const float y1[1] = {yv[k]};
+					kg_pred_add<1>(a1, y1, w & (0x80000000u >> (4 * t4 + k)));
+					acc = a1[0];
+				}
+			}
+		}
+		uint32_t c = n1;
+		c += __shfl_xor_sync(0xffffffffu, c, 1);
+		c += __shfl_xor_sync(0xffffffffu, c, 2);
+		const float l0 = __shfl_sync(0xffffffffu, acc, grp_base + 0);
+		const float l1 = __shfl_sync(0xffffffffu, acc, grp_base + 1);
+		const float l2 = __shfl_sync(0xffffffffu, acc, grp_base + 2);
+		const float l3 = __shfl_sync(0xffffffffu, acc, grp_base + 3);
+		// :121  (popcnt >= mac) && (popcnt <= N - mac)  (the filter already applied it; kept for symmetry with list mode)
+		const bool keep = valid && c >= prm.min_count && c + prm.min_count <= prm.n_used;
+		if (L == 0 && keep && p < prm.n_pheno) {
+			const double score = kg_score_epilogue(l0, l1, l2, l3, Nd, (double)c, prm.sums[p]);
+			const double th = prm.thr[p];
+			if (th < 0.0 || score > th) {
+				const unsigned long long at = atomicAdd(prm.hit_count, 1ull);
+				if (at < prm.hit_capacity) {
+					kg_hit h;
+					h.row = prm.first_row_id + id;
+					h.kmer = prm.view.base[row * prm.view.stride];
+					h.score = score;
+					h.pheno = p;
+					h.pad_ = 0;
+					prm.hits[at] = h;
 				}
 			}
 		}

@@ -55,6 +55,7 @@
 #define KG_F_MMA_WARPS 2         // issuers that take turns with the A-stage batches of the MMA stream (see the MMA role below)
 #endif
 #define KG_F_THREADS ((KG_F_MMA_WARP0 + KG_F_MMA_WARPS) * 32)
+#define KG_F_NO_Q INT32_MIN      // ent_q marker: this (row, group) entry has no recorded accumulators
 #define KG_F_ONE 1               // accumulator units per presence bit: A holds -1 (0xFF, s8), B holds the NEGATED phenotype column
 
 // Per 16-column group: the loosest bound of its phenotype columns, in accumulator units (x KG_F_ONE).
@@ -89,6 +90,10 @@ struct KgFilterParams {
 	uint32_t *group_list;      // out: group_list[g * group_cap + k] = position in row_list of the k-th row whose
 	unsigned long long *group_count;   // 16-column group g survived; group_count[g] zeroed before the launch
 	uint64_t group_cap;        // = capacity of row_list (n_rows)
+	// The first qcap entries of every group list also carry what the per-column test (kg_pair_select_kernel) needs:
+	int32_t *ent_q;            // [p_pad / 16][qcap][16] the accumulators of the group's 16 columns (q[0] = KG_F_NO_Q: not recorded)
+	uint32_t *ent_n1;          // [p_pad / 16][qcap] row popcount
+	uint64_t qcap;
 	unsigned long long *kept_count;
 	int32_t *q_out;            // debug mode: [n_rows][p_pad] accumulators
 	uint32_t n_issuers;        // MMA issuer warps in use, 1 .. KG_F_MMA_WARPS
@@ -104,11 +109,6 @@ __host__ __device__ inline size_t kg_filter_smem_bytes(uint32_t w_file, uint32_t
 // 16 columns the two 2-bit fields of the column index are swapped; B is stored with the same permutation.
 __host__ __device__ inline uint32_t kg_filter_k_of_column(uint32_t col) { return (col & ~15u) | ((col & 3u) << 2) | ((col >> 2) & 3u); }
 
-__device__ __forceinline__ uint32_t kg_prmt(uint32_t a, uint32_t b, uint32_t sel) {
-	uint32_t d;
-	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-	return d;
-}
 // 32 presence bits -> 32 s8 operand bytes (0xFF = -1 for a set bit, 0x00) in 8 registers: 8 PRMTs + 3 shifts, ALU
 // pipe only (the former 64-bit multiply per presence byte paid 2 IMADs + 3 ALU operations per 8 bits).
 // PRMT picks result byte n from the 8 bytes {b, a} with selector nibble n (its low 16 bits = 16 presence bits); a
@@ -382,14 +382,36 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 							gmask |= 1u << ((c0 >> 4) + 1);
 					}
 				}
-				// accumulators are in registers: hand the TMEM buffer back to the MMA warp before the bookkeeping
-				kg_tc_fence_before();
-				__syncwarp();
-				if (lane == 0) kg_mbar_arrive(&tm_empty[buf]);
 				// load_kmers :121  (popcnt >= mac) && (popcnt <= N - mac)
 				const bool keep = grow < prm.n_rows && n1 >= prm.min_count && n1 + prm.min_count <= prm.n_used;
 				kept_local += __popc(__ballot_sync(0xffffffffu, keep));
 				if (!keep) gmask = 0;
+				// The 16 accumulators of a row's FIRST surviving group travel with its list entry (per-column re-test,
+				// kg_pair_select_kernel): survivors are rare, so they are re-read from tensor memory here, outside the hot
+				// loop, by the warps that have one (tcgen05.ld is warp-wide: one load per group some lane of the warp needs).
+				const uint32_t kept_k = gmask ? (uint32_t)__ffs(gmask) - 1u : 0xFFFFFFFFu;
+				int32_t keepv[16];
+#pragma unroll
+				for (int j = 0; j < 16; j++) keepv[j] = 0;
+				if (prm.qcap) {
+					uint32_t need = __reduce_or_sync(0xffffffffu, gmask ? 1u << kept_k : 0u);
+					while (need) {
+						const uint32_t k = __ffs(need) - 1;
+						need &= need - 1;
+						uint32_t w[16];
+						kg_tmem_ld16(taddr + 16 * k, w);
+						kg_tmem_ld_wait();
+						if (k == kept_k) {
+#pragma unroll
+							for (int j = 0; j < 16; j++) keepv[j] = (int32_t)w[j];
+							if (k == 0) keepv[0] = 0;   // column 0 is the popcount column
+						}
+					}
+				}
+				// accumulators are in registers: hand the TMEM buffer back to the MMA warp before the bookkeeping
+				kg_tc_fence_before();
+				__syncwarp();
+				if (lane == 0) kg_mbar_arrive(&tm_empty[buf]);
 				// rows that could not be ruled out go to the exact kernel, which re-scores them (in the reference's fp32
 				// order) against the phenotypes of the surviving groups only; one atomic per warp and list
 				const uint32_t mb = __ballot_sync(0xffffffffu, gmask != 0);
@@ -407,7 +429,20 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 						unsigned long long gbase = 0;
 						if (lane == 0) gbase = atomicAdd(prm.group_count + k, (unsigned long long)__popc(gb));
 						gbase = __shfl_sync(0xffffffffu, gbase, 0);
-						if ((gmask >> k) & 1u) prm.group_list[(size_t)k * prm.group_cap + gbase + __popc(gb & ((1u << lane) - 1u))] = pos;
+						if ((gmask >> k) & 1u) {
+							const uint64_t idx = gbase + __popc(gb & ((1u << lane) - 1u));
+							prm.group_list[(size_t)k * prm.group_cap + idx] = pos;
+							if (idx < prm.qcap) {
+								prm.ent_n1[(size_t)k * prm.qcap + idx] = n1;
+								int4 *q = reinterpret_cast<int4 *>(prm.ent_q + ((size_t)k * prm.qcap + idx) * 16);
+								if (k == kept_k) {
+#pragma unroll
+									for (int j = 0; j < 4; j++) q[j] = make_int4(keepv[4 * j], keepv[4 * j + 1], keepv[4 * j + 2], keepv[4 * j + 3]);
+								} else {
+									q[0] = make_int4(KG_F_NO_Q, 0, 0, 0);   // a second surviving group of the same row: columns untested
+								}
+							}
+						}
 					}
 				}
 			}
@@ -424,4 +459,67 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 	kg_tc_fence_before();
 	__syncthreads();
 	if (warp == KG_F_MMA_WARP0) kg_tmem_dealloc(tmem_base, KG_F_TMEM_COLS);
+}
+
+// ---- per-column test of the listed (row, group) entries ------------------------------------------------------------
+// The filter kernel tests 16 columns at a time against the group's loosest bound.  For the groups whose list is short
+// (<= dense_limit entries: the normal case once the heaps are warm) this kernel repeats the test per COLUMN with the
+// phenotype's own constants -- alpha_p, kappa_p and the exact slack table F_p(m) instead of the group's tangents -- and
+// emits (list position, phenotype) pairs for kg_scan_pair_kernel, which re-scores ONE phenotype per pair in the
+// reference's fp32 order instead of two tiles of 8.  Groups with longer lists stay with kg_scan_exact_kernel (list mode).
+struct KgPairSelectParams {
+	const unsigned long long *group_count;   // [n_groups]
+	const uint32_t *group_list;              // [n_groups][group_cap] positions in row_list
+	uint64_t group_cap;
+	const int32_t *ent_q;
+	const uint32_t *ent_n1;
+	uint64_t qcap, dense_limit;              // dense_limit <= qcap
+	uint32_t n_groups, n_used;
+	const int32_t *tile_pheno;               // [16 n_groups] phenotype of every filter column, -1 = none
+	const float *alpha, *kappa;              // [P] in accumulator units, rounded like the group constants
+	const float *slack;                      // [P][n_used / 2 + 1] F_p(m), rounded up
+	uint2 *pairs;                            // out: (position in row_list, phenotype)
+	unsigned long long *pair_count;          // zeroed before the launch
+	uint64_t pair_cap;
+	unsigned long long *overflow;            // set if pairs ran out of room (cannot happen with pair_cap = 16 n_groups dense_limit)
+};
+
+__global__ void __launch_bounds__(256) kg_pair_select_kernel(const KgPairSelectParams prm) {
+	const uint64_t total = (uint64_t)prm.n_groups * prm.dense_limit;
+	const uint32_t m_stride = prm.n_used / 2 + 1;
+	const float Nf = (float)prm.n_used;
+	for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+		const uint32_t k = (uint32_t)(e / prm.dense_limit);
+		const uint64_t idx = e - (uint64_t)k * prm.dense_limit;
+		const uint64_t cnt = prm.group_count[k];
+		if (cnt > prm.dense_limit || idx >= cnt) continue;
+		const uint32_t pos = prm.group_list[(size_t)k * prm.group_cap + idx];
+		const uint32_t n1 = prm.ent_n1[(size_t)k * prm.qcap + idx];
+		const int4 *qp = reinterpret_cast<const int4 *>(prm.ent_q + ((size_t)k * prm.qcap + idx) * 16);
+		int32_t q[16];
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const int4 t = qp[j];
+			q[4 * j] = t.x; q[4 * j + 1] = t.y; q[4 * j + 2] = t.z; q[4 * j + 3] = t.w;
+		}
+		const bool untested = q[0] == KG_F_NO_Q;
+		const float n1f = (float)n1, n0f = Nf - n1f;
+		const uint32_t m = (uint32_t)fminf(n1f, n0f);
+		const float g = __fmul_rd(__fsqrt_rd(n1f * n0f), 0.999999f);   // as in the filter epilogue
+#pragma unroll
+		for (int j = 0; j < 16; j++) {
+			const int32_t ph = prm.tile_pheno[16 * k + j];
+			if (ph < 0) continue;
+			bool list = untested;
+			if (!list) {
+				const float thr = __fsub_rd(__fmaf_rd(prm.alpha[ph], g, -prm.kappa[ph]), prm.slack[(size_t)ph * m_stride + m]);
+				list = !((float)abs(q[j]) < thr);
+			}
+			if (list) {
+				const unsigned long long at = atomicAdd(prm.pair_count, 1ull);
+				if (at < prm.pair_cap) prm.pairs[at] = make_uint2(pos, (uint32_t)ph);
+				else *prm.overflow = 1ull;
+			}
+		}
+	}
 }

@@ -8,6 +8,8 @@
 
 static void kg_tc_free(KgTcState *tc) {
 	cudaFree(tc->d_row_list); cudaFree(tc->d_group_list); cudaFree(tc->d_group_count); cudaFree(tc->d_tile_pheno);
+	cudaFree(tc->d_ent_q); cudaFree(tc->d_ent_n1); cudaFree(tc->d_pairs); cudaFree(tc->d_slack);
+	tc->d_ent_q = nullptr; tc->d_ent_n1 = nullptr; tc->d_pairs = nullptr; tc->d_slack = nullptr; tc->qcap = 0;
 	tc->d_group_list = nullptr; tc->d_group_count = nullptr; tc->d_tile_pheno = nullptr;
 	cudaFree(tc->d_yq); cudaFree(tc->d_gconst); cudaFree(tc->d_kin_groups); cudaFree(tc->d_kin_delta); cudaFree(tc->d_kin_ctas);
 	tc->d_kin_groups = nullptr; tc->d_kin_delta = nullptr; tc->d_kin_ctas = nullptr; cudaFree(tc->d_scratch); cudaFree(tc->d_aligned);
@@ -158,7 +160,10 @@ static kg_status kg_tc_update_thresholds(kg_ctx *c, KgFilterGroupConst *gc_pinne
 		KG_CUDA(c, cudaMemcpyAsync(tc.d_yq, img, tc.b_bytes, cudaMemcpyHostToDevice, c->stream));
 		KG_CUDA(c, cudaEventRecord(tc.img_ev[slot], c->stream));
 	}
-	KG_CUDA(c, cudaMemcpyAsync(tc.d_gconst, gc, n_groups * sizeof(KgFilterGroupConst), cudaMemcpyHostToDevice, c->stream));
+	// per-phenotype constants of the per-column test follow the 16 group slots (same staging slot, one copy)
+	float *pc = reinterpret_cast<float *>(gc + 16);
+	for (uint32_t p = 0; p < P; p++) { pc[p] = alpha[p]; pc[P + p] = kappa[p]; }
+	KG_CUDA(c, cudaMemcpyAsync(tc.d_gconst, gc, 16 * sizeof(KgFilterGroupConst) + 2 * (size_t)P * sizeof(float), cudaMemcpyHostToDevice, c->stream));
 	return KG_OK;
 }
 
@@ -269,8 +274,15 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc tile table: %s", cudaGetErrorString(e));
 	e = cudaMalloc((void **)&tc.d_group_count, (16 + 16) * sizeof(unsigned long long));   // + 32 u32 tile chunk counters
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc group counters: %s", cudaGetErrorString(e));
-	e = cudaMalloc((void **)&tc.d_gconst, (tc.p_pad / 16) * sizeof(KgFilterGroupConst));
+	e = cudaMalloc((void **)&tc.d_gconst, 16 * sizeof(KgFilterGroupConst) + 2 * (size_t)P * sizeof(float));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc filter constants: %s", cudaGetErrorString(e));
+	cudaFree(tc.d_slack);
+	tc.d_slack = nullptr;
+	static_assert(KG_F_ONE == 1, "the slack table is uploaded in accumulator units");
+	e = cudaMalloc((void **)&tc.d_slack, tc.slack_table.size() * sizeof(float));
+	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc slack table: %s", cudaGetErrorString(e));
+	KG_CUDA(c, cudaMemcpyAsync(tc.d_slack, tc.slack_table.data(), tc.slack_table.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+	tc.use_pairs = !(getenv("KG_FILTER_NO_PAIRS") && atoi(getenv("KG_FILTER_NO_PAIRS")));   // perf experiments: list mode only
 	KG_CUDA(c, cudaFuncSetAttribute(kg_scan_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	KG_CUDA(c, cudaFuncSetAttribute(kg_scan_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	tc.scan_ready = true;
@@ -324,6 +336,9 @@ static KgFilterParams kg_tc_filter_params(kg_ctx *c, const uint64_t *dev, uint64
 	f.group_list = tc.d_group_list;
 	f.group_count = tc.d_group_count;
 	f.group_cap = tc.row_list_cap;
+	f.ent_q = tc.d_ent_q;
+	f.ent_n1 = tc.d_ent_n1;
+	f.qcap = tc.use_pairs ? tc.qcap : 0;
 	f.kept_count = c->d_counters + 1;
 	f.n_issuers = KG_F_MMA_WARPS;
 	if (const char *e = getenv("KG_FILTER_ISSUERS")) f.n_issuers = (uint32_t)std::max(1, std::min(KG_F_MMA_WARPS, atoi(e)));   // perf experiments
@@ -346,6 +361,19 @@ static kg_status kg_tc_ensure_row_list(kg_ctx *c, uint64_t n_rows) {
 	e = cudaMalloc((void **)&tc.d_group_list, (size_t)(tc.p_pad / 16) * cap * sizeof(uint32_t));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc filter group lists: %s", cudaGetErrorString(e));
 	tc.row_list_cap = cap;
+	// entries that carry their accumulators: the first qcap of every group list (longer lists stay in list mode)
+	cudaFree(tc.d_ent_q); cudaFree(tc.d_ent_n1); cudaFree(tc.d_pairs);
+	tc.d_ent_q = nullptr; tc.d_ent_n1 = nullptr; tc.d_pairs = nullptr;
+	// measured (B200, P = 101): a pair costs ~1.3 ns, a list-mode entry ~3.9 ns, and the per-column test leaves about
+	// one pair per entry, so pair mode wins for every list that is not most of the tile
+	tc.qcap = std::max<uint64_t>(4096, cap / 16);
+	const size_t n_groups = tc.p_pad / 16;
+	e = cudaMalloc((void **)&tc.d_ent_q, n_groups * tc.qcap * 16 * sizeof(int32_t));
+	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc filter entry sums: %s", cudaGetErrorString(e));
+	e = cudaMalloc((void **)&tc.d_ent_n1, n_groups * tc.qcap * sizeof(uint32_t));
+	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc filter entry counts: %s", cudaGetErrorString(e));
+	e = cudaMalloc((void **)&tc.d_pairs, n_groups * tc.qcap * 16 * sizeof(uint2));
+	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc pair list: %s", cudaGetErrorString(e));
 	return KG_OK;
 }
 
@@ -400,9 +428,49 @@ static kg_status kg_tc_scan_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_r
 	prm.tile_chunk_counter = reinterpret_cast<unsigned int *>(tc.d_group_count + 16);
 	prm.list_compact = compact;
 	timing_begin(c, KG_KERNEL_SCAN_REFINE, 0);
+	if (tc.use_pairs) {
+		// short group lists: per-column re-test, then one phenotype per (row, phenotype) pair
+		unsigned long long *pair_count = tc.d_group_count + 24;   // [24] pairs [25] overflow flag (both zeroed above)
+		KgPairSelectParams ps;
+		memset(&ps, 0, sizeof ps);
+		ps.group_count = tc.d_group_count;
+		ps.group_list = tc.d_group_list;
+		ps.group_cap = tc.row_list_cap;
+		ps.ent_q = tc.d_ent_q;
+		ps.ent_n1 = tc.d_ent_n1;
+		ps.qcap = tc.qcap;
+		ps.dense_limit = tc.qcap;
+		ps.n_groups = tc.p_pad / 16;
+		ps.n_used = (uint32_t)c->n_used;
+		ps.tile_pheno = tc.d_tile_pheno;
+		ps.alpha = reinterpret_cast<const float *>(tc.d_gconst + 16);
+		ps.kappa = ps.alpha + c->n_pheno;
+		ps.slack = tc.d_slack;
+		ps.pairs = tc.d_pairs;
+		ps.pair_count = pair_count;
+		ps.pair_cap = (uint64_t)ps.n_groups * tc.qcap * 16;
+		ps.overflow = pair_count + 1;
+		const uint64_t entries = std::min<uint64_t>((uint64_t)ps.n_groups * tc.qcap, (uint64_t)ps.n_groups * n_rows);
+		const unsigned sel_grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((entries + 255) / 256, (uint64_t)c->sm_count * 8));
+		kg_pair_select_kernel<<<sel_grid, 256, 0, c->stream>>>(ps);
+		KG_LAUNCH_CHECK(c);
+		prm.dense_limit = tc.qcap;
+		prm.pairs = tc.d_pairs;
+		prm.pair_count = pair_count;
+		kg_scan_pair_kernel<<<(unsigned)c->sm_count * 8, 256, 0, c->stream>>>(prm);
+		KG_LAUNCH_CHECK(c);
+	}
 	st = launch_exact_list(c, prm, tc.p_pad / 8);
 	timing_end(c);
 	if (st != KG_OK) return st;
+	if (getenv("KG_FILTER_STATS")) {   // diagnosis only: synchronises the stream
+		unsigned long long h[32];
+		cudaStreamSynchronize(c->stream);
+		cudaMemcpy(h, tc.d_group_count, sizeof h, cudaMemcpyDeviceToHost);
+		fprintf(stderr, "[kg filter] rows %llu qcap %llu groups:", (unsigned long long)n_rows, (unsigned long long)tc.qcap);
+		for (uint32_t g = 0; g < tc.p_pad / 16; g++) fprintf(stderr, " %llu", h[g]);
+		fprintf(stderr, "  pairs %llu\n", h[24]);
+	}
 	kg_add_counter_kernel<<<1, 1, 0, c->stream>>>(c->d_counters + 2, c->d_counters + 5);
 	KG_LAUNCH_CHECK(c);
 	kg_sum_counters_kernel<<<1, 1, 0, c->stream>>>(tc.d_group_count, tc.p_pad / 16, c->d_counters + 6);
@@ -519,14 +587,32 @@ static kg_status kg_tc_kinship_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t 
 	k.rows = dev;
 	k.n_rows = n_rows;
 	k.w_file = c->w_file;
-	k.file_mask = c->d_file_mask;
-	k.n_used = (uint32_t)c->n_used;
-	k.min_count = (uint32_t)std::min<uint64_t>(c->kin_min_count, 0xFFFFFFFFull);
+	// MAC filter bits + kept-row count, once per tile (every tile group of the Gram kernel reads the same rows)
+	const size_t kb_need = (size_t)((n_rows + 31) / 32);
+	if (c->keep_bits_cap < kb_need) {
+		KG_CUDA(c, cudaStreamSynchronize(c->stream));
+		cudaFree(c->d_keep_bits);
+		c->d_keep_bits = nullptr;
+		c->keep_bits_cap = 0;
+		cudaError_t me = cudaMalloc((void **)&c->d_keep_bits, kb_need * 4);
+		if (me != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc keep bits: %s", cudaGetErrorString(me));
+		c->keep_bits_cap = kb_need;
+	}
+	{
+		const KgRowView raw{dev, n_rows, c->w_file + 1, c->w_file};
+		const unsigned grid = (unsigned)std::min<uint64_t>((n_rows + 255) / 256, (uint64_t)c->sm_count * 8);
+		timing_begin(c, KG_KERNEL_AUX, n_rows);
+		kg_prefilter_kernel<<<std::max(grid, 1u), 256, 0, c->stream>>>(raw, c->d_file_mask, (uint32_t)c->n_used,
+		                                                               (uint32_t)std::min<uint64_t>(c->kin_min_count, 0xFFFFFFFFull),
+		                                                               c->d_keep_bits, tc.d_kin_delta + (size_t)ld * ld);
+		timing_end(c);
+		KG_LAUNCH_CHECK(c);
+	}
+	k.keep_bits = c->d_keep_bits;
 	k.groups = tc.d_kin_groups;
 	k.ctas = tc.d_kin_ctas;
 	k.delta = tc.d_kin_delta;
 	k.ld = ld;
-	k.kept_count = tc.d_kin_delta + (size_t)ld * ld;
 	timing_begin(c, KG_KERNEL_KINSHIP, n_rows);
 	kg_kinship_tc_kernel<<<tc.kin_ctas, KG_K_THREADS, tc.kin_smem, c->stream>>>(k);
 	timing_end(c);

@@ -18,6 +18,13 @@ __device__ __forceinline__ bool kg_elect_one() {
 	return pred != 0;
 }
 
+// byte permute (PRMT): result byte n = byte (sel nibble n & 7) of {b, a}; nibble bit 3 replicates that byte's sign
+__device__ __forceinline__ uint32_t kg_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+	uint32_t d;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+	return d;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------
 __device__ __forceinline__ void kg_mbar_init(uint64_t *bar, uint32_t count) {
 	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(kg_smem_u32(bar)), "r"(count) : "memory");

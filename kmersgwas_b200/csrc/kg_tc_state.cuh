@@ -15,6 +15,13 @@ struct KgTcState {
 	uint32_t *d_group_list = nullptr;      // [p_pad / 16][row_list_cap] positions in d_row_list, per 16-column group
 	unsigned long long *d_group_count = nullptr;   // [16]
 	int32_t *d_tile_pheno = nullptr;       // [p_pad] phenotype of every filter column (-1: none)
+	// per-column re-test of the short group lists (kg_pair_select_kernel) and pair-mode re-scoring
+	int32_t *d_ent_q = nullptr;            // [p_pad / 16][qcap][16]
+	uint32_t *d_ent_n1 = nullptr;          // [p_pad / 16][qcap]
+	uint2 *d_pairs = nullptr;              // [16 (p_pad / 16) qcap]
+	uint64_t qcap = 0;
+	float *d_slack = nullptr;              // [P][n_used / 2 + 1] = slack_table
+	bool use_pairs = true;
 	// scan filter: quantised centred phenotypes in UMMA (K-major core matrix) layout + per-phenotype constants
 	int8_t *d_yq = nullptr;
 	struct KgFilterGroupConst *d_gconst = nullptr;   // [p_pad / 16] per column group, see kg_scan_filter.cuh
