@@ -4,8 +4,8 @@
 // phenotype values (hard part 2).  The reference's result is defined by a float32
 // summation order, so the tensor core cannot produce it -- but it can prove, for almost every
 // (row, phenotype) pair, that the reference score cannot exceed the heap threshold.  Only the pairs it
-// cannot rule out send their ROW to the exact kernel (kg_scan_exact_kernel in row-list mode), so the reported
-// hits stay bit-identical.
+// cannot rule out are re-scored in the reference's fp32 order (kg_scan_pair_kernel per (row, phenotype) pair;
+// kg_scan_exact_kernel in row-list mode for column groups with long lists), so the reported hits stay bit-identical.
 //
 // Bound (DESIGN.md section 4 has the derivation).  Per phenotype p, host side (kg_tc.cuh):
 //   ybar = sum_ref / N,  c_i = y_i - ybar,  s = max|c_i| / 127,  q_i = rint(c_i / s) in [-127, 127],
@@ -20,20 +20,24 @@
 // The phenotype columns are sorted by alpha and tested 16 at a time: max |Q| of the group against the group's
 // smallest alpha and largest kappa.  A row with no surviving group is ruled out for every phenotype.
 //
-// Kernel: persistent, one CTA per SM, 128-row blocks, warp-specialised:
-//   warp 0      bulk-async-copies raw 128-row blocks (contiguous 128 * 8(1+W) bytes) into a 2-stage ring
-//   warps 2-13  expand presence bits -> u8 {0,0x80} with one 64-bit multiply per presence byte and store them with
-//               tcgen05.st straight into TENSOR MEMORY (A operand from TMEM: lane = row, 4 bytes of K per column);
-//               TMEM holds the two accumulator buffers (2 x P_pad columns) and the A stages: at N = 1135, P = 101 that
-//               is 2 x 112 + 2 x 144 columns = two stages of half a row block each (every stage hand-off costs a
-//               barrier round trip of ~1.5 k cycles, so few large stages beat many small ones)
-//   warp 1      one elected thread issues tcgen05.mma kind::i8 (M = 128, N = P_pad, K = 32 per instruction, A from
-//               TMEM, B from shared memory) into a double-buffered TMEM accumulator; B (quantised phenotypes,
-//               P_pad x K_pad s8, K-major core matrices, no swizzle) stays resident in shared memory
-//   warps 14-21 epilogue (two sets of 4 warps alternate blocks, one accumulator buffer each): tcgen05.ld of the 128 x P_pad accumulators; column 0 of B is all-ones over the used
-//               columns, so its accumulator is the row popcount (MAC filter) for free; pass 1 takes max |Q| over the
-//               row with 3-input min/max and rules the whole row out against the loosest column bound; rows that
-//               survive (rare) are appended to a global row list for the exact kernel
+// Kernel: persistent, one CTA per SM, 128-row blocks, warp-specialised (23 warps):
+//   warp 0        bulk-async-copies raw 128-row blocks (contiguous 128 * 8(1+W) bytes) into a 4-stage ring
+//   warps 1-12    expanders: presence bits -> s8 {0, -1} with 8 PRMTs per 32 bits (byte-permute against constant
+//                 tables, ALU pipe only), stored with tcgen05.st straight into TENSOR MEMORY (A operand from TMEM: lane =
+//                 row, 4 bytes of K per column).  TMEM holds the two accumulator buffers (2 x P_pad columns) and the A
+//                 stages: at N = 1135, P = 101 that is 2 x 112 + 2 x 144 columns = two stages of half a row block each.
+//                 A thread expands its words of a stage BEFORE it waits for the stage, so the stage is held only for
+//                 the stores.
+//   warps 21-22   MMA issuers: tcgen05.mma kind::i8 (M = 128, N = P_pad, K = 32 per instruction, A from TMEM, B from
+//                 shared memory) into a double-buffered TMEM accumulator; B (negated quantised phenotypes, P_pad x K_pad
+//                 s8, K-major core matrices, no swizzle) stays resident in shared memory.  TWO issuers take turns with
+//                 the A-stage batches because a tcgen05.commit stalls its issuing thread for ~670 cycles (measured:
+//                 profiles/probes/umma_rate.cu, profiles/r01_umma_probe.md) -- see the role's comment.
+//   warps 13-20   epilogue (two sets of 4 warps alternate blocks, one accumulator buffer each): tcgen05.ld of the
+//                 128 x P_pad accumulators; column 0 of B is -1 over the used columns, so its accumulator is the row
+//                 popcount (MAC filter) for free; per 16-column group max |Q| (3-input min/max) against the group's
+//                 loosest bound; (row, group) pairs that survive (rare) are appended to the group's list together with
+//                 the row popcount and the group's 16 accumulators, for the per-column re-test (kg_pair_select_kernel)
 #pragma once
 #include "kg_common.cuh"
 #include "kg_tc_ptx.cuh"
