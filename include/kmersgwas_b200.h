@@ -68,8 +68,12 @@ enum {
 	KG_OPT_SCAN_ENGINE = 1, /* 0 = auto, 1 = exact fp32-order kernel on every row, 2 = int8 tensor filter + exact refine */
 	KG_OPT_HIT_CAPACITY = 2, /* number of kg_hit the device hit buffer holds (default 1<<22); set before first submit */
 	KG_OPT_KINSHIP_ENGINE = 3, /* 0 = auto, 1 = popcount kernel, 2 = int8 tensor-core Gram */
-	KG_OPT_KERNEL_TIMING = 4   /* 1 = bracket every hot-path kernel launch with CUDA events on the context's stream
+	KG_OPT_KERNEL_TIMING = 4,  /* 1 = bracket every hot-path kernel launch with CUDA events on the context's stream
 	                              (read back with kg_kernel_time); 0 = off (default) */
+	KG_OPT_FILTER_PAIR_LIMIT = 5 /* tensor filter: column groups whose list of surviving rows has at most this many
+	                              entries are re-tested per phenotype column and re-scored as single (row, phenotype)
+	                              pairs; longer lists are re-scored 16 phenotypes at a time.  0 = never use pair
+	                              mode, -1 = default (1/16 of the tile capacity).  Results are identical either way. */
 };
 
 /* Kernel classes reported by kg_kernel_time */

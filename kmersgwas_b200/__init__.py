@@ -8,7 +8,7 @@ Layout:
 """
 from . import build  # noqa: F401
 from ._abi import Context, KgError, HIT_DTYPE, ABI_SYMBOLS, load, lib_path  # noqa: F401
-from ._abi import OPT_SCAN_ENGINE, OPT_HIT_CAPACITY, OPT_KINSHIP_ENGINE, OPT_KERNEL_TIMING  # noqa: F401
+from ._abi import OPT_SCAN_ENGINE, OPT_HIT_CAPACITY, OPT_KINSHIP_ENGINE, OPT_KERNEL_TIMING, OPT_FILTER_PAIR_LIMIT  # noqa: F401
 from ._abi import KERNEL_CLASS_NAMES, kernel_times  # noqa: F401
 
 from ._host import Session, HeapSet  # noqa: F401

@@ -15,7 +15,7 @@ from . import build as _build
 
 KG_OK = 0
 KG_ERR_HITS_OVERFLOW = 4
-OPT_SCAN_ENGINE, OPT_HIT_CAPACITY, OPT_KINSHIP_ENGINE, OPT_KERNEL_TIMING = 1, 2, 3, 4
+OPT_SCAN_ENGINE, OPT_HIT_CAPACITY, OPT_KINSHIP_ENGINE, OPT_KERNEL_TIMING, OPT_FILTER_PAIR_LIMIT = 1, 2, 3, 4, 5
 KERNEL_SCAN_EXACT, KERNEL_SCAN_FILTER, KERNEL_SCAN_REFINE, KERNEL_KINSHIP, KERNEL_AUX = 0, 1, 2, 3, 4
 KERNEL_CLASS_NAMES = ["scan_exact", "scan_filter", "scan_refine", "kinship", "aux"]
 

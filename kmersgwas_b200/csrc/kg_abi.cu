@@ -339,6 +339,10 @@ extern "C" kg_status kg_set_option(kg_ctx *c, int option, int64_t value) {
 	case KG_OPT_KERNEL_TIMING:
 		c->timing = value != 0;
 		return KG_OK;
+	case KG_OPT_FILTER_PAIR_LIMIT:
+		if (value < -1) KG_FAIL(c, KG_ERR_INVALID, "filter pair limit must be >= -1");
+		c->tc.pair_limit = value;
+		return KG_OK;
 	default:
 		KG_FAIL(c, KG_ERR_INVALID, "unknown option %d", option);
 	}

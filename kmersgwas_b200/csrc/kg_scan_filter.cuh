@@ -120,7 +120,7 @@ __host__ __device__ inline uint32_t kg_filter_k_of_column(uint32_t col) { return
 // selector nibble means "replicate the sign of the selected byte", which maps 0xFF / 0x00 onto themselves, so the
 // other bits of a nibble never disturb the result; bit 3 itself is read as bit 2 of (x >> 1).
 __device__ __forceinline__ void kg_expand_u32(uint32_t x, uint32_t *out8) {
-	const uint32_t x1 = x >> 1, y = x >> 16, y1 = x >> 17;
+	const uint32_t x1 = x >> 1, y = x >> 16, y1 = x >> 17;   // (IMAD.HI shifts on the FMA pipe measured no faster)
 	out8[0] = kg_prmt(0xFF00FF00u, 0xFF00FF00u, x);
 	out8[1] = kg_prmt(0xFFFF0000u, 0xFFFF0000u, x);
 	out8[2] = kg_prmt(0x00000000u, 0xFFFFFFFFu, x);

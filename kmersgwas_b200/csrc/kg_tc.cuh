@@ -428,7 +428,7 @@ static kg_status kg_tc_scan_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_r
 	prm.tile_chunk_counter = reinterpret_cast<unsigned int *>(tc.d_group_count + 16);
 	prm.list_compact = compact;
 	timing_begin(c, KG_KERNEL_SCAN_REFINE, 0);
-	if (tc.use_pairs) {
+	if (tc.use_pairs && tc.pair_limit != 0) {
 		// short group lists: per-column re-test, then one phenotype per (row, phenotype) pair
 		unsigned long long *pair_count = tc.d_group_count + 24;   // [24] pairs [25] overflow flag (both zeroed above)
 		KgPairSelectParams ps;
@@ -439,7 +439,8 @@ static kg_status kg_tc_scan_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_r
 		ps.ent_q = tc.d_ent_q;
 		ps.ent_n1 = tc.d_ent_n1;
 		ps.qcap = tc.qcap;
-		ps.dense_limit = tc.qcap;
+		const uint64_t dense_limit = tc.pair_limit < 0 ? tc.qcap : std::min<uint64_t>(tc.qcap, (uint64_t)tc.pair_limit);
+		ps.dense_limit = dense_limit;
 		ps.n_groups = tc.p_pad / 16;
 		ps.n_used = (uint32_t)c->n_used;
 		ps.tile_pheno = tc.d_tile_pheno;
@@ -454,7 +455,7 @@ static kg_status kg_tc_scan_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_r
 		const unsigned sel_grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((entries + 255) / 256, (uint64_t)c->sm_count * 8));
 		kg_pair_select_kernel<<<sel_grid, 256, 0, c->stream>>>(ps);
 		KG_LAUNCH_CHECK(c);
-		prm.dense_limit = tc.qcap;
+		prm.dense_limit = dense_limit;
 		prm.pairs = tc.d_pairs;
 		prm.pair_count = pair_count;
 		kg_scan_pair_kernel<<<(unsigned)c->sm_count * 8, 256, 0, c->stream>>>(prm);

@@ -24,7 +24,6 @@ __device__ __forceinline__ uint32_t kg_prmt(uint32_t a, uint32_t b, uint32_t sel
 	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
 	return d;
 }
-
 // ---- mbarrier ---------------------------------------------------------------------------------
 __device__ __forceinline__ void kg_mbar_init(uint64_t *bar, uint32_t count) {
 	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(kg_smem_u32(bar)), "r"(count) : "memory");

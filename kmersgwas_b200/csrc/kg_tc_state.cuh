@@ -22,6 +22,7 @@ struct KgTcState {
 	uint64_t qcap = 0;
 	float *d_slack = nullptr;              // [P][n_used / 2 + 1] = slack_table
 	bool use_pairs = true;
+	int64_t pair_limit = -1;               // KG_OPT_FILTER_PAIR_LIMIT
 	// scan filter: quantised centred phenotypes in UMMA (K-major core matrix) layout + per-phenotype constants
 	int8_t *d_yq = nullptr;
 	struct KgFilterGroupConst *d_gconst = nullptr;   // [p_pad / 16] per column group, see kg_scan_filter.cuh

@@ -65,8 +65,12 @@ def test_filter_sums_subset_columns_and_device_rows(kg):
     ctx.close()
 
 
+# pair_limit: -1 = default (every list of these small tiles goes through the per-column re-test and pair mode),
+# 0 = list mode only (16 phenotypes per listed row), 1500 = mixed: the cold column's group is "dense" (every kept row
+# of a 7001-row tile is listed for it) and stays in list mode, the other groups go through pair mode
+@pytest.mark.parametrize("pair_limit", [-1, 0, 1500])
 @pytest.mark.parametrize("n_file,n_pheno", [(241, 8), (1135, 101), (96, 3)])
-def test_filter_engine_hits_identical_to_exact_engine(kg, n_file, n_pheno):
+def test_filter_engine_hits_identical_to_exact_engine(kg, n_file, n_pheno, pair_limit):
     n_rows = 20000
     table = S.synth_table(300 + n_file, n_rows, n_file)
     y = S.synth_phenotypes(400 + n_file, n_file, n_pheno)
@@ -80,6 +84,7 @@ def test_filter_engine_hits_identical_to_exact_engine(kg, n_file, n_pheno):
     for engine in (1, 2):
         ctx = kg.Context.identity(n_file)
         ctx.set_option(kg.OPT_SCAN_ENGINE, engine)
+        ctx.set_option(kg.OPT_FILTER_PAIR_LIMIT, pair_limit)
         ctx.set_phenotypes(y, mc)
         ctx.set_thresholds(thr)
         for r0 in range(0, n_rows, 7001):     # several ragged tiles between two fetches
