@@ -489,14 +489,25 @@ struct KgPairSelectParams {
 };
 
 __global__ void __launch_bounds__(256) kg_pair_select_kernel(const KgPairSelectParams prm) {
-	const uint64_t total = (uint64_t)prm.n_groups * prm.dense_limit;
+	// work items = the entries of the short lists, back to back: first[k] = items before group k (n_groups <= 16)
+	__shared__ uint64_t first[17];
+	if (threadIdx.x == 0) {
+		uint64_t run = 0;
+		for (uint32_t k = 0; k < prm.n_groups; k++) {
+			first[k] = run;
+			const uint64_t cnt = prm.group_count[k];
+			if (cnt <= prm.dense_limit) run += cnt;
+		}
+		for (uint32_t k = prm.n_groups; k <= 16; k++) first[k] = run;
+	}
+	__syncthreads();
+	const uint64_t total = first[16];
 	const uint32_t m_stride = prm.n_used / 2 + 1;
 	const float Nf = (float)prm.n_used;
 	for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
-		const uint32_t k = (uint32_t)(e / prm.dense_limit);
-		const uint64_t idx = e - (uint64_t)k * prm.dense_limit;
-		const uint64_t cnt = prm.group_count[k];
-		if (cnt > prm.dense_limit || idx >= cnt) continue;
+		uint32_t k = 0;
+		while (k + 1 < prm.n_groups && e >= first[k + 1]) k++;
+		const uint64_t idx = e - first[k];
 		const uint32_t pos = prm.group_list[(size_t)k * prm.group_cap + idx];
 		const uint32_t n1 = prm.ent_n1[(size_t)k * prm.qcap + idx];
 		const int4 *qp = reinterpret_cast<const int4 *>(prm.ent_q + ((size_t)k * prm.qcap + idx) * 16);

@@ -273,6 +273,7 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	e = cudaMalloc((void **)&tc.d_tile_pheno, tc.p_pad * sizeof(int32_t));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc tile table: %s", cudaGetErrorString(e));
 	e = cudaMalloc((void **)&tc.d_group_count, (16 + 16) * sizeof(unsigned long long));   // + 32 u32 tile chunk counters
+	if (e == cudaSuccess) e = cudaMemset(tc.d_group_count, 0, (16 + 16) * sizeof(unsigned long long));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc group counters: %s", cudaGetErrorString(e));
 	e = cudaMalloc((void **)&tc.d_gconst, 16 * sizeof(KgFilterGroupConst) + 2 * (size_t)P * sizeof(float));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc filter constants: %s", cudaGetErrorString(e));
@@ -377,11 +378,19 @@ static kg_status kg_tc_ensure_row_list(kg_ctx *c, uint64_t n_rows) {
 	return KG_OK;
 }
 
-__global__ void kg_add_counter_kernel(const unsigned long long *src, unsigned long long *dst) { *dst += *src; }
-__global__ void kg_sum_counters_kernel(const unsigned long long *src, uint32_t n, unsigned long long *dst) {
-	unsigned long long t = 0;
-	for (uint32_t i = 0; i < n; i++) t += src[i];
-	*dst += t;
+// End of a filtered tile: interval totals += the tile's counts ([5] listed rows, [6] (row, group) entries, [7] (row,
+// phenotype) pairs), then the per-tile counters are zeroed for the next tile (no memsets in front of the filter launch).
+__global__ void kg_tile_end_kernel(unsigned long long *interval_cnt, unsigned long long *tile_cnt, uint32_t n_groups) {
+	if (threadIdx.x == 0) {
+		unsigned long long t = 0;
+		for (uint32_t i = 0; i < n_groups; i++) t += tile_cnt[i];
+		interval_cnt[5] += interval_cnt[2];
+		interval_cnt[6] += t;
+		interval_cnt[7] += tile_cnt[24];
+		interval_cnt[2] = 0;
+	}
+	__syncthreads();
+	if (threadIdx.x < 32) tile_cnt[threadIdx.x] = 0;
 }
 
 // filter the tile on the tensor cores, then re-score the rows it could not rule out with the exact kernel
@@ -396,8 +405,8 @@ static kg_status kg_tc_scan_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_r
 		st = ensure_squeeze_scratch(c, n_rows);
 		if (st != KG_OK) return st;
 	}
-	KG_CUDA(c, cudaMemsetAsync(c->d_counters + 2, 0, sizeof(unsigned long long), c->stream));
-	KG_CUDA(c, cudaMemsetAsync(tc.d_group_count, 0, (16 + 16) * sizeof(unsigned long long), c->stream));
+	// per-tile counters (d_counters[2], tc.d_group_count[0..31]) are zero here: zeroed at allocation / interval open and
+	// by kg_tile_end_kernel after every tile
 	KgFilterParams f = kg_tc_filter_params(c, dev, n_rows);
 	const uint32_t n_blocks = (uint32_t)((n_rows + KG_F_ROWS - 1) / KG_F_ROWS);
 	const unsigned grid = std::max(1u, std::min<uint32_t>(n_blocks, (uint32_t)c->sm_count));
@@ -472,9 +481,7 @@ static kg_status kg_tc_scan_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_r
 		for (uint32_t g = 0; g < tc.p_pad / 16; g++) fprintf(stderr, " %llu", h[g]);
 		fprintf(stderr, "  pairs %llu\n", h[24]);
 	}
-	kg_add_counter_kernel<<<1, 1, 0, c->stream>>>(c->d_counters + 2, c->d_counters + 5);
-	KG_LAUNCH_CHECK(c);
-	kg_sum_counters_kernel<<<1, 1, 0, c->stream>>>(tc.d_group_count, tc.p_pad / 16, c->d_counters + 6);
+	kg_tile_end_kernel<<<1, 32, 0, c->stream>>>(c->d_counters, tc.d_group_count, tc.p_pad / 16);
 	KG_LAUNCH_CHECK(c);
 	return KG_OK;
 }
