@@ -52,7 +52,7 @@ unsigned kgh_host_threads() {
 
 // ------------------------------------------------------------------------------------------ pool
 KghTaskPool::KghTaskPool(unsigned n_threads) {
-	for (unsigned i = 1; i < n_threads; i++) m_workers.emplace_back([this] { worker(); });
+	for (unsigned i = 1; i < n_threads; i++) m_workers.emplace_back([this, i] { worker(i); });
 }
 
 KghTaskPool::~KghTaskPool() {
@@ -64,7 +64,12 @@ KghTaskPool::~KghTaskPool() {
 	for (std::thread &t : m_workers) t.join();
 }
 
-void KghTaskPool::drain() {
+void KghTaskPool::drain(unsigned index) {
+	if (m_static) {
+		const std::size_t T = m_workers.size() + 1;
+		for (std::size_t i = index; i < m_n; i += T) (*m_fn)(i);
+		return;
+	}
 	for (;;) {
 		const std::size_t i = m_next.fetch_add(1, std::memory_order_relaxed);
 		if (i >= m_n) return;
@@ -72,7 +77,7 @@ void KghTaskPool::drain() {
 	}
 }
 
-void KghTaskPool::worker() {
+void KghTaskPool::worker(unsigned index) {
 	uint64_t seen = 0;
 	for (;;) {
 		{
@@ -81,12 +86,18 @@ void KghTaskPool::worker() {
 			if (m_stop) return;
 			seen = m_generation;
 		}
-		drain();
+		drain(index);
 		{
 			std::lock_guard<std::mutex> lk(m_mu);
 			if (--m_active == 0) m_cv_done.notify_one();
 		}
 	}
+}
+
+void KghTaskPool::run_static(std::size_t n_tasks, const std::function<void(std::size_t)> &fn) {
+	m_static = true;    // read by the workers only after the generation bump under the mutex in run()
+	run(n_tasks, fn);
+	m_static = false;
 }
 
 void KghTaskPool::run(std::size_t n_tasks, const std::function<void(std::size_t)> &fn) {
@@ -104,7 +115,7 @@ void KghTaskPool::run(std::size_t n_tasks, const std::function<void(std::size_t)
 		m_generation++;
 	}
 	m_cv_work.notify_all();
-	drain();
+	drain(0);
 	std::unique_lock<std::mutex> lk(m_mu);
 	m_cv_done.wait(lk, [&] { return m_active == 0; });
 	m_fn = nullptr;
@@ -209,9 +220,9 @@ static bool replay_in_flight(kg_ctx *ctx, BestAssociationsHeap *const *heaps, st
 	const std::vector<std::size_t> &off = S.bucket_off;
 	// one task per phenotype; in sharded runs task 0 appends the round's hits to the shard log meanwhile
 	const std::size_t log_task = (S.log_hits && n_hits) ? 1 : 0;
-	S.pool->run(P + log_task, [&](std::size_t task) {
-		if (task < log_task) { S.log_append(raw, n_hits); return; }
-		const std::size_t j = task - log_task;
+	S.pool->run_static(P + log_task, [&](std::size_t task) {
+		if (task >= P) { S.log_append(raw, n_hits); return; }
+		const std::size_t j = task;
 		kg_hit *b = base + off[j], *e = base + off[j + 1];
 		std::sort(b, e, [](const kg_hit &x, const kg_hit &y) { return x.row < y.row; });
 		heaps[j]->add_hits(b, (std::size_t)(e - b));

@@ -30,10 +30,13 @@ class KghTaskPool {
 		KghTaskPool(const KghTaskPool &) = delete;
 		KghTaskPool &operator=(const KghTaskPool &) = delete;
 		void run(std::size_t n_tasks, const std::function<void(std::size_t)> &fn);
+		// Same, but task i always runs on thread i mod threads(): per-phenotype heaps (240 KB each at K = 10001) then
+		// stay in the L2 of the core that replayed them last round instead of migrating with a dynamic schedule.
+		void run_static(std::size_t n_tasks, const std::function<void(std::size_t)> &fn);
 		unsigned threads() const { return (unsigned)m_workers.size() + 1; }
 	private:
-		void worker();
-		void drain();
+		void worker(unsigned index);
+		void drain(unsigned index);
 		std::vector<std::thread> m_workers;
 		std::mutex m_mu;
 		std::condition_variable m_cv_work, m_cv_done;
@@ -43,6 +46,7 @@ class KghTaskPool {
 		std::size_t m_active = 0;
 		uint64_t m_generation = 0;
 		bool m_stop = false;
+		bool m_static = false;
 };
 
 struct AssociationDriverState {
