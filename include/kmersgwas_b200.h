@@ -140,6 +140,12 @@ kg_status kg_scan_clear_hits(kg_ctx *ctx);
  * its rows: the state is as it was after the last consumed interval (recovery after KG_ERR_HITS_OVERFLOW). */
 kg_status kg_scan_discard(kg_ctx *ctx);
 
+/* The MAC filter of load_kmers alone (/root/reference/src/kmers_multiple_databases.cpp:117-121 with
+ * calculate_unsqueezed_popcnt :149-154): keep[r] = 1 iff min_count <= popcount(row r & used columns) <= N_used - min_count.
+ * No phenotypes needed.  rows: host or device; keep: HOST buffer of n_rows bytes; *kept (may be NULL) = number of ones.
+ * Used by the kmers_table_to_bed CLI (table -> PLINK conversion of every kept row). */
+kg_status kg_mac_filter(kg_ctx *ctx, const uint64_t *rows, uint64_t n_rows, uint64_t min_count, uint8_t *keep, uint64_t *kept);
+
 /* Testing / --k_mers_scores aid: exact scores of EVERY row of one tile.
  * keep[r] = row passes the MAC filter; scores[p * n_rows + r] valid where keep[r].  Host outputs. */
 kg_status kg_scan_scores_dense(kg_ctx *ctx, const uint64_t *rows, uint64_t n_rows,

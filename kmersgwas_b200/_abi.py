@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "kg_scan_set_phenotypes", "kg_scan_set_thresholds", "kg_scan_submit", "kg_scan_mark", "kg_scan_fetch",
     "kg_scan_clear_hits", "kg_scan_discard", "kg_scan_scores_dense", "kg_kinship_begin", "kg_kinship_accum_len",
     "kg_kinship_submit", "kg_kinship_fetch", "kg_host_alloc", "kg_host_free", "kg_synth_rows_device",
-    "kg_launch_count", "kg_kernel_time", "kg_kernel_time_reset", "kg_scan_filter_sums",
+    "kg_launch_count", "kg_kernel_time", "kg_kernel_time_reset", "kg_scan_filter_sums", "kg_mac_filter",
 ]
 
 
@@ -75,6 +75,7 @@ def load():
     lib.kg_scan_clear_hits.argtypes = [vp]
     lib.kg_scan_discard.argtypes = [vp]
     lib.kg_scan_scores_dense.argtypes = [vp, vp, u64, C.POINTER(C.c_uint8), C.POINTER(C.c_double)]
+    lib.kg_mac_filter.argtypes = [vp, vp, u64, u64, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]
     lib.kg_kinship_begin.argtypes = [vp, u64, vp]
     lib.kg_kinship_accum_len.argtypes = [vp]
     lib.kg_kinship_accum_len.restype = C.c_size_t
@@ -210,6 +211,14 @@ class Context:
                                                  keep.ctypes.data_as(C.POINTER(C.c_uint8)),
                                                  scores.ctypes.data_as(C.POINTER(C.c_double))))
         return keep.astype(bool), scores
+
+    def mac_filter(self, rows, n_rows: int, min_count: int):
+        """-> (keep[n_rows] bool, kept): load_kmers' MAC filter alone (no phenotypes needed)"""
+        keep = np.zeros(n_rows, dtype=np.uint8)
+        kept = C.c_uint64(0)
+        self._chk(self._lib.kg_mac_filter(self._h, _rows_ptr(rows), int(n_rows), int(min_count),
+                                          keep.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(kept)))
+        return keep.astype(bool), int(kept.value)
 
     def filter_sums(self, rows, n_rows: int):
         """-> (q[n_rows, P] int32 exact sums of the tensor-core filter, yq[P, 64*W_file] int8 quantised phenotypes)"""

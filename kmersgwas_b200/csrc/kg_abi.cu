@@ -820,6 +820,61 @@ extern "C" kg_status kg_scan_clear_hits(kg_ctx *c) {
 	return KG_OK;
 }
 
+// keep bits -> one byte per row
+__global__ void kg_keep_bytes_kernel(const uint32_t *__restrict__ keep_bits, uint64_t n_rows, uint8_t *__restrict__ keep) {
+	for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (uint64_t)gridDim.x * blockDim.x)
+		keep[r] = (uint8_t)((keep_bits[r >> 5] >> (r & 31)) & 1u);
+}
+
+extern "C" kg_status kg_mac_filter(kg_ctx *c, const uint64_t *rows, uint64_t n_rows, uint64_t min_count, uint8_t *keep, uint64_t *kept) {
+	if (!c) return KG_ERR_INVALID;
+	if (kept) *kept = 0;
+	if (n_rows == 0) return KG_OK;
+	if (!rows || !keep) KG_FAIL(c, KG_ERR_INVALID, "kg_mac_filter: null argument");
+	if (n_rows >= (1ull << 31)) KG_FAIL(c, KG_ERR_INVALID, "kg_mac_filter: tile too large (max 2^31-1 rows)");
+	KG_CUDA(c, cudaSetDevice(c->device));
+	const uint64_t *dev = nullptr;
+	kg_status st = acquire_tile(c, rows, n_rows, &dev);
+	if (st != KG_OK) return st;
+	const size_t kb_need = (size_t)((n_rows + 31) / 32);
+	if (c->keep_bits_cap < kb_need) {
+		KG_CUDA(c, cudaStreamSynchronize(c->stream));
+		cudaFree(c->d_keep_bits);
+		c->d_keep_bits = nullptr;
+		c->keep_bits_cap = 0;
+		cudaError_t me = cudaMalloc((void **)&c->d_keep_bits, kb_need * 4);
+		if (me != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc keep bits: %s", cudaGetErrorString(me));
+		c->keep_bits_cap = kb_need;
+	}
+	uint8_t *d_keep = nullptr;
+	unsigned long long *d_kept = nullptr;
+	cudaError_t me = cudaMalloc((void **)&d_keep, n_rows + 8);
+	if (me != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc keep bytes: %s", cudaGetErrorString(me));
+	me = cudaMalloc((void **)&d_kept, sizeof(unsigned long long));
+	if (me != cudaSuccess) { cudaFree(d_keep); KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc kept counter: %s", cudaGetErrorString(me)); }
+	cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long), c->stream);
+	const KgRowView raw{dev, n_rows, c->w_file + 1, c->w_file};
+	const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_rows + 255) / 256, (uint64_t)c->sm_count * 8));
+	timing_begin(c, KG_KERNEL_AUX, n_rows);
+	kg_prefilter_kernel<<<grid, 256, 0, c->stream>>>(raw, c->d_file_mask, (uint32_t)c->n_used,
+	                                                 (uint32_t)std::min<uint64_t>(min_count, 0xFFFFFFFFull), c->d_keep_bits, d_kept);
+	kg_keep_bytes_kernel<<<grid, 256, 0, c->stream>>>(c->d_keep_bits, n_rows, d_keep);
+	timing_end(c);
+	c->launches += 2;
+	cudaError_t e0 = cudaGetLastError();
+	st = release_tile(c);
+	cudaError_t e1 = cudaStreamSynchronize(c->stream);
+	cudaError_t e2 = cudaMemcpy(keep, d_keep, n_rows, cudaMemcpyDeviceToHost);
+	unsigned long long h_kept = 0;
+	cudaError_t e3 = cudaMemcpy(&h_kept, d_kept, sizeof h_kept, cudaMemcpyDeviceToHost);
+	cudaFree(d_keep);
+	cudaFree(d_kept);
+	if (st != KG_OK) return st;
+	KG_CUDA(c, e0); KG_CUDA(c, e1); KG_CUDA(c, e2); KG_CUDA(c, e3);
+	if (kept) *kept = h_kept;
+	return KG_OK;
+}
+
 extern "C" kg_status kg_scan_scores_dense(kg_ctx *c, const uint64_t *rows, uint64_t n_rows, uint8_t *keep,
                                           double *scores) {
 	if (!c) return KG_ERR_INVALID;

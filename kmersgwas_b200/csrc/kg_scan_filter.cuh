@@ -101,7 +101,7 @@ struct KgFilterParams {
 	unsigned long long *kept_count;
 	int32_t *q_out;            // debug mode: [n_rows][p_pad] accumulators
 	uint32_t n_issuers;        // MMA issuer warps in use, 1 .. KG_F_MMA_WARPS
-	uint32_t dbg;              // perf experiments only (env KG_FILTER_DEBUG): 1 skip expansion, 2 skip epilogue work, 4 skip MMAs, 8 skip loads, 16 plain a_empty arrive, 32 SS-mode MMAs on garbage A
+	uint32_t dbg;              // perf experiments only (env KG_FILTER_DEBUG): 1 skip expansion, 2 skip epilogue work, 4 skip MMAs, 8 skip loads, 64 no tcgen05.st, 128 no expansion arithmetic
 };
 
 __host__ __device__ inline uint32_t kg_filter_raw_stage_bytes(uint32_t w_file) { return KG_F_ROWS * 8u * (w_file + 1); }
@@ -301,8 +301,13 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 					for (uint32_t i = 0; i < KG_F_MAX_WPT; i++) {
 						if (lo + i < hi) {
 							const uint64_t w = wp[lo + i];
-							kg_expand_u32((uint32_t)w, v[i]);
-							kg_expand_u32((uint32_t)(w >> 32), v[i] + 8);
+							if (prm.dbg & 128) {   // perf experiment: no expansion arithmetic, stores only
+#pragma unroll
+								for (int j = 0; j < 16; j++) v[i][j] = (uint32_t)w;
+							} else {
+								kg_expand_u32((uint32_t)w, v[i]);
+								kg_expand_u32((uint32_t)(w >> 32), v[i] + 8);
+							}
 						}
 					}
 				}
@@ -312,7 +317,14 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 				if (!(prm.dbg & 1)) {
 #pragma unroll
 					for (uint32_t i = 0; i < KG_F_MAX_WPT; i++)
-						if (lo + i < hi) kg_tmem_st16(taddr + 16 * (lo + i), v[i]);
+						if (lo + i < hi) {
+							if (prm.dbg & 64) {   // perf experiment: expansion arithmetic only, no tensor-memory stores
+#pragma unroll
+								for (int j = 0; j < 16; j++) asm volatile("" ::"r"(v[i][j]));
+							} else {
+								kg_tmem_st16(taddr + 16 * (lo + i), v[i]);
+							}
+						}
 					kg_tmem_st_wait();
 				}
 				kg_tc_fence_before();

@@ -262,6 +262,32 @@ void MultipleKmersDataBases::output_plink_bed_file_selected(BedBimFilesHandle &f
 	}
 }
 
+// ---- whole-table PLINK conversion (kmers_table_to_bed) ---------------------------------------------
+void MultipleKmersDataBases::mac_filter_loaded(const size_t &min_count, vector<uint8_t> &keep) const {
+	keep.assign(m_rows_loaded, 0);
+	const size_t stride = 1 + m_hash_words_db_file;
+	for (uint64_t off = 0; off < m_rows_loaded; off += kSubTileRows) {
+		const uint64_t n = std::min<uint64_t>(kSubTileRows, m_rows_loaded - off);
+		check(kg_mac_filter(m_ctx, m_batch + off * stride, n, min_count, keep.data() + off, nullptr), "kg_mac_filter");
+	}
+}
+
+void MultipleKmersDataBases::output_plink_loaded_row(BedBimFilesHandle &f, size_t r) const {
+	const uint64_t *row = m_batch + r * (1 + m_hash_words_db_file);
+	vector<uint64_t> mem_row;
+	squeeze_row(row, mem_row);
+	write_PA(bits2kmer31(row[0], m_kmer_len), mem_row, f);
+}
+
+uint64_t MultipleKmersDataBases::presence_absence_pattern_hash_loaded_row(size_t r) const {
+	static const Hash64 hasher;
+	vector<uint64_t> mem_row;
+	squeeze_row(m_batch + r * (1 + m_hash_words_db_file), mem_row);
+	uint64_t seed = 0;
+	for (size_t w = 0; w < m_hash_words; w++) seed ^= hasher(mem_row[w]) + 0x9e3779b97f4a7c15ull + (seed << 6) + (seed >> 2);
+	return seed;
+}
+
 // ---- presence/absence pattern counter (:367-380), host implementation ("next" row of SURVEY 8(f)) -----
 void MultipleKmersDataBases::update_presence_absence_pattern_counter(KmersSet &pa_pattern_counter) const {
 	static const Hash64 hasher;

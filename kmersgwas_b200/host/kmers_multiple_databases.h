@@ -55,6 +55,13 @@ class MultipleKmersDataBases {
 		void output_plink_bed_file_selected(BedBimFilesHandle &f, const std::vector<AssociationOutputInfo> &kmer_list);
 
 		void update_presence_absence_pattern_counter(KmersSet &pa_pattern_counter) const;
+
+		// kmers_table_to_bed (reference :204-216, :262-272): PLINK output of EVERY row load_kmers keeps.  The reference's
+		// load_kmers stops after batch_size KEPT rows; here a batch is a range of raw file rows, so the caller walks the
+		// loaded rows with the keep flags of the device MAC filter and cuts its output files itself.
+		void mac_filter_loaded(const std::size_t &min_count, std::vector<uint8_t> &keep) const;
+		void output_plink_loaded_row(BedBimFilesHandle &f, std::size_t row_in_batch) const;      // name = the k-mer (:208)
+		uint64_t presence_absence_pattern_hash_loaded_row(std::size_t row_in_batch) const;       // (:367-374)
 		inline const std::vector<std::string> get_dbs_names() { return m_db_names_table; }
 		void clear() { m_rows_loaded = 0; }
 

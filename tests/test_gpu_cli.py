@@ -131,3 +131,35 @@ def test_associate_kmers_two_shards_equal_one(bins, tmp_path):
     os.environ.pop("KMERSGWAS_SHARDS_ON_ONE_DEVICE", None)
     _same_dir(dirs[0], dirs[1])
     _same_dir(dirs[0], dirs[2])
+
+
+@pytest.mark.parametrize("name,batch,unique,rows_per_load", [
+    ("plumbing_n64", 1000000, False, 4194304),     # one batch
+    ("subset_n300", 700, False, 333),              # several batch files, phenotype-order subset of the columns,
+                                                   # device passes that do not line up with the batch boundaries
+    ("ties_n96", 50, True, 64),                    # -u: duplicate presence/absence patterns dropped across batches
+    ("identity_n131", 1, False, 1000),             # one kept row per file
+])
+def test_kmers_table_to_bed_outputs_byte_identical(bins, tmp_path, name, batch, unique, rows_per_load):
+    """table -> PLINK conversion of every row that passes the MAC filter (device MAC filter)."""
+    if not (bins / "kmers_table_to_bed").exists() or not (S.REF_DIR / "kmers_table_to_bed").exists():
+        pytest.skip("kmers_table_to_bed not built")
+    g = S.Golden(name)
+    if batch == 1:
+        g.table = g.table[:300]                    # one file triple per kept row: keep the directory small
+    table, pheno = g.write_inputs(tmp_path)
+    dirs = []
+    for tag, exe in (("ref", S.REF_DIR / "kmers_table_to_bed"), ("ours", bins / "kmers_table_to_bed")):
+        out = tmp_path / tag
+        out.mkdir()
+        args = ["-t", table, "-k", 31, "-p", pheno, "--maf", g.maf, "--mac", g.mac, "-b", batch, "-o", out / "conv"]
+        if unique:
+            args.append("-u")
+        if tag == "ours":
+            args += ["--rows_per_load", rows_per_load]
+        r = _run(exe, args)
+        assert r.returncode == 0, r.stderr[-2000:]
+        dirs.append(out)
+    files = _same_dir(*dirs)
+    assert "conv.0.bed" in files and "conv.0.fam" in files
+

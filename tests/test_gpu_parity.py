@@ -375,3 +375,19 @@ def test_ecoli_shape_through_the_pipeline(kg):
         k, s, r = sess.heap(j)
         assert np.array_equal(k, ko) and np.array_equal(_bits(s), _bits(so)) and np.array_equal(r, ro)
     sess.close()
+
+
+def test_mac_filter_matches_numpy(kg):
+    """kg_mac_filter = load_kmers' MAC filter alone (reference :117-121), subset of the columns in shuffled order."""
+    n_file, n_rows = 300, 5000
+    rng = np.random.default_rng(11)
+    used = rng.permutation(n_file)[:211]
+    table = S.synth_table(21, n_rows, n_file)
+    ctx = kg.Context(n_file, (used // 64).astype(np.uint32), (used % 64).astype(np.uint32))
+    for mc in (0, 1, 11, 105, 106):
+        keep, kept = ctx.mac_filter(table, n_rows, mc)
+        bits = np.unpackbits(table[:, 1:].copy().view(np.uint8), axis=1, bitorder="little")[:, used]
+        cnt = bits.sum(axis=1)
+        want = (cnt >= mc) & (cnt <= len(used) - mc)
+        assert np.array_equal(keep, want) and kept == int(want.sum())
+    ctx.close()
