@@ -101,7 +101,7 @@ struct KgFilterParams {
 	unsigned long long *kept_count;
 	int32_t *q_out;            // debug mode: [n_rows][p_pad] accumulators
 	uint32_t n_issuers;        // MMA issuer warps in use, 1 .. KG_F_MMA_WARPS
-	uint32_t dbg;              // perf experiments only (env KG_FILTER_DEBUG): 1 skip expansion, 2 skip epilogue work, 4 skip MMAs, 8 skip loads, 64 no tcgen05.st, 128 no expansion arithmetic
+	uint32_t dbg;              // perf experiments only (env KG_FILTER_DEBUG): 1 skip expansion, 2 skip epilogue work, 4 skip MMAs, 8 skip loads, 64 no tcgen05.st, 128 no expansion arithmetic, 256 epilogue reads 32 columns only
 };
 
 __host__ __device__ inline uint32_t kg_filter_raw_stage_bytes(uint32_t w_file) { return KG_F_ROWS * 8u * (w_file + 1); }
@@ -365,7 +365,8 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 				uint32_t n1 = 0;
 				float g = 0.f, hm = 0.f;
 				uint32_t gmask = 0;   // bit k: group k could not be ruled out for this row
-				for (uint32_t c0 = 0; c0 < ((prm.dbg & 2) ? 0u : prm.p_pad); c0 += 32) {
+				// (dbg 256: perf experiment, only the first 32 accumulator columns are read back)
+				for (uint32_t c0 = 0; c0 < ((prm.dbg & 2) ? 0u : ((prm.dbg & 256) ? 32u : prm.p_pad)); c0 += 32) {
 					uint32_t v[16], u[16];
 					kg_tmem_ld16(taddr + c0, v);
 					const bool second = c0 + 16 < prm.p_pad;   // warp-uniform
