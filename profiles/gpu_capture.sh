@@ -32,7 +32,7 @@ timeout -k 5 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40
 
 echo "== ncu full: filter, pair kernel, kinship" ; date
 timeout -k 5 600 ncu --set full --clock-control none --import-source on -k regex:kg_scan_filter -s 24 -c 1 -f -o $out/${tag}_prof_filter \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --kinship-rows 0 --e2e-buffers 1 > $out/${tag}_prof_filter.log 2>&1; echo "rc=$?"
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --kinship-rows 0 --e2e-buffers 1 --cold-steps 0 > $out/${tag}_prof_filter.log 2>&1; echo "rc=$?"
 timeout -k 5 600 ncu --set full --clock-control none --import-source on -k regex:kg_scan_pair -s 24 -c 1 -f -o $out/${tag}_prof_pair \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --kinship-rows 0 --e2e-buffers 1 > $out/${tag}_prof_pair.log 2>&1; echo "rc=$?"
 timeout -k 5 600 ncu --set full --clock-control none --import-source on -k regex:kg_kinship_tc -s 2 -c 1 -f -o $out/${tag}_prof_kinship \
