@@ -135,11 +135,14 @@ def test_filter_engine_degenerate_phenotypes(kg):
     assert np.array_equal(sa[~nan], sb[~nan])
 
 
+@pytest.mark.parametrize("pair_limit", [-1, 0, 40])
 @pytest.mark.parametrize("name", ["subset_n300", "ties_n96", "thaliana_n1135"])
-def test_topk_golden_through_filter_engine(kg, name):
-    """Reference top-K (golden fixtures) through the product's host driver with the filter engine forced on."""
+def test_topk_golden_through_filter_engine(kg, name, pair_limit):
+    """Reference top-K (golden fixtures) through the product's host driver with the filter engine forced on; pair mode,
+    list mode and their mix (subset_n300: shuffled subset of the columns, i.e. squeezed copies of the listed rows)."""
     g = S.Golden(name)
     sess = kg.Session(g.n_file, g.map_word, g.map_bit, g.y, g.min_count, g.kbest, scan_engine=2)
+    sess.set_option(kg.OPT_FILTER_PAIR_LIMIT, pair_limit)
     for r0 in range(0, g.n_rows, 1500):
         n = min(1500, g.n_rows - r0)
         sess.associate(np.ascontiguousarray(g.table[r0:r0 + n]), n, r0)
