@@ -113,3 +113,35 @@ def test_cli_help_and_usage_errors_run_without_a_gpu(kg):
     exe = ROOT / "kmersgwas_b200" / "bin" / "emma_kinship_kmers"
     r = subprocess.run([str(exe), "--help"], capture_output=True, text=True)
     assert r.returncode == 0 and "--kmers_len" in r.stderr
+
+
+def test_kmers_table_to_bed_usage_errors_run_without_a_gpu(kg, tmp_path):
+    """Flag handling of the converter mirrors the reference (kmers_table_to_bed.cpp:52-90): --help exits 0, a missing
+    required flag / a missing file / a bad k-mer length exit 1 before any device is touched."""
+    exe = ROOT / "kmersgwas_b200" / "bin" / "kmers_table_to_bed"
+    assert exe.exists()
+    run = lambda *a: subprocess.run([str(exe)] + [str(x) for x in a], capture_output=True, text=True)
+    assert run("--help").returncode == 0
+    r = run("-t", tmp_path / "t", "-k", 31)
+    assert r.returncode == 1 and "is a required parameter" in r.stderr
+    r = run("-t", tmp_path / "missing", "-k", 31, "-p", tmp_path / "p.tsv", "--maf", 0.05, "--mac", 5, "-b", 10, "-o", tmp_path / "o")
+    assert r.returncode == 1 and "Couldn't find file" in r.stderr
+    assert run("--nonsense").returncode == 1
+
+
+def test_bench_reference_arm_json_contract(tmp_path):
+    """`bench.py --impl reference` (the unmodified reference binary on the host cores) prints ONE JSON line with the
+    keys the driver reads; runs here without a GPU on a tiny sample."""
+    if not S.have_ref():
+        pytest.skip("oracle/_ref not built")
+    import json
+    r = subprocess.run(["python", str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup-ref", "0",
+                        "--ref-rows", "3000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "k-mers scored/sec" and d["unit"] == "k-mers/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
