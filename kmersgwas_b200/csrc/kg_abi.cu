@@ -55,6 +55,7 @@ struct kg_ctx {
 		                                       // [6] (row, column group) pairs listed (whole interval)
 		unsigned long long *h_cnt = nullptr;   // pinned copy of d_cnt, valid once `done` has completed
 		cudaEvent_t done = nullptr;
+		cudaEvent_t closed_ev = nullptr;       // recorded on the compute stream when the interval is marked
 		uint64_t rows = 0;                     // rows submitted into this interval
 		bool closed = false;                   // marked, waiting for kg_scan_fetch
 		bool used_filter = false;
@@ -263,6 +264,7 @@ static kg_status ctx_init(kg_ctx *c, int device, const kg_shape *shape, void *st
 		KG_CUDA(c, cudaMemset(c->iv[i].d_cnt, 0, 8 * sizeof(unsigned long long)));
 		KG_CUDA(c, cudaMallocHost((void **)&c->iv[i].h_cnt, 8 * sizeof(unsigned long long)));
 		KG_CUDA(c, cudaEventCreateWithFlags(&c->iv[i].done, cudaEventDisableTiming));
+		KG_CUDA(c, cudaEventCreateWithFlags(&c->iv[i].closed_ev, cudaEventDisableTiming));
 	}
 	for (int i = 0; i < 4; i++) KG_CUDA(c, cudaEventCreateWithFlags(&c->thr_stage[i].ev, cudaEventDisableTiming));
 	c->cur = 0;
@@ -295,6 +297,7 @@ extern "C" void kg_ctx_destroy(kg_ctx *c) {
 		cudaFree(c->iv[i].d_hits); cudaFree(c->iv[i].d_cnt);
 		if (c->iv[i].h_cnt) cudaFreeHost(c->iv[i].h_cnt);
 		if (c->iv[i].done) cudaEventDestroy(c->iv[i].done);
+		if (c->iv[i].closed_ev) cudaEventDestroy(c->iv[i].closed_ev);
 	}
 	for (int i = 0; i < 4; i++) {
 		if (c->thr_stage[i].h_thr) cudaFreeHost(c->thr_stage[i].h_thr);
@@ -569,11 +572,45 @@ extern "C" kg_status kg_scan_set_phenotypes(kg_ctx *c, const float *y, uint32_t 
 	return st;
 }
 
+// Per-round constants travel as KERNEL ARGUMENTS (copied at launch, no staging buffer, no copy-engine round trip in front
+// of the filter launch): thresholds of the exact kernels + the filter's group slots and per-phenotype (alpha, kappa).
+// Used when they fit the 4 KB argument space (P <= 128); larger P goes through pinned staging + cudaMemcpyAsync.
+#define KG_RC_MAX_P 128
+struct KgRoundConsts {
+	double thr[KG_RC_MAX_P];
+	unsigned char gc[16 * 48 + 2 * KG_RC_MAX_P * sizeof(float)];   // 16 KgFilterGroupConst, then alpha[P], kappa[P]
+	uint32_t p_alloc, gc_bytes;
+};
+__global__ void kg_round_constants_kernel(const KgRoundConsts rc, double *__restrict__ d_thr, unsigned char *__restrict__ d_gconst) {
+	for (uint32_t i = threadIdx.x; i < rc.p_alloc; i += blockDim.x) d_thr[i] = rc.thr[i];
+	if (d_gconst)
+		for (uint32_t i = threadIdx.x; i < rc.gc_bytes / 4; i += blockDim.x)
+			reinterpret_cast<uint32_t *>(d_gconst)[i] = reinterpret_cast<const uint32_t *>(rc.gc)[i];
+}
+
 extern "C" kg_status kg_scan_set_thresholds(kg_ctx *c, const double *thr, uint32_t n_pheno) {
 	if (!c || !thr) return KG_ERR_INVALID;
 	if (n_pheno != c->n_pheno || !c->d_thr) KG_FAIL(c, KG_ERR_STATE, "kg_scan_set_thresholds: phenotypes not set / count mismatch");
 	KG_CUDA(c, cudaSetDevice(c->device));
 	for (uint32_t p = 0; p < n_pheno; p++) c->h_thr[p] = thr[p];
+	if (c->p_alloc <= KG_RC_MAX_P) {
+		static_assert(sizeof(KgRoundConsts) <= 4000, "kernel argument space");
+		KgRoundConsts rc;
+		for (uint32_t p = 0; p < c->p_alloc; p++) rc.thr[p] = c->h_thr[p];
+		rc.p_alloc = c->p_alloc;
+		rc.gc_bytes = 0;
+		unsigned char *d_gc = nullptr;
+		if (c->tc.scan_ready) {
+			memset(rc.gc, 0, sizeof rc.gc);
+			kg_status st = kg_tc_update_thresholds(c, reinterpret_cast<KgFilterGroupConst *>(rc.gc), false);
+			if (st != KG_OK) return st;
+			rc.gc_bytes = (uint32_t)(16 * sizeof(KgFilterGroupConst) + 2 * (size_t)c->n_pheno * sizeof(float));
+			d_gc = reinterpret_cast<unsigned char *>(c->tc.d_gconst);
+		}
+		kg_round_constants_kernel<<<1, 256, 0, c->stream>>>(rc, c->d_thr, d_gc);
+		KG_LAUNCH_CHECK(c);
+		return KG_OK;
+	}
 	// stream-ordered through a pinned staging slot: tiles already queued keep the thresholds they were submitted
 	// with, and the host never waits for the device here
 	kg_ctx::ThrStage &stg = c->thr_stage[c->thr_next];
@@ -732,8 +769,12 @@ extern "C" kg_status kg_scan_mark(kg_ctx *c) {
 		KG_FAIL(c, KG_ERR_STATE, "kg_scan_mark: the previous interval has not been fetched yet");
 	KG_CUDA(c, cudaSetDevice(c->device));
 	kg_ctx::ScanInterval &v = c->iv[c->cur];
-	KG_CUDA(c, cudaMemcpyAsync(v.h_cnt, v.d_cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-	KG_CUDA(c, cudaEventRecord(v.done, c->stream));
+	// the counters are read back on the D2H stream behind an event, so that the copy engine's round trip does not sit
+	// between this interval's last kernel and the next interval's first one on the compute stream
+	KG_CUDA(c, cudaEventRecord(v.closed_ev, c->stream));
+	KG_CUDA(c, cudaStreamWaitEvent(c->d2h_stream, v.closed_ev, 0));
+	KG_CUDA(c, cudaMemcpyAsync(v.h_cnt, v.d_cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->d2h_stream));
+	KG_CUDA(c, cudaEventRecord(v.done, c->d2h_stream));
 	v.closed = true;
 	c->cur ^= 1;
 	kg_ctx::ScanInterval &n = c->iv[c->cur];

@@ -51,7 +51,8 @@ static float kg_float_up(double x) {  // smallest float >= x
 
 // Column order + per-group (alpha, kappa) from the current thresholds, and the B image in that order
 // (see kg_scan_filter.cuh header).  Column 0 = all-ones (popcount); phenotypes follow sorted by alpha.
-static kg_status kg_tc_update_thresholds(kg_ctx *c, KgFilterGroupConst *gc_pinned) {
+// upload = false: the caller ships the group slots + per-phenotype constants itself (kg_round_constants_kernel)
+static kg_status kg_tc_update_thresholds(kg_ctx *c, KgFilterGroupConst *gc_pinned, bool upload = true) {
 	KgTcState &tc = c->tc;
 	if (!tc.scan_ready) return KG_OK;
 	const uint32_t P = c->n_pheno, N = (uint32_t)c->n_used;
@@ -163,7 +164,8 @@ static kg_status kg_tc_update_thresholds(kg_ctx *c, KgFilterGroupConst *gc_pinne
 	// per-phenotype constants of the per-column test follow the 16 group slots (same staging slot, one copy)
 	float *pc = reinterpret_cast<float *>(gc + 16);
 	for (uint32_t p = 0; p < P; p++) { pc[p] = alpha[p]; pc[P + p] = kappa[p]; }
-	KG_CUDA(c, cudaMemcpyAsync(tc.d_gconst, gc, 16 * sizeof(KgFilterGroupConst) + 2 * (size_t)P * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+	if (upload)
+		KG_CUDA(c, cudaMemcpyAsync(tc.d_gconst, gc, 16 * sizeof(KgFilterGroupConst) + 2 * (size_t)P * sizeof(float), cudaMemcpyHostToDevice, c->stream));
 	return KG_OK;
 }
 
