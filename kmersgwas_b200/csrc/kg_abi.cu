@@ -90,6 +90,8 @@ struct kg_ctx {
 	uint64_t kin_min_count = 0;
 	uint32_t *d_keep_bits = nullptr;
 	size_t keep_bits_cap = 0;
+	uint8_t *d_keep_bytes = nullptr;   // kg_mac_filter scratch: [cap] keep flags, then one u64 counter (8-byte aligned)
+	size_t keep_bytes_cap = 0;
 	unsigned long long *d_ibs = nullptr;
 
 	// tensor-core engine state (kg_tc.cuh)
@@ -292,6 +294,7 @@ extern "C" void kg_ctx_destroy(kg_ctx *c) {
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
 	cudaFree(c->d_map_mem); cudaFree(c->d_map_lane); cudaFree(c->d_file_mask); cudaFree(c->d_mem_mask);
+	cudaFree(c->d_keep_bytes);
 	cudaFree(c->d_mask32); cudaFree(c->d_y_lane); cudaFree(c->d_y_pair); cudaFree(c->d_sums); cudaFree(c->d_thr);
 	for (int i = 0; i < 2; i++) {
 		cudaFree(c->iv[i].d_hits); cudaFree(c->iv[i].d_cnt);
@@ -887,13 +890,19 @@ extern "C" kg_status kg_mac_filter(kg_ctx *c, const uint64_t *rows, uint64_t n_r
 		if (me != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc keep bits: %s", cudaGetErrorString(me));
 		c->keep_bits_cap = kb_need;
 	}
-	uint8_t *d_keep = nullptr;
-	unsigned long long *d_kept = nullptr;
-	cudaError_t me = cudaMalloc((void **)&d_keep, n_rows + 8);
-	if (me != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc keep bytes: %s", cudaGetErrorString(me));
-	me = cudaMalloc((void **)&d_kept, sizeof(unsigned long long));
-	if (me != cudaSuccess) { cudaFree(d_keep); KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc kept counter: %s", cudaGetErrorString(me)); }
-	cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long), c->stream);
+	if (c->keep_bytes_cap < n_rows) {
+		KG_CUDA(c, cudaStreamSynchronize(c->stream));
+		cudaFree(c->d_keep_bytes);
+		c->d_keep_bytes = nullptr;
+		c->keep_bytes_cap = 0;
+		const size_t cap = (size_t)((n_rows + 7) & ~7ull);
+		cudaError_t me = cudaMalloc((void **)&c->d_keep_bytes, cap + sizeof(unsigned long long));
+		if (me != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc keep bytes: %s", cudaGetErrorString(me));
+		c->keep_bytes_cap = cap;
+	}
+	uint8_t *d_keep = c->d_keep_bytes;
+	unsigned long long *d_kept = reinterpret_cast<unsigned long long *>(c->d_keep_bytes + c->keep_bytes_cap);
+	KG_CUDA(c, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long), c->stream));
 	const KgRowView raw{dev, n_rows, c->w_file + 1, c->w_file};
 	const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_rows + 255) / 256, (uint64_t)c->sm_count * 8));
 	timing_begin(c, KG_KERNEL_AUX, n_rows);
@@ -908,8 +917,6 @@ extern "C" kg_status kg_mac_filter(kg_ctx *c, const uint64_t *rows, uint64_t n_r
 	cudaError_t e2 = cudaMemcpy(keep, d_keep, n_rows, cudaMemcpyDeviceToHost);
 	unsigned long long h_kept = 0;
 	cudaError_t e3 = cudaMemcpy(&h_kept, d_kept, sizeof h_kept, cudaMemcpyDeviceToHost);
-	cudaFree(d_keep);
-	cudaFree(d_kept);
 	if (st != KG_OK) return st;
 	KG_CUDA(c, e0); KG_CUDA(c, e1); KG_CUDA(c, e2); KG_CUDA(c, e3);
 	if (kept) *kept = h_kept;

@@ -286,6 +286,9 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc slack table: %s", cudaGetErrorString(e));
 	KG_CUDA(c, cudaMemcpyAsync(tc.d_slack, tc.slack_table.data(), tc.slack_table.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
 	tc.use_pairs = !(getenv("KG_FILTER_NO_PAIRS") && atoi(getenv("KG_FILTER_NO_PAIRS")));   // perf experiments: list mode only
+	tc.dbg_flags = getenv("KG_FILTER_DEBUG") ? (uint32_t)atoi(getenv("KG_FILTER_DEBUG")) : 0u;
+	tc.n_issuers = getenv("KG_FILTER_ISSUERS") ? (uint32_t)std::max(1, std::min(KG_F_MMA_WARPS, atoi(getenv("KG_FILTER_ISSUERS")))) : 0u;
+	tc.print_stats = getenv("KG_FILTER_STATS") != nullptr;
 	KG_CUDA(c, cudaFuncSetAttribute(kg_scan_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	KG_CUDA(c, cudaFuncSetAttribute(kg_scan_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	tc.scan_ready = true;
@@ -343,9 +346,8 @@ static KgFilterParams kg_tc_filter_params(kg_ctx *c, const uint64_t *dev, uint64
 	f.ent_n1 = tc.d_ent_n1;
 	f.qcap = tc.use_pairs ? tc.qcap : 0;
 	f.kept_count = c->d_counters + 1;
-	f.n_issuers = KG_F_MMA_WARPS;
-	if (const char *e = getenv("KG_FILTER_ISSUERS")) f.n_issuers = (uint32_t)std::max(1, std::min(KG_F_MMA_WARPS, atoi(e)));   // perf experiments
-	if (const char *e = getenv("KG_FILTER_DEBUG")) f.dbg = (uint32_t)atoi(e);   // perf experiments only (results are wrong)
+	f.n_issuers = tc.n_issuers ? tc.n_issuers : KG_F_MMA_WARPS;
+	f.dbg = tc.dbg_flags;
 	return f;
 }
 
@@ -475,7 +477,7 @@ static kg_status kg_tc_scan_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_r
 	st = launch_exact_list(c, prm, tc.p_pad / 8);
 	timing_end(c);
 	if (st != KG_OK) return st;
-	if (getenv("KG_FILTER_STATS")) {   // diagnosis only: synchronises the stream
+	if (tc.print_stats) {   // diagnosis only: synchronises the stream
 		unsigned long long h[32];
 		cudaStreamSynchronize(c->stream);
 		cudaMemcpy(h, tc.d_group_count, sizeof h, cudaMemcpyDeviceToHost);

@@ -23,6 +23,10 @@ struct KgTcState {
 	float *d_slack = nullptr;              // [P][n_used / 2 + 1] = slack_table
 	bool use_pairs = true;
 	int64_t pair_limit = -1;               // KG_OPT_FILTER_PAIR_LIMIT
+	// perf-experiment switches, read from the environment once per kg_scan_set_phenotypes (kg_tc_prepare_scan)
+	uint32_t dbg_flags = 0;                // KG_FILTER_DEBUG (results are wrong when set)
+	uint32_t n_issuers = 0;                // KG_FILTER_ISSUERS (0 = default)
+	bool print_stats = false;              // KG_FILTER_STATS: per-tile list sizes on stderr (synchronises the stream)
 	// scan filter: quantised centred phenotypes in UMMA (K-major core matrix) layout + per-phenotype constants
 	int8_t *d_yq = nullptr;
 	struct KgFilterGroupConst *d_gconst = nullptr;   // [p_pad / 16] per column group, see kg_scan_filter.cuh
