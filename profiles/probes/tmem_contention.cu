@@ -6,7 +6,7 @@
 #include <cstdio>
 #include "kg_tc_ptx.cuh"
 
-__global__ void __launch_bounds__(32 * 9, 1) probe(int ss_mode, int ld_sets, int n_mma, long long *out) {
+__global__ void __launch_bounds__(32 * 9, 1) probe(int ss_mode, int ld_sets, int n_mma, long long *out, int writers) {
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 	__shared__ uint64_t bar;
@@ -55,6 +55,13 @@ __global__ void __launch_bounds__(32 * 9, 1) probe(int ss_mode, int ld_sets, int
 		unsigned long long n = 0;
 		uint32_t sink = 0;
 		while (stop_flag != 1) {
+			if (writers) {   // tcgen05.st instead: the expanders' side (7 x 16 columns per sweep, then wait::st)
+				uint32_t v[16];
+#pragma unroll
+				for (int j = 0; j < 16; j++) v[j] = lane + j;
+				for (uint32_t c0 = 0; c0 < 112; c0 += 16) kg_tmem_st16(taddr + c0, v);
+				kg_tmem_st_wait();
+			} else
 			for (uint32_t c0 = 0; c0 < 112; c0 += 32) {
 				uint32_t v[16], u[16];
 				kg_tmem_ld16(taddr + c0, v);
@@ -79,16 +86,17 @@ int main() {
 	const int smem = 162 * 1024;
 	cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	const int n_mma = 4096;
+	for (int writers = 0; writers < 2; writers++)
 	for (int ss = 0; ss < 2; ss++)
-		for (int sets = 0; sets <= 2; sets++) {
+		for (int sets = (writers ? 1 : 0); sets <= 2; sets++) {
 			cudaMemset(d, 0, 32);
-			probe<<<148, 32 * 9, smem>>>(ss, sets, n_mma, d);
+			probe<<<148, 32 * 9, smem>>>(ss, sets, n_mma, d, writers);
 			cudaError_t e = cudaDeviceSynchronize();
 			if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
 			cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost);
 			// one sweep of one warp = 32 lanes x 112 columns x 4 B = 14 336 B
 			const double bytes_per_clk = h[0] > 0 ? (double)h[1] * 14336.0 / (double)h[0] : 0.0;
-			printf("A from %s, %d reader warps: %6.1f clk/MMA, readers moved %6.1f B/clk (%.0f KB per 36 MMAs)\n", ss ? "smem" : "TMEM", 4 * sets,
+			printf("A from %s, %d %s warps: %6.1f clk/MMA, they moved %6.1f B/clk (%.0f KB per 36 MMAs)\n", ss ? "smem" : "TMEM", 4 * sets, writers ? "tcgen05.st" : "tcgen05.ld",
 			       (double)h[0] / n_mma, bytes_per_clk, bytes_per_clk * ((double)h[0] / n_mma) * 36 / 1024.0);
 		}
 	return 0;
