@@ -70,10 +70,16 @@ enum {
 	KG_OPT_KINSHIP_ENGINE = 3, /* 0 = auto, 1 = popcount kernel, 2 = int8 tensor-core Gram */
 	KG_OPT_KERNEL_TIMING = 4,  /* 1 = bracket every hot-path kernel launch with CUDA events on the context's stream
 	                              (read back with kg_kernel_time); 0 = off (default) */
-	KG_OPT_FILTER_PAIR_LIMIT = 5 /* tensor filter: column groups whose list of surviving rows has at most this many
+	KG_OPT_FILTER_PAIR_LIMIT = 5, /* tensor filter: column groups whose list of surviving rows has at most this many
 	                              entries are re-tested per phenotype column and re-scored as single (row, phenotype)
 	                              pairs; longer lists are re-scored 16 phenotypes at a time.  0 = never use pair
 	                              mode, -1 = default (1/16 of the tile capacity).  Results are identical either way. */
+	/* device-side selection (kg_select_*): set before kg_select_begin */
+	KG_OPT_SELECT_GROWTH_PERMILLE = 6, /* round length = growth x rows scanned so far, in 1/1000 (default 500); the expected
+	                              number of candidates per phenotype and round is growth x K */
+	KG_OPT_SELECT_MAX_ROUND = 7,  /* longest round in rows (default 1 << 23) */
+	KG_OPT_SELECT_CAND_CAP = 8,   /* candidates a phenotype's segment holds per round (default max(4 K, 65536)) */
+	KG_OPT_SELECT_LOG_CAP = 9     /* admission-log entries per phenotype (default 32 K + 65536); KG_SELECT_LOG only */
 };
 
 /* Kernel classes reported by kg_kernel_time */
@@ -83,7 +89,8 @@ enum {
 	KG_KERNEL_SCAN_REFINE = 2, /* exact re-score of the listed rows (reported "rows" = rows re-scored) */
 	KG_KERNEL_KINSHIP = 3,     /* Gram accumulation (popcount or tensor-core engine) */
 	KG_KERNEL_AUX = 4,         /* squeeze / MAC prefilter / finalize / synthetic generator */
-	KG_KERNEL_CLASSES = 5
+	KG_KERNEL_SCAN_SELECT = 5, /* device heaps: round bookkeeping + candidate sort + heap replay + filter re-tuning */
+	KG_KERNEL_CLASSES = 6
 };
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
@@ -156,6 +163,57 @@ kg_status kg_scan_scores_dense(kg_ctx *ctx, const uint64_t *rows, uint64_t n_row
  * and (optional, may be NULL) the quantised values yq[p * 64 * W_file + file_column].  Host outputs.
  * Fails with KG_ERR_INVALID when the engine is unavailable for the context's shape. */
 kg_status kg_scan_filter_sums(kg_ctx *ctx, const uint64_t *rows, uint64_t n_rows, int32_t *q, int8_t *yq);
+
+/* ---- device-side selection: BestAssociationsHeap on the GPU -------------------------------------
+ * Replaces BestAssociationsHeap::add_association (/root/reference/src/best_associations_heap.cpp:43-59) for all
+ * phenotypes: after kg_select_begin, kg_scan_submit feeds P device-resident heaps that perform exactly the
+ * std::priority_queue<.., cmp_second> element moves of the reference (/root/reference/src/kmer_general.h:113-128;
+ * libstdc++ push_heap / pop_heap), in row order, so set, ties and pop order (ranks) are the reference's.  Thresholds and
+ * the tensor filter's constants stay on the device: the host is not in the scan loop (no kg_scan_set_thresholds /
+ * kg_scan_mark / kg_scan_fetch in this mode; they return KG_ERR_STATE).  Tiles must be submitted in ascending row order. */
+enum {
+	KG_SELECT_LOG = 1   /* keep, per phenotype, every candidate the heap admitted (row order): the hit log of a row shard
+	                       other than the first, replayed on the merging GPU with kg_select_replay */
+};
+/* k_best[p] = capacity of heap p (associate_kmers.cpp:92-96).  Requires kg_scan_set_phenotypes with the same n_pheno.
+ * Fails with KG_ERR_INVALID when a heap does not fit shared memory (k_best > ~14000: use the host replay path). */
+kg_status kg_select_begin(kg_ctx *ctx, const uint64_t *k_best, uint32_t n_pheno, uint32_t flags);
+/* Leave selection mode and free its buffers. */
+kg_status kg_select_end(kg_ctx *ctx);
+/* Wait for the device.  *rows_applied = rows whose candidates are in the heaps, *rows_kept = those of them that passed
+ * the MAC filter (number_of_insertion(), .tested_kmers).  KG_ERR_HITS_OVERFLOW: a round produced more candidates for one
+ * phenotype than its segment holds (scores rising along the table); that round and every later one were NOT applied:
+ * resubmit the rows from *rows_applied on (the library has already shortened its rounds). */
+kg_status kg_select_sync(kg_ctx *ctx, uint64_t *rows_applied, uint64_t *rows_kept);
+/* Heap state image, u64 words: [P][4] {size, cnt_push, cnt_pops, 0}, then [P][k_max][3] {kmer, score bits, row} in
+ * libstdc++ layout order (position 0 = top; pushing a phenotype's entries in this order into an empty
+ * std::priority_queue reproduces the layout).  state: host or device memory.  import also sets the row / kept totals. */
+size_t kg_select_state_len(const kg_ctx *ctx);
+kg_status kg_select_export(kg_ctx *ctx, uint64_t *state);
+kg_status kg_select_import(kg_ctx *ctx, const uint64_t *state, uint64_t rows_applied, uint64_t rows_kept);
+/* Order-sensitive 64-bit digest of all heaps (layout order, k-mer + score bits + row): equal digests <=> equal heaps. */
+kg_status kg_select_digest(kg_ctx *ctx, uint64_t *digest);
+/* Current thresholds (lowest kept score, -1 while a heap is not full), host output [n_pheno]. */
+kg_status kg_select_thresholds(kg_ctx *ctx, double *thr);
+/* Admission log (KG_SELECT_LOG).  kg_select_log_reset drops what was logged so far and zeroes the kept-row total (call
+ * after scanning the shared prefix); counts: host [n_pheno]; export packs the entries {row, kmer, score bits} of
+ * phenotype p at entries[3 * offsets[p] ...] (offsets: host [n_pheno + 1], entries: host or device). */
+kg_status kg_select_log_reset(kg_ctx *ctx);
+kg_status kg_select_log_counts(kg_ctx *ctx, uint64_t *counts);
+kg_status kg_select_log_export(kg_ctx *ctx, uint64_t *entries, const uint64_t *offsets);
+/* Replay candidates that are already in ascending row order per phenotype (a shard's exported log) through the
+ * heaps; rows / kept are added to the totals.  entries: host or device, packed as kg_select_log_export writes them. */
+kg_status kg_select_replay(kg_ctx *ctx, const uint64_t *entries, const uint64_t *offsets, uint64_t rows, uint64_t kept);
+/* Multi-GPU threshold exchange (optional; shrinks the shards' logs).  kg_select_export_scores writes, position by
+ * position, the scores of this context's heap entries whose row id is >= min_row into scores[P][k_max] (DEVICE memory;
+ * -1 elsewhere): a shard passes the first row id of its own block, so that the shards contribute disjoint row sets.
+ * kg_select_set_floor takes n_heaps such arrays back to back (scores[g][p][k_max], e.g. an NCCL all-gather restricted
+ * to this shard and the shards BEFORE it in row order): the k_best-th largest score of their union is a lower bound of
+ * the sequential heap's threshold for every row this context still scans, and becomes a floor under its thresholds
+ * (candidates at or below it are dropped before they reach the heap or the log).  Floors never decrease. */
+kg_status kg_select_export_scores(kg_ctx *ctx, uint64_t min_row, double *scores);
+kg_status kg_select_set_floor(kg_ctx *ctx, const double *scores, uint32_t n_heaps);
+uint32_t kg_select_kmax(const kg_ctx *ctx);
 
 /* ---- kinship ----------------------------------------------------------------------------------
  * Replaces MultipleKmersDataBases::update_emma_kinshhip_calculation

@@ -16,8 +16,10 @@ from . import build as _build
 KG_OK = 0
 KG_ERR_HITS_OVERFLOW = 4
 OPT_SCAN_ENGINE, OPT_HIT_CAPACITY, OPT_KINSHIP_ENGINE, OPT_KERNEL_TIMING, OPT_FILTER_PAIR_LIMIT = 1, 2, 3, 4, 5
-KERNEL_SCAN_EXACT, KERNEL_SCAN_FILTER, KERNEL_SCAN_REFINE, KERNEL_KINSHIP, KERNEL_AUX = 0, 1, 2, 3, 4
-KERNEL_CLASS_NAMES = ["scan_exact", "scan_filter", "scan_refine", "kinship", "aux"]
+OPT_SELECT_GROWTH_PERMILLE, OPT_SELECT_MAX_ROUND, OPT_SELECT_CAND_CAP, OPT_SELECT_LOG_CAP = 6, 7, 8, 9
+SELECT_LOG = 1
+KERNEL_SCAN_EXACT, KERNEL_SCAN_FILTER, KERNEL_SCAN_REFINE, KERNEL_KINSHIP, KERNEL_AUX, KERNEL_SCAN_SELECT = 0, 1, 2, 3, 4, 5
+KERNEL_CLASS_NAMES = ["scan_exact", "scan_filter", "scan_refine", "kinship", "aux", "scan_select"]
 
 HIT_DTYPE = np.dtype([("row", "<u8"), ("kmer", "<u8"), ("score", "<f8"), ("pheno", "<u4"), ("pad", "<u4")])
 
@@ -28,6 +30,9 @@ ABI_SYMBOLS = [
     "kg_scan_clear_hits", "kg_scan_discard", "kg_scan_scores_dense", "kg_kinship_begin", "kg_kinship_accum_len",
     "kg_kinship_submit", "kg_kinship_fetch", "kg_host_alloc", "kg_host_free", "kg_synth_rows_device",
     "kg_launch_count", "kg_kernel_time", "kg_kernel_time_reset", "kg_scan_filter_sums", "kg_mac_filter",
+    "kg_select_begin", "kg_select_end", "kg_select_sync", "kg_select_state_len", "kg_select_export", "kg_select_import",
+    "kg_select_digest", "kg_select_thresholds", "kg_select_log_reset", "kg_select_log_counts", "kg_select_log_export",
+    "kg_select_replay", "kg_select_set_floor", "kg_select_export_scores", "kg_select_kmax",
 ]
 
 
@@ -90,6 +95,23 @@ def load():
     lib.kg_scan_filter_sums.argtypes = [vp, vp, u64, vp, vp]
     lib.kg_kernel_time.argtypes = [vp, C.c_int, C.POINTER(C.c_double), u64p, u64p]
     lib.kg_kernel_time_reset.argtypes = [vp]
+    lib.kg_select_begin.argtypes = [vp, vp, C.c_uint32, C.c_uint32]
+    lib.kg_select_end.argtypes = [vp]
+    lib.kg_select_sync.argtypes = [vp, u64p, u64p]
+    lib.kg_select_state_len.argtypes = [vp]
+    lib.kg_select_state_len.restype = C.c_size_t
+    lib.kg_select_export.argtypes = [vp, vp]
+    lib.kg_select_import.argtypes = [vp, vp, u64, u64]
+    lib.kg_select_digest.argtypes = [vp, u64p]
+    lib.kg_select_thresholds.argtypes = [vp, vp]
+    lib.kg_select_log_reset.argtypes = [vp]
+    lib.kg_select_log_counts.argtypes = [vp, vp]
+    lib.kg_select_log_export.argtypes = [vp, vp, vp]
+    lib.kg_select_replay.argtypes = [vp, vp, vp, u64, u64]
+    lib.kg_select_set_floor.argtypes = [vp, vp, C.c_uint32]
+    lib.kg_select_export_scores.argtypes = [vp, u64, vp]
+    lib.kg_select_kmax.argtypes = [vp]
+    lib.kg_select_kmax.restype = C.c_uint32
     _lib = lib
     return lib
 
@@ -226,6 +248,98 @@ class Context:
         yq = np.zeros((self.n_pheno, 64 * self.w_file), dtype=np.int8)
         self._chk(self._lib.kg_scan_filter_sums(self._h, _rows_ptr(rows), int(n_rows), q.ctypes.data, yq.ctypes.data))
         return q, yq
+
+    # ---- device-side selection (BestAssociationsHeap on the GPU)
+    def select_begin(self, kbest, flags: int = 0):
+        kb = np.ascontiguousarray(np.broadcast_to(np.asarray(kbest, dtype=np.uint64), (self.n_pheno,)))
+        self._chk(self._lib.kg_select_begin(self._h, kb.ctypes.data, self.n_pheno, int(flags)))
+        self._kmax = int(kb.max())
+
+    def select_end(self):
+        self._chk(self._lib.kg_select_end(self._h))
+
+    def select_sync(self):
+        """-> (rows_applied, rows_kept); raises KgError(status KG_ERR_HITS_OVERFLOW) when a round overflowed."""
+        a, k = C.c_uint64(0), C.c_uint64(0)
+        st = self._lib.kg_select_sync(self._h, C.byref(a), C.byref(k))
+        if st != KG_OK:
+            e = KgError(st, self._lib.kg_last_error(self._h).decode())
+            e.rows_applied, e.rows_kept = int(a.value), int(k.value)
+            raise e
+        return int(a.value), int(k.value)
+
+    def select_state_len(self) -> int:
+        return int(self._lib.kg_select_state_len(self._h))
+
+    def select_export(self, dev_ptr: int | None = None):
+        """Heap state image: numpy uint64 array (host) or written to dev_ptr."""
+        if dev_ptr is not None:
+            self._chk(self._lib.kg_select_export(self._h, C.c_void_p(dev_ptr)))
+            return None
+        out = np.zeros(self.select_state_len(), dtype=np.uint64)
+        self._chk(self._lib.kg_select_export(self._h, out.ctypes.data))
+        return out
+
+    def select_import(self, state, rows_applied: int = 0, rows_kept: int = 0):
+        ptr = state.ctypes.data if isinstance(state, np.ndarray) else int(state)
+        self._keepalive2 = state
+        self._chk(self._lib.kg_select_import(self._h, C.c_void_p(ptr), int(rows_applied), int(rows_kept)))
+
+    def select_heaps(self):
+        """-> list over phenotypes of (kmers, scores, rows) in libstdc++ LAYOUT order (position 0 = top)."""
+        st = self.select_export()
+        P, kmax = self.n_pheno, self._kmax
+        hdr = st[:4 * P].reshape(P, 4)
+        ent = st[4 * P:].reshape(P, kmax, 3)
+        out = []
+        for p in range(P):
+            n = int(hdr[p, 0])
+            out.append((ent[p, :n, 0].copy(), ent[p, :n, 1].copy().view(np.float64), ent[p, :n, 2].copy()))
+        return out
+
+    def select_digest(self) -> int:
+        d = C.c_uint64(0)
+        self._chk(self._lib.kg_select_digest(self._h, C.byref(d)))
+        return int(d.value)
+
+    def select_thresholds(self):
+        thr = np.zeros(self.n_pheno, dtype=np.float64)
+        self._chk(self._lib.kg_select_thresholds(self._h, thr.ctypes.data))
+        return thr
+
+    def select_log_reset(self):
+        self._chk(self._lib.kg_select_log_reset(self._h))
+
+    def select_log(self, dev_ptr: int | None = None):
+        """-> (offsets[P + 1], entries[total, 3] uint64 {row, kmer, score bits}); entries go to dev_ptr if given."""
+        counts = np.zeros(self.n_pheno, dtype=np.uint64)
+        self._chk(self._lib.kg_select_log_counts(self._h, counts.ctypes.data))
+        off = np.zeros(self.n_pheno + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(counts)
+        if dev_ptr is not None:
+            self._chk(self._lib.kg_select_log_export(self._h, C.c_void_p(dev_ptr), off.ctypes.data))
+            return off, None
+        ent = np.zeros((int(off[-1]), 3), dtype=np.uint64)
+        self._chk(self._lib.kg_select_log_export(self._h, ent.ctypes.data if len(ent) else None, off.ctypes.data))
+        return off, ent
+
+    def select_log_counts(self):
+        counts = np.zeros(self.n_pheno, dtype=np.uint64)
+        self._chk(self._lib.kg_select_log_counts(self._h, counts.ctypes.data))
+        return counts
+
+    def select_replay(self, entries, offsets, rows: int = 0, kept: int = 0):
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ptr = entries.ctypes.data if isinstance(entries, np.ndarray) else int(entries or 0)
+        self._keepalive2 = entries
+        self._chk(self._lib.kg_select_replay(self._h, C.c_void_p(ptr), off.ctypes.data, int(rows), int(kept)))
+
+    def select_set_floor(self, scores_dev: int, n_heaps: int):
+        """scores_dev: device [n_heaps][P][k_max] f64 as select_export_scores writes them (disjoint row sets!)"""
+        self._chk(self._lib.kg_select_set_floor(self._h, C.c_void_p(scores_dev), int(n_heaps)))
+
+    def select_export_scores(self, min_row: int, scores_dev: int):
+        self._chk(self._lib.kg_select_export_scores(self._h, int(min_row), C.c_void_p(scores_dev)))
 
     # ---- kinship
     def kinship_accum_len(self) -> int:

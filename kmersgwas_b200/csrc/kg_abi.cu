@@ -96,6 +96,8 @@ struct kg_ctx {
 
 	// tensor-core engine state (kg_tc.cuh)
 	KgTcState tc;
+	// device-resident heaps (kg_select_host.cuh)
+	KgSelState sel;
 
 	int scan_engine = 0, kin_engine = 0;
 
@@ -180,9 +182,6 @@ template <int MODE> static kg_status launch_exact_pt(kg_ctx *c, const KgScanPara
 static kg_status launch_exact_list(kg_ctx *c, const KgScanParams &prm, uint32_t n_tiles);
 static kg_status ensure_squeeze_scratch(kg_ctx *c, uint64_t n_rows);
 
-// tensor-core engine (needs kg_ctx and the macros above)
-#include "kg_tc.cuh"
-
 template <typename T>
 static cudaError_t dev_alloc_copy(T **dst, const std::vector<T> &src) {
 	cudaError_t e = cudaMalloc((void **)dst, std::max<size_t>(src.size(), 1) * sizeof(T));
@@ -190,6 +189,18 @@ static cudaError_t dev_alloc_copy(T **dst, const std::vector<T> &src) {
 	if (!src.empty()) e = cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
 	return e;
 }
+
+static bool is_device_pointer(const void *p);
+static kg_status acquire_tile(kg_ctx *c, const uint64_t *rows, uint64_t n_rows, const uint64_t **dev);
+static kg_status release_tile(kg_ctx *c);
+static kg_status memory_view(kg_ctx *c, const uint64_t *dev, uint64_t n_rows, KgRowView *view);
+static kg_status kg_sel_finish_round(kg_ctx *c, uint64_t n_rows, uint64_t first_row_id, bool filter_counters);
+static const uint64_t kHostSubTileRows = 1ull << 20;
+
+// tensor-core engine (needs kg_ctx and the macros above)
+#include "kg_tc.cuh"
+// device-resident heaps
+#include "kg_select_host.cuh"
 
 extern "C" int kg_abi_version(void) { return KG_ABI_VERSION; }
 
@@ -312,6 +323,7 @@ extern "C" void kg_ctx_destroy(kg_ctx *c) {
 	cudaFree(c->d_ibs);
 	if (c->own_accum) cudaFree(c->d_accum);
 	kg_tc_free(&c->tc);
+	kg_sel_free(&c->sel);
 	for (int i = 0; i < 2; i++) {
 		cudaFree(c->d_tile[i]);
 		if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
@@ -348,6 +360,24 @@ extern "C" kg_status kg_set_option(kg_ctx *c, int option, int64_t value) {
 	case KG_OPT_FILTER_PAIR_LIMIT:
 		if (value < -1) KG_FAIL(c, KG_ERR_INVALID, "filter pair limit must be >= -1");
 		c->tc.pair_limit = value;
+		return KG_OK;
+	case KG_OPT_SELECT_GROWTH_PERMILLE:
+		if (value < 1 || value > 100000) KG_FAIL(c, KG_ERR_INVALID, "selection round growth must be in [1, 100000] per mille");
+		c->sel.growth = (double)value / 1000.0;
+		return KG_OK;
+	case KG_OPT_SELECT_MAX_ROUND:
+		if (value < 1 || value >= (1ll << 31)) KG_FAIL(c, KG_ERR_INVALID, "selection round length must be in [1, 2^31)");
+		c->sel.max_round = (uint64_t)value;
+		return KG_OK;
+	case KG_OPT_SELECT_CAND_CAP:
+		if (value < 1) KG_FAIL(c, KG_ERR_INVALID, "candidate capacity must be >= 1");
+		if (c->sel.active) KG_FAIL(c, KG_ERR_STATE, "candidate capacity must be set before kg_select_begin");
+		c->sel.cand_cap_opt = (uint64_t)value;
+		return KG_OK;
+	case KG_OPT_SELECT_LOG_CAP:
+		if (value < 1) KG_FAIL(c, KG_ERR_INVALID, "log capacity must be >= 1");
+		if (c->sel.active) KG_FAIL(c, KG_ERR_STATE, "log capacity must be set before kg_select_begin");
+		c->sel.log_cap_opt = (uint64_t)value;
 		return KG_OK;
 	default:
 		KG_FAIL(c, KG_ERR_INVALID, "unknown option %d", option);
@@ -501,6 +531,7 @@ extern "C" kg_status kg_scan_set_phenotypes(kg_ctx *c, const float *y, uint32_t 
 	if (!c || !y || n_pheno == 0) { if (c) c->err = "kg_scan_set_phenotypes: bad arguments"; return KG_ERR_INVALID; }
 	KG_CUDA(c, cudaSetDevice(c->device));
 	KG_CUDA(c, cudaStreamSynchronize(c->stream));
+	kg_sel_free(&c->sel);   // heaps belong to a phenotype set
 	c->n_pheno = n_pheno;
 	c->min_count = min_count;
 	c->pt = n_pheno > 4 ? 8 : (n_pheno > 2 ? 4 : n_pheno);
@@ -594,6 +625,7 @@ __global__ void kg_round_constants_kernel(const KgRoundConsts rc, double *__rest
 extern "C" kg_status kg_scan_set_thresholds(kg_ctx *c, const double *thr, uint32_t n_pheno) {
 	if (!c || !thr) return KG_ERR_INVALID;
 	if (n_pheno != c->n_pheno || !c->d_thr) KG_FAIL(c, KG_ERR_STATE, "kg_scan_set_thresholds: phenotypes not set / count mismatch");
+	if (c->sel.active) KG_FAIL(c, KG_ERR_STATE, "kg_scan_set_thresholds: thresholds live on the device while a selection is active (kg_select_begin)");
 	KG_CUDA(c, cudaSetDevice(c->device));
 	for (uint32_t p = 0; p < n_pheno; p++) c->h_thr[p] = thr[p];
 	if (c->p_alloc <= KG_RC_MAX_P) {
@@ -696,6 +728,12 @@ static KgScanParams scan_params(kg_ctx *c, const KgRowView &view, uint64_t first
 	prm.hit_capacity = c->hit_capacity;
 	prm.kept_count = c->d_counters + 1;
 	prm.first_row_id = first_row_id;
+	if (c->sel.active) {
+		prm.cand = c->sel.d_cand;
+		prm.cand_count = c->sel.d_cand_count;
+		prm.cand_cap = c->sel.cand_cap;
+		prm.kept_count = c->sel.d_status + KG_SEL_ST_ROUND_KEPT;
+	}
 	return prm;
 }
 
@@ -707,9 +745,8 @@ static bool is_device_pointer(const void *p) {
 
 static kg_status scan_submit_one(kg_ctx *c, const uint64_t *rows, uint64_t n_rows, uint64_t first_row_id);
 
-// Host tiles are cut into sub-tiles so that the H2D copy of sub-tile i+1 runs under the kernels of sub-tile i
-// (two device slots); device tiles are scanned in place, in one launch.
-static const uint64_t kHostSubTileRows = 1ull << 20;
+// Host tiles are cut into sub-tiles (kHostSubTileRows) so that the H2D copy of sub-tile i+1 runs under the kernels of
+// sub-tile i (two device slots); device tiles are scanned in place, in one launch.
 
 extern "C" kg_status kg_scan_submit(kg_ctx *c, const uint64_t *rows, uint64_t n_rows, uint64_t first_row_id) {
 	if (!c) return KG_ERR_INVALID;
@@ -718,6 +755,7 @@ extern "C" kg_status kg_scan_submit(kg_ctx *c, const uint64_t *rows, uint64_t n_
 	if (!rows) KG_FAIL(c, KG_ERR_INVALID, "kg_scan_submit: null rows");
 	if (n_rows >= (1ull << 31)) KG_FAIL(c, KG_ERR_INVALID, "kg_scan_submit: tile of %llu rows too large (max 2^31-1)", (unsigned long long)n_rows);
 	KG_CUDA(c, cudaSetDevice(c->device));
+	if (c->sel.active) return kg_sel_submit(c, rows, n_rows, first_row_id);
 	if (n_rows <= kHostSubTileRows || is_device_pointer(rows)) return scan_submit_one(c, rows, n_rows, first_row_id);
 	const size_t stride = (size_t)c->w_file + 1;
 	for (uint64_t off = 0; off < n_rows; off += kHostSubTileRows) {
@@ -768,6 +806,7 @@ static void timing_resolve_completed(kg_ctx *c) {
 extern "C" kg_status kg_scan_mark(kg_ctx *c) {
 	if (!c) return KG_ERR_INVALID;
 	if (!c->d_y_lane) KG_FAIL(c, KG_ERR_STATE, "kg_scan_mark: call kg_scan_set_phenotypes first");
+	if (c->sel.active) KG_FAIL(c, KG_ERR_STATE, "kg_scan_mark: no hit intervals while a selection is active (kg_select_sync / kg_select_export)");
 	if (c->iv[c->cur ^ 1].closed)
 		KG_FAIL(c, KG_ERR_STATE, "kg_scan_mark: the previous interval has not been fetched yet");
 	KG_CUDA(c, cudaSetDevice(c->device));
@@ -808,6 +847,7 @@ extern "C" kg_status kg_scan_fetch(kg_ctx *c, kg_hit *out, size_t cap, size_t *n
                                    uint64_t *rows_kept) {
 	if (!c) return KG_ERR_INVALID;
 	if (!c->d_y_lane) KG_FAIL(c, KG_ERR_STATE, "kg_scan_fetch: call kg_scan_set_phenotypes first");
+	if (c->sel.active) KG_FAIL(c, KG_ERR_STATE, "kg_scan_fetch: no hit intervals while a selection is active (kg_select_sync / kg_select_export)");
 	KG_CUDA(c, cudaSetDevice(c->device));
 	if (!c->iv[c->cur ^ 1].closed) {
 		kg_status st = kg_scan_mark(c);

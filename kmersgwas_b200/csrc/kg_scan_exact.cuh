@@ -14,6 +14,7 @@
 // per g so the four distinct L addresses of a warp-wide LDS.128 fall in different banks.
 #pragma once
 #include "kg_common.cuh"
+#include "kg_select.cuh"
 
 struct KgScanParams {
 	KgRowView view;          // memory-order rows (identity map: the raw tile itself)
@@ -49,7 +50,31 @@ struct KgScanParams {
 	// pair mode (kg_scan_pair_kernel): (position in row_list, phenotype) pairs from kg_pair_select_kernel
 	const uint2 *pairs;
 	const unsigned long long *pair_count;
+	// device-selection mode (kg_select.cuh): hits go to per-phenotype candidate segments instead of `hits`
+	KgCand *cand;            // [P][cand_cap], NULL = host mode
+	uint32_t *cand_count;    // [P]
+	uint32_t cand_cap;
 };
+
+// one admitted (row, phenotype): host mode appends a kg_hit to the interval buffer, device-selection mode appends a
+// candidate to the phenotype's segment (counts may run past the capacity: the round is then discarded, kg_select.cuh)
+__device__ __forceinline__ void kg_emit_hit(const KgScanParams &prm, uint32_t p, uint64_t row_id, uint64_t kmer, double score) {
+	if (prm.cand) {
+		const uint32_t pos = atomicAdd(prm.cand_count + p, 1u);
+		if (pos < prm.cand_cap) {
+			KgCand c;
+			c.row = row_id; c.kmer = kmer; c.score = score;
+			prm.cand[(size_t)p * prm.cand_cap + pos] = c;
+		}
+		return;
+	}
+	const unsigned long long pos = atomicAdd(prm.hit_count, 1ull);
+	if (pos < prm.hit_capacity) {
+		kg_hit h;
+		h.row = row_id; h.kmer = kmer; h.score = score; h.pheno = p; h.pad_ = 0;
+		prm.hits[pos] = h;
+	}
+}
 
 __device__ __forceinline__ double kg_score_epilogue(float l0, float l1, float l2, float l3, double Nd,
                                                     double N1d, float sum) {
@@ -240,18 +265,7 @@ __global__ void __launch_bounds__(256) kg_scan_exact_kernel(const KgScanParams p
 						prm.scores_out[(size_t)p * prm.view.n_rows + row] = score;
 					} else {
 						const double th = prm.thr[p];
-						if (th < 0.0 || score > th) {
-							const unsigned long long pos = atomicAdd(prm.hit_count, 1ull);
-							if (pos < prm.hit_capacity) {
-								kg_hit h;
-								h.row = prm.first_row_id + ids_of[r];
-								h.kmer = prm.view.base[row * prm.view.stride];
-								h.score = score;
-								h.pheno = p;
-								h.pad_ = 0;
-								prm.hits[pos] = h;
-							}
-						}
+						if (th < 0.0 || score > th) kg_emit_hit(prm, p, prm.first_row_id + ids_of[r], prm.view.base[row * prm.view.stride], score);
 					}
 				}
 			}
@@ -318,18 +332,7 @@ __global__ void __launch_bounds__(256) kg_scan_pair_kernel(const KgScanParams pr
 		if (L == 0 && keep && p < prm.n_pheno) {
 			const double score = kg_score_epilogue(l0, l1, l2, l3, Nd, (double)c, prm.sums[p]);
 			const double th = prm.thr[p];
-			if (th < 0.0 || score > th) {
-				const unsigned long long at = atomicAdd(prm.hit_count, 1ull);
-				if (at < prm.hit_capacity) {
-					kg_hit h;
-					h.row = prm.first_row_id + id;
-					h.kmer = prm.view.base[row * prm.view.stride];
-					h.score = score;
-					h.pheno = p;
-					h.pad_ = 0;
-					prm.hits[at] = h;
-				}
-			}
+			if (th < 0.0 || score > th) kg_emit_hit(prm, p, prm.first_row_id + id, prm.view.base[row * prm.view.stride], score);
 		}
 	}
 }

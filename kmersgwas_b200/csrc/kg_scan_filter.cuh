@@ -61,6 +61,13 @@
 #define KG_F_THREADS ((KG_F_MMA_WARP0 + KG_F_MMA_WARPS) * 32)
 #define KG_F_NO_Q INT32_MIN      // ent_q marker: this (row, group) entry has no recorded accumulators
 #define KG_F_ONE 1               // accumulator units per presence bit: A holds -1 (0xFF, s8), B holds the NEGATED phenotype column
+// perf-experiment switches (KgFilterParams::dbg) exist only in builds with -DKG_PERF_SWITCHES; a production build
+// compiles every such branch away
+#ifdef KG_PERF_SWITCHES
+#define KG_F_DBG(prm, bits) (((prm).dbg & (bits)) != 0u)
+#else
+#define KG_F_DBG(prm, bits) (false)
+#endif
 
 // Per 16-column group: the loosest bound of its phenotype columns, in accumulator units (x KG_F_ONE).
 //   a row is ruled out for the group iff  max |Q| < alpha * sqrt(den) - kappa - slack(m),
@@ -196,7 +203,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 				uint8_t *dst = sRaw + st * raw_stage_bytes;
 				if (bytes != bulk)  // 8 trailing bytes of a ragged last block
 					*reinterpret_cast<uint64_t *>(dst + bulk) = *reinterpret_cast<const uint64_t *>(src + bulk);
-				if (prm.dbg & 8) { kg_mbar_arrive(&raw_full[st]); continue; }
+				if KG_F_DBG(prm, 8) { kg_mbar_arrive(&raw_full[st]); continue; }
 				kg_mbar_arrive_expect_tx(&raw_full[st], bulk);
 				if (bulk) kg_bulk_g2s(dst, src, bulk, &raw_full[st]);
 			}
@@ -247,7 +254,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 			// of its commits then overlap with the next issuers' batches.
 			const uint32_t at = a_tmem0 + st * a_stage_cols;
 			const uint64_t bd = b_desc0 + (uint64_t)c * prm.a_words * 32;
-			const uint32_t ksteps = (prm.dbg & 4) ? 0u : 2 * (c + 1 == prm.nc ? words_last : prm.a_words);
+			const uint32_t ksteps = KG_F_DBG(prm, 4) ? 0u : 2 * (c + 1 == prm.nc ? words_last : prm.a_words);
 			uint32_t kk0 = 0;
 			if (c == 0 && ksteps) {
 				// A: 8 TMEM columns per K = 32 step, 16 per presence word.  B descriptor address field is in 16-byte
@@ -296,12 +303,12 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 				// (at most KG_F_MAX_WPT) are loaded and expanded into registers, so that the stage is held only for
 				// the tcgen05.st instructions themselves.
 				uint32_t v[KG_F_MAX_WPT][16];
-				if (!(prm.dbg & 1)) {
+				if (!KG_F_DBG(prm, 1)) {
 #pragma unroll
 					for (uint32_t i = 0; i < KG_F_MAX_WPT; i++) {
 						if (lo + i < hi) {
 							const uint64_t w = wp[lo + i];
-							if (prm.dbg & 128) {   // perf experiment: no expansion arithmetic, stores only
+							if KG_F_DBG(prm, 128) {   // perf experiment: no expansion arithmetic, stores only
 #pragma unroll
 								for (int j = 0; j < 16; j++) v[i][j] = (uint32_t)w;
 							} else {
@@ -314,11 +321,11 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 				kg_mbar_wait(&a_empty[st], st_par);
 				kg_tc_fence_after();
 				const uint32_t taddr = a_taddr0 + st * a_stage_cols;
-				if (!(prm.dbg & 1)) {
+				if (!KG_F_DBG(prm, 1)) {
 #pragma unroll
 					for (uint32_t i = 0; i < KG_F_MAX_WPT; i++)
 						if (lo + i < hi) {
-							if (prm.dbg & 64) {   // perf experiment: expansion arithmetic only, no tensor-memory stores
+							if KG_F_DBG(prm, 64) {   // perf experiment: expansion arithmetic only, no tensor-memory stores
 #pragma unroll
 								for (int j = 0; j < 16; j++) asm volatile("" ::"r"(v[i][j]));
 							} else {
@@ -366,7 +373,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 				float g = 0.f, hm = 0.f;
 				uint32_t gmask = 0;   // bit k: group k could not be ruled out for this row
 				// (dbg 256: perf experiment, only the first 32 accumulator columns are read back)
-				for (uint32_t c0 = 0; c0 < ((prm.dbg & 2) ? 0u : ((prm.dbg & 256) ? 32u : prm.p_pad)); c0 += 32) {
+				for (uint32_t c0 = 0; c0 < (KG_F_DBG(prm, 2) ? 0u : (KG_F_DBG(prm, 256) ? 32u : prm.p_pad)); c0 += 32) {
 					uint32_t v[16], u[16];
 					kg_tmem_ld16(taddr + c0, v);
 					const bool second = c0 + 16 < prm.p_pad;   // warp-uniform

@@ -16,6 +16,10 @@ static void kg_tc_free(KgTcState *tc) {
 	tc->d_row_list = nullptr; tc->d_yq = nullptr; tc->d_gconst = nullptr; tc->d_scratch = nullptr; tc->d_aligned = nullptr;
 	tc->aligned_cap = 0;
 	tc->row_list_cap = 0;
+	cudaFree(tc->d_scale); cudaFree(tc->d_kappa0); cudaFree(tc->d_degenerate); cudaFree(tc->d_q); cudaFree(tc->d_kidx);
+	cudaFree(tc->d_col_of); cudaFree(tc->d_group_lines);
+	tc->d_scale = nullptr; tc->d_kappa0 = nullptr; tc->d_degenerate = nullptr; tc->d_q = nullptr; tc->d_kidx = nullptr;
+	tc->d_col_of = nullptr; tc->d_group_lines = nullptr;
 	for (int i = 0; i < 2; i++) {
 		if (tc->img_ev[i]) { cudaEventDestroy(tc->img_ev[i]); tc->img_ev[i] = nullptr; }
 		if (tc->h_img_pinned[i]) { cudaFreeHost(tc->h_img_pinned[i]); tc->h_img_pinned[i] = nullptr; }
@@ -132,7 +136,7 @@ static kg_status kg_tc_update_thresholds(kg_ctx *c, KgFilterGroupConst *gc_pinne
 		// pinned image ring: the copy is stream-ordered behind the kernels still reading the old image
 		if (!tc.h_img_pinned[0]) {
 			for (int i = 0; i < 2; i++) {
-				KG_CUDA(c, cudaMallocHost((void **)&tc.h_img_pinned[i], tc.b_bytes + tc.p_pad * sizeof(int32_t)));
+				KG_CUDA(c, cudaMallocHost((void **)&tc.h_img_pinned[i], tc.b_bytes + tc.p_pad * sizeof(int32_t) + P * sizeof(uint32_t) + 16 * 8 * sizeof(float)));
 				KG_CUDA(c, cudaEventCreateWithFlags(&tc.img_ev[i], cudaEventDisableTiming));
 			}
 			tc.img_bytes = tc.b_bytes;
@@ -157,8 +161,14 @@ static kg_status kg_tc_update_thresholds(kg_ctx *c, KgFilterGroupConst *gc_pinne
 		for (uint32_t k = 0; k < tc.p_pad; k++) tp[k] = -1;
 		for (uint32_t p = 0; p < P; p++) tp[col_of[p]] = (int32_t)p;
 		KG_CUDA(c, cudaMemcpyAsync(tc.d_tile_pheno, tp, tc.p_pad * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-		tc.h_yq_image.assign(img, img + tc.b_bytes);
 		KG_CUDA(c, cudaMemcpyAsync(tc.d_yq, img, tc.b_bytes, cudaMemcpyHostToDevice, c->stream));
+		// device twins of the column assignment (kg_filter_retune_kernel continues from them; the debug entry point reads them)
+		uint32_t *cd = reinterpret_cast<uint32_t *>(tp + tc.p_pad);
+		for (uint32_t p = 0; p < P; p++) cd[p] = col_of[p];
+		float *gl = reinterpret_cast<float *>(cd + P);
+		for (size_t i = 0; i < 16 * 8; i++) gl[i] = i < tc.group_lines.size() ? tc.group_lines[i] : 0.0f;
+		KG_CUDA(c, cudaMemcpyAsync(tc.d_col_of, cd, P * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+		KG_CUDA(c, cudaMemcpyAsync(tc.d_group_lines, gl, 16 * 8 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
 		KG_CUDA(c, cudaEventRecord(tc.img_ev[slot], c->stream));
 	}
 	// per-phenotype constants of the per-column test follow the 16 group slots (same staging slot, one copy)
@@ -176,6 +186,16 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	cudaFree(tc.d_yq); cudaFree(tc.d_gconst);
 	tc.d_yq = nullptr; tc.d_gconst = nullptr;
 	tc.col_of.clear();
+	// the filter's list buffers are sized for the phenotype count they were allocated with ([p_pad / 16][capacity]):
+	// a new phenotype set starts from scratch (kg_tc_ensure_row_list reallocates on the next tile)
+	cudaFree(tc.d_row_list); cudaFree(tc.d_group_list); cudaFree(tc.d_ent_q); cudaFree(tc.d_ent_n1); cudaFree(tc.d_pairs);
+	tc.d_row_list = nullptr; tc.d_group_list = nullptr; tc.d_ent_q = nullptr; tc.d_ent_n1 = nullptr; tc.d_pairs = nullptr;
+	tc.row_list_cap = 0;
+	tc.qcap = 0;
+	cudaFree(tc.d_scale); cudaFree(tc.d_kappa0); cudaFree(tc.d_degenerate); cudaFree(tc.d_q); cudaFree(tc.d_kidx);
+	cudaFree(tc.d_col_of); cudaFree(tc.d_group_lines);
+	tc.d_scale = nullptr; tc.d_kappa0 = nullptr; tc.d_degenerate = nullptr; tc.d_q = nullptr; tc.d_kidx = nullptr;
+	tc.d_col_of = nullptr; tc.d_group_lines = nullptr;
 	for (int i = 0; i < 2; i++) {
 		if (tc.img_ev[i]) { cudaEventSynchronize(tc.img_ev[i]); cudaEventDestroy(tc.img_ev[i]); tc.img_ev[i] = nullptr; }
 		if (tc.h_img_pinned[i]) { cudaFreeHost(tc.h_img_pinned[i]); tc.h_img_pinned[i] = nullptr; }
@@ -190,10 +210,12 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 		const uint32_t a_cols = KG_F_TMEM_COLS - 2 * tc.p_pad;
 		tc.a_words = std::max(1u, std::min<uint32_t>(c->w_file, a_cols / 32));           // at least two stages (few large stages measured best)
 		tc.a_words = std::min<uint32_t>(tc.a_words, KG_F_MAX_WPT * KG_F_NSUB);            // register budget of the expanders
-		if (const char *e = getenv("KG_FILTER_A_WORDS")) {                                // perf experiments
+#ifdef KG_PERF_SWITCHES   // perf experiments only (profiles/filter_dbg_sweep.sh builds with -DKG_PERF_SWITCHES)
+		if (const char *e = getenv("KG_FILTER_A_WORDS")) {
 			const uint32_t v = (uint32_t)atoi(e);
 			if (v >= 1 && v <= c->w_file && v <= a_cols / 32 && v <= KG_F_MAX_WPT * KG_F_NSUB) tc.a_words = v;
 		}
+#endif
 		tc.a_stages = std::max(2u, std::min<uint32_t>(KG_F_MAX_A_STAGES, a_cols / (16 * tc.a_words)));
 		tc.nc = (c->w_file + tc.a_words - 1) / tc.a_words;
 	}
@@ -285,10 +307,30 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	e = cudaMalloc((void **)&tc.d_slack, tc.slack_table.size() * sizeof(float));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc slack table: %s", cudaGetErrorString(e));
 	KG_CUDA(c, cudaMemcpyAsync(tc.d_slack, tc.slack_table.data(), tc.slack_table.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-	tc.use_pairs = !(getenv("KG_FILTER_NO_PAIRS") && atoi(getenv("KG_FILTER_NO_PAIRS")));   // perf experiments: list mode only
+	{
+		// device twins of the per-phenotype tables (kg_filter_retune_kernel)
+		std::vector<uint32_t> kidx(N);
+		for (uint32_t i = 0; i < N; i++) kidx[i] = kg_filter_k_of_column(c->map_word[i] * 64 + c->map_bit[i]);
+		std::vector<uint32_t> zero_cols(P, 0u);
+		std::vector<float> zero_lines(16 * 8, 0.0f);
+		KG_CUDA(c, dev_alloc_copy(&tc.d_scale, tc.scale));
+		KG_CUDA(c, dev_alloc_copy(&tc.d_kappa0, tc.kappa));
+		KG_CUDA(c, dev_alloc_copy(&tc.d_degenerate, tc.degenerate));
+		KG_CUDA(c, dev_alloc_copy(&tc.d_q, tc.h_q));
+		KG_CUDA(c, dev_alloc_copy(&tc.d_kidx, kidx));
+		KG_CUDA(c, dev_alloc_copy(&tc.d_col_of, zero_cols));
+		KG_CUDA(c, dev_alloc_copy(&tc.d_group_lines, zero_lines));
+	}
+	tc.use_pairs = true;
+	tc.dbg_flags = 0u;
+	tc.n_issuers = 0u;
+	tc.print_stats = false;
+#ifdef KG_PERF_SWITCHES   // perf experiments only: a production build never reads these (results are wrong with KG_FILTER_DEBUG)
+	tc.use_pairs = !(getenv("KG_FILTER_NO_PAIRS") && atoi(getenv("KG_FILTER_NO_PAIRS")));
 	tc.dbg_flags = getenv("KG_FILTER_DEBUG") ? (uint32_t)atoi(getenv("KG_FILTER_DEBUG")) : 0u;
 	tc.n_issuers = getenv("KG_FILTER_ISSUERS") ? (uint32_t)std::max(1, std::min(KG_F_MMA_WARPS, atoi(getenv("KG_FILTER_ISSUERS")))) : 0u;
 	tc.print_stats = getenv("KG_FILTER_STATS") != nullptr;
+#endif
 	KG_CUDA(c, cudaFuncSetAttribute(kg_scan_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	KG_CUDA(c, cudaFuncSetAttribute(kg_scan_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	tc.scan_ready = true;
@@ -345,7 +387,7 @@ static KgFilterParams kg_tc_filter_params(kg_ctx *c, const uint64_t *dev, uint64
 	f.ent_q = tc.d_ent_q;
 	f.ent_n1 = tc.d_ent_n1;
 	f.qcap = tc.use_pairs ? tc.qcap : 0;
-	f.kept_count = c->d_counters + 1;
+	f.kept_count = c->sel.active ? c->sel.d_status + KG_SEL_ST_ROUND_KEPT : c->d_counters + 1;
 	f.n_issuers = tc.n_issuers ? tc.n_issuers : KG_F_MMA_WARPS;
 	f.dbg = tc.dbg_flags;
 	return f;
@@ -485,6 +527,7 @@ static kg_status kg_tc_scan_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_r
 		for (uint32_t g = 0; g < tc.p_pad / 16; g++) fprintf(stderr, " %llu", h[g]);
 		fprintf(stderr, "  pairs %llu\n", h[24]);
 	}
+	if (c->sel.active) return kg_sel_finish_round(c, n_rows, first_row_id, true);
 	kg_tile_end_kernel<<<1, 32, 0, c->stream>>>(c->d_counters, tc.d_group_count, tc.p_pad / 16);
 	KG_LAUNCH_CHECK(c);
 	return KG_OK;
@@ -515,9 +558,14 @@ static kg_status kg_tc_filter_debug(kg_ctx *c, const uint64_t *dev_in, uint64_t 
 	cudaError_t e3 = cudaMemcpy(q.data(), d_q, q.size() * sizeof(int32_t), cudaMemcpyDeviceToHost);
 	cudaFree(d_q);
 	KG_CUDA(c, e1); KG_CUDA(c, e2); KG_CUDA(c, e3);
+	// the column assignment and the operand image as the device holds them (the host or the re-tune kernel wrote them)
+	std::vector<uint32_t> col_of(c->n_pheno);
+	std::vector<int8_t> image(tc.b_bytes);
+	KG_CUDA(c, cudaMemcpy(col_of.data(), tc.d_col_of, col_of.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	KG_CUDA(c, cudaMemcpy(image.data(), tc.d_yq, image.size(), cudaMemcpyDeviceToHost));
 	for (uint64_t r = 0; r < n_rows; r++)
 		for (uint32_t p = 0; p < c->n_pheno; p++) {
-			const int32_t v = q[r * tc.p_pad + tc.col_of[p]];
+			const int32_t v = q[r * tc.p_pad + col_of[p]];
 			if (v % KG_F_ONE != 0) KG_FAIL(c, KG_ERR_STATE, "filter accumulator not a multiple of %d", KG_F_ONE);
 			q_host[r * c->n_pheno + p] = v / KG_F_ONE;
 		}
@@ -525,7 +573,7 @@ static kg_status kg_tc_filter_debug(kg_ctx *c, const uint64_t *dev_in, uint64_t 
 		const uint32_t kpad = 64 * c->w_file;
 		for (uint32_t p = 0; p < c->n_pheno; p++)
 			for (uint32_t col = 0; col < kpad; col++)
-				yq_host[(size_t)p * kpad + col] = (int8_t)-tc.h_yq_image[kg_tc_b_offset(tc, tc.col_of[p], kg_filter_k_of_column(col))];
+				yq_host[(size_t)p * kpad + col] = (int8_t)-image[kg_tc_b_offset(tc, col_of[p], kg_filter_k_of_column(col))];
 	}
 	return KG_OK;
 }

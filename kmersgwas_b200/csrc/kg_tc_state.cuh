@@ -53,4 +53,35 @@ struct KgTcState {
 	uint32_t kin_groups = 0, kin_ctas = 0;
 	size_t kin_smem = 0;
 	void *d_scratch = nullptr;
+	// device twins of the host-side filter tables, for kg_filter_retune_kernel (device-selection mode)
+	double *d_scale = nullptr;             // [P]
+	float *d_kappa0 = nullptr;             // [P]
+	uint8_t *d_degenerate = nullptr;       // [P]
+	int8_t *d_q = nullptr;                 // [P][n_used]
+	uint32_t *d_kidx = nullptr;            // [n_used] operand K index of memory column i
+	uint32_t *d_col_of = nullptr;          // [P] column assignment the device image was built with
+	float *d_group_lines = nullptr;        // [16][8]
+};
+
+// Device-resident BestAssociationsHeap set (kg_select.cuh); owned by kg_ctx.
+struct KgSelState {
+	bool active = false;
+	bool log_enabled = false;
+	uint32_t n_pheno = 0, kmax = 0, cand_cap = 0, sort_stride = 0, sort_smem = 0, log_cap = 0;
+	size_t smem = 0;
+	std::vector<uint32_t> kbest;
+	uint32_t *d_kbest = nullptr, *d_hsize = nullptr, *d_hslot = nullptr, *d_cand_count = nullptr, *d_order = nullptr, *d_log_count = nullptr;
+	double *d_hscore = nullptr, *d_floor = nullptr;
+	uint64_t *d_pay_kmer = nullptr, *d_pay_row = nullptr;
+	unsigned long long *d_hstat = nullptr, *d_sort_buf = nullptr, *d_status = nullptr, *d_digest = nullptr;
+	struct KgCand *d_cand = nullptr, *d_log = nullptr;
+	unsigned long long *h_status = nullptr;   // pinned copy of d_status
+	bool floor_set = false;
+	// round schedule (host side, deterministic: the host never sees the thresholds)
+	uint64_t rows_submitted = 0;           // rows handed to the device since kg_select_begin / the last overflow recovery
+	uint64_t fill_rows = 0;                // rows scanned by the dense exact kernel before the filter takes over
+	double growth = 0.5;                   // round length = growth x rows submitted so far (candidates per phenotype ~ growth x K)
+	uint64_t max_round = 1ull << 23;
+	uint64_t min_round = 4096;
+	uint64_t cand_cap_opt = 0, log_cap_opt = 0;   // KG_OPT_SELECT_CAND_CAP / KG_OPT_SELECT_LOG_CAP (0 = default)
 };
