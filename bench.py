@@ -4,19 +4,21 @@
   python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA kernels through the C ABI)
   python bench.py --impl reference [--gpus N] [--steps K] ...    the unmodified reference CPU binary
 
-Workload (config.workload): the shape of BASELINE.json configs[1] -- 1135 samples, 1 phenotype + 100
-permutations (P = 101), best K = 10001, maf 0.05 / mac 5 -- on synthetic rows of the counter-based
-generator documented in oracle/oracle.c.  The full 2.3e9-row table (350 GB) does not fit one GPU's HBM, so a
-"step" is one batch of --rows-per-step rows (default 2^23 = 1.27 GB, larger than the 126 MB L2; the reference's default
---batch_size is 10^7 rows) pushed through
-the product's associate loop (kmersgwas_b200/host/association_driver.cpp: device scan -> candidate hits ->
-exact replay through BestAssociationsHeap); every step scans rows no earlier step saw, and the heaps carry over.
+Workload (config.workload): BASELINE.json configs[1] -- 2.3e9 k-mers x 1135 samples, 1 phenotype + 100 permutations
+(P = 101), best K = 10001, maf 0.05 / mac 5 -- on synthetic rows of the counter-based generator documented in
+oracle/oracle.c.  The timed region is the WHOLE JOB from empty heaps: --job-rows rows per GPU (default 2.3e9) cut into
+K steps, every step one kg_scan_submit of its batch; the device-resident BestAssociationsHeap set (kg_select_*) takes
+the candidates, so the cold phase, the heap work and (N > 1) the exact merge of the shards are all inside the timing.
+The table (350 GB per GPU) is larger than HBM: the steps are generated into an HBM-resident ring segment by segment
+(untimed) and each segment is then scanned (timed); the job time is the sum of the segments.
 
-  value  : rows/s with the batches already resident in HBM (device pointers handed to the C ABI)
-  e2e    : rows/s with the batches in pinned HOST memory; H2D of the rows and D2H of the hits inside the timing
-  N > 1  : rows sharded by k-mer block across ranks ("weak": every rank scans --rows-per-step rows per step), no
-           data-path collective; after the timed steps the per-rank hit logs are exchanged (one all-to-all by
-           phenotype) and merged exactly, every rank merging its share of the phenotypes (merge_ms).
+  value  : rows of the job / job time, batches resident in HBM (device pointers handed to the C ABI)
+  e2e    : rows/s with the batches in pinned HOST memory; H2D of the rows and the D2H read of the result inside the timing
+  N > 1  : weak scaling, every rank scans its own --job-rows k-mer block; no data-path collective in the scan; ranks > 0
+           warm-start from a shared prefix and log what their heaps admit; the logs are all-gathered over NCCL and
+           replayed on rank 0 through the same device heaps (merge_ms, inside the timed region)
+  parity : bench-scale checks (untimed): tensor-filter engine == exact engine on a full 2^23-row tile at the job's final
+           thresholds, and the shard protocol == one sequential scan (heap digests)
 """
 from __future__ import annotations
 
@@ -231,99 +233,161 @@ def our_arm(args):
         if world > 1:
             dist.barrier()
 
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     n, p = args.samples, args.phenos
     w_file = (n + 63) // 64
     stride = w_file + 1
     row_bytes = 8 * stride
-    R = args.rows_per_step
     W, K = args.warmup, args.steps
+    J = args.job_rows                                   # rows per GPU (the whole config-2 table at N = 1)
+    R = (J + K - 1) // K                                # rows per step
     y = phenotypes(n, p)
     mc = min_count_of(n, MAF, MAC)
-    idx = np.arange(n)
-    mw, mb = (idx // 64).astype(np.uint32), (idx % 64).astype(np.uint32)
+    row0 = rank * J                                     # first global row of this rank's k-mer block
 
     stream = torch.cuda.Stream()
-    sess = kg.Session(n, mw, mb, y, mc, args.kbest, device=local, stream=stream.cuda_stream,
-                      scan_engine=args.scan_engine, log_hits=(world > 1))
-    abi = kg.load()
-    h = sess.ctx_handle
-    sess.set_option(kg.OPT_KERNEL_TIMING, 1)
+    ctx = kg.Context.identity(n, device=local, stream=stream.cuda_stream)
+    ctx.set_option(kg.OPT_SCAN_ENGINE, args.scan_engine)
+    ctx.set_option(kg.OPT_KERNEL_TIMING, 1)
+    ctx.set_phenotypes(y, mc)
+    int8_peak = ctx.probe_int8_peak()
 
-    # ---- resident batches: step s, rank r scans global rows [(s*world + r) * R, +R)
-    n_e2e = min(K, args.e2e_buffers)
-    total_steps = W + K + n_e2e
+    # ---- batch ring: as many steps resident in HBM as fit; the job runs in segments of that many steps, each segment
+    # generated (untimed) and then scanned (timed); the heaps carry over, so the timed regions add up to the whole job
     free_b, _tot = torch.cuda.mem_get_info()
-    resident = min(W + K, max(2, int(free_b * 0.6) // (R * row_bytes)))
-    bufs = [torch.empty(R * stride, dtype=torch.int64, device="cuda") for _ in range(resident)]
+    seg_steps = max(1, min(K, int(free_b * args.hbm_fraction) // (R * row_bytes)))
+    bufs = [torch.empty(R * stride, dtype=torch.int64, device="cuda") for _ in range(seg_steps)]
 
-    # Scan position.  The timed steps should look like the bulk of the 2.3e9-row job, not like its first 2 %
-    # (where the heaps have seen few rows, thresholds are low and most of the time goes into exact re-scoring of
-    # candidates): --prefill-rows rows per GPU are scanned first, untimed, through the same associate loop.
-    prefill_steps = (args.prefill_rows + R - 1) // R
+    def step_rows(s):
+        return min(R, J - s * R)
 
-    def first_row(step):
-        return ((prefill_steps + step) * world + rank) * R
+    def fill(buf, first_global_row, rows):
+        ctx.synth_rows_device(SEED_TABLE, first_global_row, rows, buf.data_ptr())
 
-    def fill(buf, step):
-        st = abi.kg_synth_rows_device(h, SEED_TABLE, first_row(step), R, buf.data_ptr())
-        assert st == 0, abi.kg_last_error(h)
-
-    launches0 = None
+    sampler = ClockSampler(local)
     with torch.cuda.stream(stream):
-        t_pre0 = time.perf_counter()
-        for ps in range(prefill_steps):
-            b = bufs[ps % 2]
-            st = abi.kg_synth_rows_device(h, SEED_TABLE, (ps * world + rank) * R, R, b.data_ptr())
-            assert st == 0, abi.kg_last_error(h)
-            sess.associate(b.data_ptr(), R, (ps * world + rank) * R)   # refills of b are stream-ordered behind its scan
-        sess.finish()
-        prefill_s = time.perf_counter() - t_pre0
-        for s in range(min(resident, W + K)):
-            fill(bufs[s], s)
-        stream.synchronize()
-        # ---- warm-up (fills the heaps: the cold phase of the scan happens here)
+        # ---- warm-up: W untimed steps of the same loop on other rows (allocations, first launches), then fresh heaps
+        ctx.select_begin(args.kbest)
+        wrows = min(R, 1 << 24)
         for s in range(W):
-            sess.associate(bufs[s % resident].data_ptr(), R, first_row(s))
-        sess.finish()
-        # batches beyond the resident ring are regenerated into freed slots before the timing starts
-        for s in range(resident, W + K):
-            fill(bufs[s % resident], s)
-        stream.synchronize()
-        sess.kernel_times_reset()
-        launches0 = sess.launches()
-        io0 = sess.io_bytes()
-        stats0 = sess.stats()
-        hostms0 = sess.host_ms()
-        sampler = ClockSampler(local)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            fill(bufs[0], (1 << 40) + s * wrows, wrows)
+            ctx.scan_submit(bufs[0].data_ptr(), wrows, (1 << 40) + s * wrows)
+        ctx.select_sync()
+        flags = kg.SELECT_LOG if (world > 1 and rank > 0) else 0
+        ctx.select_begin(args.kbest, flags)
+        ctx.kernel_times_reset()
+        launches0 = ctx.launches
+        step_ms, seg_ms = [], []
+        prefix_ms = 0.0
+        timed_ms = 0.0
         barrier()
-        torch.cuda.synchronize()
-        with sampler:   # (the e2e region below is sampled as well)
-            ev0.record(stream)
-            for s in range(W, W + K):
-                sess.associate(bufs[s % resident].data_ptr(), R, first_row(s))
-            sess.finish()          # the last round's hits are in the heaps before the clock stops
-            ev1.record(stream)
-            torch.cuda.synchronize()
-        barrier()
-        ms_dev = ev0.elapsed_time(ev1)
-        kt = sess.kernel_times()
-        launches_timed = sess.launches() - launches0
-        io1 = sess.io_bytes()
-        stats1 = sess.stats()
-        hostms1 = sess.host_ms()
+        with sampler:
+            # ---- ranks > 0 warm-start from the shared prefix: the first --prefix-rows rows of the table (rank 0's own
+            # first rows).  Their thresholds are then never above the sequential heap's, and their logs stay short.
+            if world > 1 and rank > 0 and args.prefix_rows > 0:
+                pre = min(args.prefix_rows, R)
+                fill(bufs[0], 0, pre)
+                stream.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                ctx.scan_submit(bufs[0].data_ptr(), pre, 0)
+                ctx.select_log_reset()
+                e1.record(stream)
+                stream.synchronize()
+                prefix_ms = e0.elapsed_time(e1)
+            s = 0
+            while s < K:
+                seg = list(range(s, min(K, s + seg_steps)))
+                for i, st in enumerate(seg):
+                    fill(bufs[i], row0 + st * R, step_rows(st))
+                torch.cuda.synchronize()
+                barrier()
+                evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(seg) + 1)]
+                evs[0].record(stream)
+                for i, st in enumerate(seg):
+                    ctx.scan_submit(bufs[i].data_ptr(), step_rows(st), row0 + st * R)
+                    evs[i + 1].record(stream)
+                if seg[-1] == K - 1:
+                    applied, kept = ctx.select_sync()      # the heaps are final before the clock stops
+                torch.cuda.synchronize()
+                seg_ms.append(evs[0].elapsed_time(evs[-1]))
+                step_ms += [evs[i].elapsed_time(evs[i + 1]) for i in range(len(seg))]
+                s += len(seg)
+            timed_ms = sum(seg_ms) + prefix_ms
+            kt = ctx.kernel_times()
+            launches_timed = ctx.launches - launches0
 
-        # ---- e2e: same loop from pinned host memory (H2D of the rows + D2H of the hits inside the timing)
-        host = [torch.empty(R * stride, dtype=torch.int64).pin_memory() for _ in range(n_e2e)]
+            # ---- N > 1: exact merge, inside the job: the logs of ranks 1 .. N-1 (what their heaps admitted, in row order)
+            # are gathered on every rank and replayed in rank order through rank 0's heaps, which are exact for its
+            # own block -> the sequential reference heaps of the whole N x J-row table (kg_select_replay)
+            merge_ms, log_entries = None, None
+            if world > 1:
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                counts = torch.zeros(p, dtype=torch.int64, device="cuda")
+                if rank > 0:
+                    counts = torch.from_numpy(ctx.select_log_counts().astype(np.int64)).cuda()
+                all_counts = torch.zeros(world * p, dtype=torch.int64, device="cuda")
+                dist.all_gather_into_tensor(all_counts, counts)
+                all_counts = all_counts.cpu().numpy().reshape(world, p)
+                totals = all_counts.sum(axis=1)
+                mx = int(totals.max())
+                mine = torch.zeros(max(mx, 1) * 3, dtype=torch.int64, device="cuda")
+                if rank > 0 and totals[rank] > 0:
+                    off = np.zeros(p + 1, dtype=np.uint64)
+                    off[1:] = np.cumsum(all_counts[rank]).astype(np.uint64)
+                    ctx.select_log(dev_ptr=mine.data_ptr())
+                gathered = torch.empty(world * max(mx, 1) * 3, dtype=torch.int64, device="cuda")
+                kept_t = torch.tensor([kept, applied], dtype=torch.int64, device="cuda")
+                kept_all = torch.zeros(2 * world, dtype=torch.int64, device="cuda")
+                stream.synchronize()
+                dist.all_gather_into_tensor(gathered, mine)
+                dist.all_gather_into_tensor(kept_all, kept_t)
+                torch.cuda.synchronize()
+                kept_all = kept_all.cpu().numpy().reshape(world, 2)
+                if rank == 0:
+                    for r in range(1, world):
+                        off = np.zeros(p + 1, dtype=np.uint64)
+                        off[1:] = np.cumsum(all_counts[r]).astype(np.uint64)
+                        ctx.select_replay(gathered.data_ptr() + r * max(mx, 1) * 24, off, J, int(kept_all[r, 0]))
+                    applied, kept = ctx.select_sync()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                merge_ms = max_over_ranks(e0.elapsed_time(e1))
+                log_entries = int(totals.sum())
+                timed_ms += merge_ms
+            barrier()
+        job_ms = max_over_ranks(timed_ms)
+        sel_stats = ctx.select_stats()
+        job_digest = ctx.select_digest() if rank == 0 else 0
+        thr_end = ctx.select_thresholds()
+        status_rows = (applied, kept)
+
+        # ---- parity at bench scale (untimed): (1) one full 2^23-row tile at the job's final thresholds through the tensor
+        # filter engine and through the exact engine -> equal heap digests; (2) the N-shard protocol against one sequential scan
+        parity = parity_block(args, kg, torch, dist, ctx, rank, world, local, n, p, y, mc, stride, stream)
+
+        # ---- e2e: K steps of 2^23 rows from pinned HOST memory through the same C-ABI calls (H2D inside the timing, one
+        # D2H read of the step's result = rows applied / kept), continuing on the job's heaps
+        Re = min(args.e2e_rows, R)
+        n_e2e = min(K, args.e2e_buffers)
+        host = [torch.empty(Re * stride, dtype=torch.int64).pin_memory() for _ in range(n_e2e)]
+        e2e_row0 = (world + rank) * J + (1 << 36)
         for i in range(n_e2e):
-            fill(bufs[0], W + K + i)
+            fill(bufs[0], e2e_row0 + i * Re, Re)
             stream.synchronize()
-            host[i].copy_(bufs[0])
+            host[i].copy_(bufs[0][: Re * stride])
         for i in range(min(2, n_e2e)):   # untimed: first touch of the pinned buffers by the DMA engine
-            sess.associate(host[i].data_ptr(), R, first_row(W + K + i))
-        sess.finish()
+            ctx.scan_submit(host[i].data_ptr(), Re, e2e_row0 + i * Re)
+        ctx.select_sync()
         torch.cuda.synchronize()
-        io2 = sess.io_bytes()
         ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         torch.cuda.synchronize()
@@ -333,164 +397,171 @@ def our_arm(args):
         with sampler2:
             ev2.record(stream)
             for i in range(K):
-                sess.associate(host[i % n_e2e].data_ptr(), R, first_row(W + K + (i % n_e2e)))
-            sess.finish()
+                ctx.scan_submit(host[i % n_e2e].data_ptr(), Re, e2e_row0 + (2 + i) * Re)
+                ctx.select_sync()
             ev3.record(stream)
             torch.cuda.synchronize()
         t_host1 = time.perf_counter()
         barrier()
-        ms_e2e = max(ev2.elapsed_time(ev3), 1e3 * (t_host1 - t_host0))
-        io3 = sess.io_bytes()
-
-    def max_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    ms_dev = max_over_ranks(ms_dev)
-    ms_e2e = max_over_ranks(ms_e2e)
-
-    # ---- N > 1: exact merge of the shards' hit logs (host side, once per job).  Phenotypes are independent, so rank r
-    # merges the phenotypes p = r (mod N): one all-to-all of the logs, then every rank replays its phenotypes' hits
-    # in global row order through fresh heaps (kgh_merge_hit_log) -- the sequential reference heap state, ties included.
-    merge_ms = None
-    if world > 1:
-        t0 = time.perf_counter()
-        log = sess.hit_log()
-        kept = sess.stats()["rows_kept"]
-        dest = (log["pheno"] % world).astype(np.int64)
-        order = np.argsort(dest, kind="stable")
-        send_counts = np.bincount(dest, minlength=world).astype(np.int64)
-        send = torch.from_numpy(log[order].view(np.uint8).reshape(-1).copy()).cuda()
-        counts_all = torch.zeros(world * world, dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(counts_all, torch.from_numpy(send_counts).cuda())
-        counts_all = counts_all.cpu().numpy().reshape(world, world)          # [src][dst]
-        recv_counts = counts_all[:, rank]
-        isz = kg.HIT_DTYPE.itemsize
-        recv = torch.empty(int(recv_counts.sum()) * isz, dtype=torch.uint8, device="cuda")
-        dist.all_to_all_single(recv, send, output_split_sizes=[int(c) * isz for c in recv_counts],
-                               input_split_sizes=[int(c) * isz for c in send_counts])
-        kept_all = torch.tensor([kept], dtype=torch.int64, device="cuda")
-        dist.all_reduce(kept_all)
-        mine = recv.cpu().numpy().view(kg.HIT_DTYPE)
-        hs = kg.HeapSet(args.kbest, p)
-        hs.merge(mine, int(kept_all.item()))
-        my_phenos = [j for j in range(p) if j % world == rank]
-        assert all(hs.tested(j) == int(kept_all.item()) for j in my_phenos)
-        merge_local = 1e3 * (time.perf_counter() - t0)
-        merge_ms = max_over_ranks(merge_local)
-
-    # ---- cold start (the first rows of the job: empty heaps, thresholds -1, then low): same loop, fresh session
-    cold = None
-    if args.cold_steps > 0:
-        cs = kg.Session(n, mw, mb, y, mc, args.kbest, device=local, stream=stream.cuda_stream, scan_engine=args.scan_engine)
-        nc_ = min(args.cold_steps, len(bufs))
-        with torch.cuda.stream(stream):
-            for s_ in range(nc_):
-                st = abi.kg_synth_rows_device(h, SEED_TABLE, (s_ * world + rank) * R, R, bufs[s_].data_ptr())
-                assert st == 0, abi.kg_last_error(h)
-            stream.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
-            torch.cuda.synchronize()
-            e0.record(stream)
-            step_ev = []
-            t_h0 = time.perf_counter()
-            host_s = []
-            for s_ in range(nc_):
-                cs.associate(bufs[s_].data_ptr(), R, (s_ * world + rank) * R)
-                ev = torch.cuda.Event(enable_timing=True)
-                ev.record(stream)
-                step_ev.append(ev)
-                host_s.append(time.perf_counter() - t_h0)
-            cs.finish()
-            e1.record(stream)
-            torch.cuda.synchronize()
-        ms_cold = max_over_ranks(e0.elapsed_time(e1))
-        cold_steps_ms = [e0.elapsed_time(step_ev[0])] + [step_ev[i - 1].elapsed_time(step_ev[i]) for i in range(1, nc_)]
-        cold_stats = cs.stats()
-        cold_host = cs.host_ms()
-        cs.close()
-        cold = {"value": R * nc_ * world / (ms_cold * 1e-3), "unit": "k-mers/s", "steps": nc_, "ms_per_step": ms_cold / nc_,
-                "device_ms_by_step": [round(v, 3) for v in cold_steps_ms], "host_s_at_step": [round(v, 4) for v in host_s],
-                "rounds": cold_stats["rounds"], "hits_replayed": cold_stats["hits_replayed"], "host_ms": cold_host,
-                "note": f"rows [0, {R * nc_ * world}) of the job from empty heaps, no warm-up: exact engine until the heaps are full, then the "
-                        f"filter with low thresholds; the headline value is measured at rows >= {prefill_steps * R * world}"}
+        ms_e2e = max_over_ranks(max(ev2.elapsed_time(ev3), 1e3 * (t_host1 - t_host0)))
 
     # ---- kinship leg (config 3 shape, bounded rows): GB/s of table consumed
     kin = kinship_leg(args, kg, torch, dist, rank, world, local, n, stride, row_bytes)
 
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
-        rows_total = R * K * world
-        value = rows_total / (ms_dev * 1e-3)
-        e2e_value = rows_total / (ms_e2e * 1e-3)
-        dom = max(("scan_exact", "scan_filter", "scan_refine"), key=lambda k_: kt[k_][0])
+        rows_total = J * world
+        value = rows_total / (job_ms * 1e-3)
+        e2e_value = Re * K * world / (ms_e2e * 1e-3)
+        dom = max(("scan_exact", "scan_filter", "scan_refine", "scan_select"), key=lambda k_: kt[k_][0])
         dom_ms, dom_launches, dom_rows = kt[dom]
-        achieved = (dom_rows * row_bytes) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-        t_fp32_row = (128 * ((n + 127) // 128)) * p / (148 * 128 * 1.965e9)
+        hbm_achieved = (dom_rows * row_bytes) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         traffic = None
         try:
-            tr = json.loads((ROOT / "profiles" / "r01_ncu_traffic.json").read_text())
+            tr = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
             if dom in tr and (n, p) == (N_SAMPLES, N_PHENO):
                 traffic = tr[dom]["dram_bytes_per_row"] * dom_rows / max(dom_launches, 1)
         except Exception:
             pass
-        n_pad_cols = 128 * ((64 * w_file + 127) // 128)
+        k_pad = 128 * ((64 * w_file + 127) // 128)
         p_pad = 16 * ((p + 1 + 15) // 16)
-        tensor_ops = 2.0 * n_pad_cols * p_pad * kt["scan_filter"][2]          # int8 MACs x 2 issued by the filter
-        tensor_tops = tensor_ops / (kt["scan_filter"][0] * 1e-3) / 1e12 if kt["scan_filter"][0] > 0 else 0.0
+        f_ms, f_launches, f_rows = kt["scan_filter"]
+        tensor_ops = 2.0 * k_pad * p_pad * f_rows                          # int8 multiply-adds x 2 the filter issues
+        tensor_tops = tensor_ops / (f_ms * 1e-3) / 1e12 if f_ms > 0 else 0.0
+        t_hbm_row = row_bytes / (hbm_peak * 1e9)
+        t_tensor_row = 2.0 * k_pad * p_pad / (int8_peak * 1e12) if int8_peak > 0 else 0.0
+        tensor_binds = dom == "scan_filter" and t_tensor_row > t_hbm_row
+        steady = step_ms[len(step_ms) // 2:]
+        roofline = {
+            "bound": "tensor_int8" if tensor_binds else "hbm", "kernel": dom,
+            "achieved": tensor_tops if tensor_binds else hbm_achieved,
+            "peak": int8_peak if tensor_binds else hbm_peak,
+            "unit": "TOP/s" if tensor_binds else "GB/s",
+            "frac": (tensor_tops / int8_peak if int8_peak > 0 else None) if tensor_binds else hbm_achieved / hbm_peak,
+            "traffic": traffic,
+            "peak_source": ("measured live: kg_probe_int8_peak (back-to-back tcgen05.mma kind::i8 M128 N256 K32 on all SMs, CUDA events)"
+                            if tensor_binds else peak_src),
+            "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak, "peak_source": peak_src,
+                    "algorithmic_bytes_per_row": row_bytes},
+            "tensor": {"achieved_int8_tops": tensor_tops, "measured_int8_peak_tops": int8_peak, "nominal_dense_int8_tops": 4500.0,
+                       "frac_of_measured": tensor_tops / int8_peak if int8_peak > 0 else None,
+                       "mma_shape_per_128_rows": f"M=128 N={p_pad} K={k_pad}",
+                       "per_row_bounds_ps": {"hbm": t_hbm_row * 1e12, "tensor_int8": t_tensor_row * 1e12}},
+            "launches": dom_launches, "avg_launch_ms": dom_ms / max(dom_launches, 1),
+            "kernel_ms_share_of_job": {k_: v[0] / job_ms for k_, v in kt.items() if v[1]},
+            "kernels": {k_: {"ms_total": v[0], "launches": v[1], "rows": v[2]} for k_, v in kt.items() if v[1]},
+            "note": (f"achieved = algorithmic work of the dominant kernel's launches / their CUDA-event time on the launching stream; HBM: "
+                     f"{row_bytes} B/row; tensor: 2 x K_pad x P_pad int8 ops/row.  At P={p} the int8 tensor pipe binds the scan "
+                     f"(SURVEY 7 hard part 2), so frac is against the live-measured int8 peak; the hbm block gives the GB/s view"),
+        }
         line = {
             "metric": "k-mers scored/sec", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 lane sums in reference order + f64 epilogue (int8 tensor filter when enabled)",
+            "ms_per_step": job_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 lane sums in reference order + f64 epilogue (int8 tensor filter in front)",
             "data": "synthetic",
             "config": {
-                "workload": f"BASELINE configs[1] shape: {n} samples x {p} phenotypes (1 + {p - 1} permutations), best K={args.kbest}, "
-                            f"maf {MAF}/mac {MAC}; step = one {R}-row batch ({R * row_bytes / 1e6:.0f} MB, > 126 MB L2) per GPU through the "
-                            f"associate loop; every step scans new rows, heaps carry over (full table = {2.3e9 / R:.0f} such steps streamed)",
-                "scan_position": f"timed steps cover rows [{(prefill_steps + W) * R * world}, {(prefill_steps + W + K) * R * world}) of the job: "
-                                 f"{prefill_steps * R} rows per GPU were scanned untimed first ({prefill_s:.1f} s) so that heap thresholds "
-                                 f"are those of the bulk of the 2.3e9-row scan; --prefill-rows 0 times the cold start instead",
-                "rows_per_step_per_gpu": R, "row_bytes": row_bytes, "l2": "inputs larger than L2, each step reads a different batch",
-                "scan_engine": args.scan_engine, "parallelism": f"k-mer-block shards x{world}, no data-path collective",
-                "hits_replayed_per_step": (stats1["hits_replayed"] - stats0["hits_replayed"]) / K,
-                "threshold_rounds_per_step": (stats1["rounds"] - stats0["rounds"]) / K,
-                "filter_listed_rows_per_step": kt["scan_refine"][2] / K,
-                "host_ms_per_step": {k_: (hostms1[k_] - hostms0[k_]) / K for k_ in hostms1},
-                "rows_per_step_by_engine": {"exact": kt["scan_exact"][2] / K, "tensor_filter": kt["scan_filter"][2] / K},
+                "workload": (f"BASELINE configs[1]: {J} rows x {n} samples x {p} phenotypes (1 + {p - 1} permutations) per GPU from EMPTY heaps, "
+                             f"best K={args.kbest}, maf {MAF}/mac {MAC}; whole job = {K} steps of {R} rows ({R * row_bytes / 1e9:.1f} GB each, > 126 MB L2), "
+                             f"cold phase, device heaps and (N>1) shard merge inside the timed region"),
+                "segments": (f"table {J * row_bytes / 1e9:.0f} GB per GPU > HBM: {len(seg_ms)} segments of <= {seg_steps} HBM-resident steps; the timed "
+                             f"region is the sum of the segments (generation between them untimed), heaps carry over"),
+                "rows_per_gpu": J, "rows_per_step_per_gpu": R, "row_bytes": row_bytes,
+                "l2": "inputs larger than L2, every step reads a different batch",
+                "scan_engine": args.scan_engine,
+                "parallelism": (f"k-mer-block shards x{world} (weak: {J} rows per GPU), no data-path collective in the scan; ranks > 0 warm-start from a "
+                                f"{args.prefix_rows}-row shared prefix; logs all-gathered and replayed on rank 0 (exact merge)"),
+                "selection": "device-resident BestAssociationsHeap set (kg_select_*): no host in the scan loop",
             },
-            "roofline": {
-                "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "tensor": {"achieved_int8_tops": tensor_tops, "nominal_dense_int8_tops": 4500.0, "frac_of_nominal": tensor_tops / 4500.0,
-                           "note": f"filter MMA shape per 128-row block: M=128, N={p_pad}, K={n_pad_cols}; at P={p} the int8 tensor pipe, not HBM, is "
-                                   f"the binding roofline of the scan (SURVEY 7, hard part 2)"},
-                "launches": dom_launches, "avg_launch_ms": dom_ms / max(dom_launches, 1),
-                "kernel_ms_share_of_step": {k_: v[0] / ms_dev for k_, v in kt.items() if v[1]},
-                "kernels": {k_: {"ms_per_launch": v[0] / v[1], "launches": v[1], "rows_per_launch": v[2] / v[1]} for k_, v in kt.items() if v[1]},
-                "note": (f"achieved = {row_bytes} algorithmic B/row x rows of the launch / CUDA-event time of the launch; the exact fp32-order "
-                         f"kernel (scan_exact / scan_refine) is bound by the FP32 add pipe ({t_fp32_row * 1e9:.2f} ns/row at P={p}), not by HBM"),
-            },
-            "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": R * row_bytes + (io3[0] - io2[0]) // K,
-                    "d2h_bytes_per_step": (io3[1] - io2[1]) // K, "ms_per_step": ms_e2e / K,
-                    "path": "pinned host rows -> kgh_session_associate (C ABI kg_scan_submit/kg_scan_fetch) -> host heaps"},
+            "timed_region_s": job_ms * 1e-3,
+            "job": {"rows": rows_total, "seconds": job_ms * 1e-3, "rows_applied_rank0": status_rows[0], "rows_kept_rank0": status_rows[1],
+                    "segment_ms": [round(v, 3) for v in seg_ms], "step_ms": [round(v, 3) for v in step_ms], "prefix_ms": prefix_ms,
+                    "merge_ms": merge_ms, "log_entries": log_entries, "selection": sel_stats, "heap_digest": f"{job_digest:016x}",
+                    "threshold_phenotype0": float(thr_end[0])},
+            "steady_state": {"value": R * len(steady) * world / (sum(steady) * 1e-3) if steady else None, "unit": "k-mers/s",
+                             "note": "secondary: the second half of the job's steps only (rank 0's device time)"},
+            "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": Re * row_bytes, "d2h_bytes_per_step": 128,
+                    "ms_per_step": ms_e2e / K, "rows_per_step_per_gpu": Re,
+                    "path": "pinned host rows -> kg_scan_submit (C ABI, H2D sub-tiles under the kernels) -> device heaps -> kg_select_sync per step"},
             "gpu_launches": launches_timed,
             "clocks": sampler.summary(),
+            "parity": parity,
             "kinship": kin,
-            "cold_start": cold,
         }
         if merge_ms is not None:
             line["merge_ms"] = merge_ms
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         emit(line)
-    sess.close()
+    ctx.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def parity_block(args, kg, torch, dist, ctx, rank, world, local, n, p, y, mc, stride, stream):
+    """Bench-scale parity (untimed, rank 0): (1) one full 2^23-row tile at the job's final thresholds, tensor filter
+    engine vs exact engine -> identical heap digests; (2) the shard protocol (prefix + log + replay) vs one sequential scan."""
+    out = {"engine_full_tile": None, "shard_merge": None}
+    if rank != 0 or args.no_parity:
+        return out
+    T = args.parity_tile_rows
+    buf = torch.empty(T * stride, dtype=torch.int64, device="cuda")
+    first = (1 << 38) + 12345
+    ctx.synth_rows_device(SEED_TABLE, first, T, buf.data_ptr())
+    state = torch.empty(ctx.select_state_len(), dtype=torch.int64, device="cuda")
+    ctx.select_export(dev_ptr=state.data_ptr())
+    applied, kept = ctx.select_sync()
+    digs, kepts = [], []
+    for engine in (2, 1):
+        c2 = kg.Context.identity(n, device=local, stream=stream.cuda_stream)
+        c2.set_option(kg.OPT_SCAN_ENGINE, engine)
+        c2.set_phenotypes(y, mc)
+        c2.select_begin(args.kbest)
+        c2.select_import(state.data_ptr(), applied, kept)
+        c2.scan_submit(buf.data_ptr(), T, first)
+        a2, k2 = c2.select_sync()
+        digs.append(c2.select_digest())
+        kepts.append((a2, k2))
+        c2.close()
+    out["engine_full_tile"] = {"ok": digs[0] == digs[1] and kepts[0] == kepts[1], "rows": T, "digest_filter": f"{digs[0]:016x}",
+                               "digest_exact": f"{digs[1]:016x}", "at_rows_scanned": applied}
+    # (2) two shards on this GPU with the bench's multi-GPU protocol vs the sequential scan of the same rows
+    S_rows, pre = args.parity_shard_rows, args.parity_shard_rows // 8
+    shards = max(2, world)
+    seq = kg.Context.identity(n, device=local, stream=stream.cuda_stream)
+    seq.set_phenotypes(y, mc)
+    seq.select_begin(args.kbest)
+    tiles = []
+    for r in range(shards):
+        b = torch.empty(S_rows * stride, dtype=torch.int64, device="cuda")
+        seq.synth_rows_device(SEED_TABLE + 7, r * S_rows, S_rows, b.data_ptr())
+        tiles.append(b)
+        seq.scan_submit(b.data_ptr(), S_rows, r * S_rows)
+    a_seq, k_seq = seq.select_sync()
+    d_seq = seq.select_digest()
+    seq.close()
+    s0 = kg.Context.identity(n, device=local, stream=stream.cuda_stream)
+    s0.set_phenotypes(y, mc)
+    s0.select_begin(args.kbest)
+    s0.scan_submit(tiles[0].data_ptr(), S_rows, 0)
+    for r in range(1, shards):
+        sr = kg.Context.identity(n, device=local, stream=stream.cuda_stream)
+        sr.set_phenotypes(y, mc)
+        sr.select_begin(args.kbest, kg.SELECT_LOG)
+        sr.scan_submit(tiles[0].data_ptr(), pre, 0)
+        sr.select_log_reset()
+        sr.scan_submit(tiles[r].data_ptr(), S_rows, r * S_rows)
+        a_r, k_r = sr.select_sync()
+        off, ent = sr.select_log()
+        s0.select_replay(ent, off, S_rows, k_r)
+        sr.close()
+    a_m, k_m = s0.select_sync()
+    d_m = s0.select_digest()
+    s0.close()
+    out["shard_merge"] = {"ok": d_m == d_seq and (a_m, k_m) == (a_seq, k_seq), "shards": shards, "rows_per_shard": S_rows,
+                          "digest_merged": f"{d_m:016x}", "digest_sequential": f"{d_seq:016x}"}
+    return out
 
 
 def kinship_leg(args, kg, torch, dist, rank, world, local, n, stride, row_bytes):
@@ -596,7 +667,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rows-per-step", type=int, default=1 << 23)
+    ap.add_argument("--job-rows", type=int, default=2_300_000_000, help="rows per GPU of the timed job (config 2: 2.3e9)")
+    ap.add_argument("--hbm-fraction", type=float, default=0.72, help="share of the free HBM the resident batch ring may use")
+    ap.add_argument("--prefix-rows", type=int, default=1 << 23, help="N > 1: rows of the shared prefix ranks > 0 warm-start from")
+    ap.add_argument("--e2e-rows", type=int, default=1 << 23, help="rows per step of the e2e (pinned host memory) leg")
+    ap.add_argument("--parity-tile-rows", type=int, default=1 << 23)
+    ap.add_argument("--parity-shard-rows", type=int, default=1 << 22)
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--samples", type=int, default=N_SAMPLES)
     ap.add_argument("--phenos", type=int, default=N_PHENO)
     ap.add_argument("--kbest", type=int, default=K_BEST)
@@ -604,8 +681,6 @@ def main():
     ap.add_argument("--kinship-engine", type=int, default=0)
     ap.add_argument("--kinship-rows", type=int, default=1 << 20)
     ap.add_argument("--e2e-buffers", type=int, default=3)
-    ap.add_argument("--prefill-rows", type=int, default=1 << 28, help="rows per GPU scanned untimed before the warm-up steps")
-    ap.add_argument("--cold-steps", type=int, default=10, help="steps of the cold-start leg (0 = skip)")
     ap.add_argument("--cpu-rows", type=int, default=400000, help="rows of the cpu_baseline sample")
     ap.add_argument("--ref-rows", type=int, default=200000, help="rows per step of --impl reference")
     ap.add_argument("--warmup-ref", type=int, default=1)

@@ -193,6 +193,9 @@ kg_status kg_select_export(kg_ctx *ctx, uint64_t *state);
 kg_status kg_select_import(kg_ctx *ctx, const uint64_t *state, uint64_t rows_applied, uint64_t rows_kept);
 /* Order-sensitive 64-bit digest of all heaps (layout order, k-mer + score bits + row): equal digests <=> equal heaps. */
 kg_status kg_select_digest(kg_ctx *ctx, uint64_t *digest);
+/* Counters since kg_select_begin (any pointer may be NULL): rounds applied, candidates replayed, candidates the heaps
+ * admitted (sum of cnt_push over the phenotypes), rebuilds of the tensor filter's column order.  Waits for the device. */
+kg_status kg_select_stats(kg_ctx *ctx, uint64_t *rounds, uint64_t *candidates, uint64_t *admitted, uint64_t *reorders);
 /* Current thresholds (lowest kept score, -1 while a heap is not full), host output [n_pheno]. */
 kg_status kg_select_thresholds(kg_ctx *ctx, double *thr);
 /* Admission log (KG_SELECT_LOG).  kg_select_log_reset drops what was logged so far and zeroes the kept-row total (call
@@ -253,6 +256,10 @@ uint64_t kg_launch_count(const kg_ctx *ctx);
  * kg_kernel_time_reset.  Waits for the stream.  Any output pointer may be NULL. */
 kg_status kg_kernel_time(kg_ctx *ctx, int kernel_class, double *ms_total, uint64_t *launches, uint64_t *rows);
 kg_status kg_kernel_time_reset(kg_ctx *ctx);
+
+/* Measured int8 tensor-pipe peak of the context's GPU in TOP/s: back-to-back tcgen05.mma.kind::i8 (M 128, N 256, K 32)
+ * on every SM, timed with CUDA events (the roofline denominator bench.py reports for the tcgen05 kernels). */
+kg_status kg_probe_int8_peak(kg_ctx *ctx, double *tops);
 
 #ifdef __cplusplus
 }

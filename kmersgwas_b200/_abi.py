@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "kg_launch_count", "kg_kernel_time", "kg_kernel_time_reset", "kg_scan_filter_sums", "kg_mac_filter",
     "kg_select_begin", "kg_select_end", "kg_select_sync", "kg_select_state_len", "kg_select_export", "kg_select_import",
     "kg_select_digest", "kg_select_thresholds", "kg_select_log_reset", "kg_select_log_counts", "kg_select_log_export",
-    "kg_select_replay", "kg_select_set_floor", "kg_select_export_scores", "kg_select_kmax",
+    "kg_select_replay", "kg_select_set_floor", "kg_select_export_scores", "kg_select_kmax", "kg_probe_int8_peak", "kg_select_stats",
 ]
 
 
@@ -110,6 +110,8 @@ def load():
     lib.kg_select_replay.argtypes = [vp, vp, vp, u64, u64]
     lib.kg_select_set_floor.argtypes = [vp, vp, C.c_uint32]
     lib.kg_select_export_scores.argtypes = [vp, u64, vp]
+    lib.kg_probe_int8_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.kg_select_stats.argtypes = [vp, u64p, u64p, u64p, u64p]
     lib.kg_select_kmax.argtypes = [vp]
     lib.kg_select_kmax.restype = C.c_uint32
     _lib = lib
@@ -297,6 +299,11 @@ class Context:
             out.append((ent[p, :n, 0].copy(), ent[p, :n, 1].copy().view(np.float64), ent[p, :n, 2].copy()))
         return out
 
+    def select_stats(self) -> dict:
+        a, b, c_, d = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._chk(self._lib.kg_select_stats(self._h, C.byref(a), C.byref(b), C.byref(c_), C.byref(d)))
+        return dict(rounds=int(a.value), candidates=int(b.value), admitted=int(c_.value), reorders=int(d.value))
+
     def select_digest(self) -> int:
         d = C.c_uint64(0)
         self._chk(self._lib.kg_select_digest(self._h, C.byref(d)))
@@ -358,6 +365,11 @@ class Context:
         p = ibs.ctypes.data_as(C.POINTER(C.c_uint64)) if want_matrix else None
         self._chk(self._lib.kg_kinship_fetch(self._h, p, C.byref(m)))
         return ibs, int(m.value)
+
+    def probe_int8_peak(self) -> float:
+        t = C.c_double(0)
+        self._chk(self._lib.kg_probe_int8_peak(self._h, C.byref(t)))
+        return float(t.value)
 
     # ---- synthetic
     def synth_rows_device(self, seed: int, first_row: int, n_rows: int, rows_dev: int):

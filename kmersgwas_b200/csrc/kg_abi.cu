@@ -10,6 +10,7 @@
 
 #include "kg_common.cuh"
 #include "kg_kinship_popc.cuh"
+#include "kg_probe.cuh"
 #include "kg_scan_exact.cuh"
 #include "kg_synth.cuh"
 #include "kg_tc_state.cuh"
@@ -1129,5 +1130,33 @@ extern "C" kg_status kg_synth_rows_device(kg_ctx *c, uint64_t seed, uint64_t fir
 	const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->sm_count * 32);
 	kg_synth_rows_kernel<<<std::max(grid, 1u), 256, 0, c->stream>>>(seed, first_row, n_rows, c->w_file, last_mask, rows_dev);
 	KG_LAUNCH_CHECK(c);
+	return KG_OK;
+}
+
+// ------------------------------------------------------------------------------------- probes
+extern "C" kg_status kg_probe_int8_peak(kg_ctx *c, double *tops) {
+	if (!c || !tops) return KG_ERR_INVALID;
+	KG_CUDA(c, cudaSetDevice(c->device));
+	KG_CUDA(c, cudaFuncSetAttribute(kg_probe_umma_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KG_PROBE_SMEM));
+	cudaEvent_t e0, e1;
+	KG_CUDA(c, cudaEventCreate(&e0));
+	KG_CUDA(c, cudaEventCreate(&e1));
+	const int n_mma = 16384;
+	double best = 0.0;
+	for (int rep = 0; rep < 4; rep++) {   // rep 0 = warm-up
+		cudaEventRecord(e0, c->stream);
+		kg_probe_umma_i8_kernel<<<c->sm_count, 128, KG_PROBE_SMEM, c->stream>>>(n_mma);
+		cudaEventRecord(e1, c->stream);
+		c->launches++;
+		cudaError_t e = cudaStreamSynchronize(c->stream);
+		if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); KG_CUDA(c, e); }
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, e0, e1);
+		const double ops = 2.0 * 128 * 256 * 32 * (double)n_mma * c->sm_count;
+		if (rep > 0 && ms > 0.f) best = std::max(best, ops / (ms * 1e-3) / 1e12);
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	*tops = best;
 	return KG_OK;
 }

@@ -13,6 +13,8 @@
 // per-phenotype candidate segments; thresholds, the tensor filter's bound constants and its column order are
 // recomputed on the device after every round (kg_filter_retune_kernel), so the host is not in the scan loop at all.
 #pragma once
+#include <string.h>
+
 #include "kg_common.cuh"
 
 struct KgCand {      // one candidate association: what add_kmers_to_heap hands to add_association (:281-283)
@@ -68,44 +70,93 @@ struct KgSelectParams {
 	uint32_t log_cap;
 };
 
+__host__ __device__ __forceinline__ long long kg_dbits(double x) {
+#ifdef __CUDA_ARCH__
+	return __double_as_longlong(x);
+#else
+	long long r;
+	memcpy(&r, &x, 8);
+	return r;
+#endif
+}
+#ifdef KG_SEL_INTCMP
+#define KG_GT(a, b) (kg_dbits(a) > kg_dbits(b))
+#else
+#define KG_GT(a, b) ((a) > (b))
+#endif
 // ---- libstdc++ heap algorithms on (score, slot) pairs; cmp_second(l, r) = l.score > r.score (min-heap) ------------
 // hs has its element 1 on a 16-byte boundary, so the two children 2h+1, 2h+2 of a node are one 128-bit load.
 __host__ __device__ __forceinline__ void kg_heap_push_up(double *hs, uint32_t *hl, int32_t hole, double v, uint32_t vs) {
-	// __push_heap(first, hole, top = 0, value): while (hole > top && comp(first[parent], value)) move the parent down
+	// __push_heap(first, hole, top = 0, value): while (hole > top && comp(first[parent], value)) move the parent down.
+	// A newly admitted score is just above the heap's minimum, so it climbs almost to the root: the ancestors of a
+	// position are known in advance, and four levels of them are loaded per shared-memory round trip (nothing written
+	// in between touches an ancestor).
 	while (hole > 0) {
-		const int32_t parent = (hole - 1) >> 1;
-		const double ps = hs[parent];
-		if (!(ps > v)) break;
-		hs[hole] = ps;
-		hl[hole] = hl[parent];
-		hole = parent;
+		const int32_t p1 = (hole - 1) >> 1;
+		const int32_t p2 = p1 > 0 ? (p1 - 1) >> 1 : 0;
+		const int32_t p3 = p2 > 0 ? (p2 - 1) >> 1 : 0;
+		const int32_t p4 = p3 > 0 ? (p3 - 1) >> 1 : 0;
+		const double s1 = hs[p1], s2 = hs[p2], s3 = hs[p3], s4 = hs[p4];
+		const uint32_t l1 = hl[p1], l2 = hl[p2], l3 = hl[p3], l4 = hl[p4];
+		if (!KG_GT(s1, v)) break;
+		hs[hole] = s1; hl[hole] = l1; hole = p1;
+		if (hole == 0 || !KG_GT(s2, v)) break;
+		hs[hole] = s2; hl[hole] = l2; hole = p2;
+		if (hole == 0 || !KG_GT(s3, v)) break;
+		hs[hole] = s3; hl[hole] = l3; hole = p3;
+		if (hole == 0 || !KG_GT(s4, v)) break;
+		hs[hole] = s4; hl[hole] = l4; hole = p4;
 	}
 	hs[hole] = v;
 	hl[hole] = vs;
 }
 
 // pop_heap + pop_back on a heap of `len` entries, then push_back + push_heap of (v_new, slot_new): the reference's
-// m_best_kmers.pop(); m_best_kmers.push(new_res) (:53-54).  Returns nothing; len is unchanged.
-__host__ __device__ __forceinline__ void kg_heap_replace_top(double *hs, uint32_t *hl, int32_t len, double v_new, uint32_t slot_new) {
+// m_best_kmers.pop(); m_best_kmers.push(new_res) (:53-54).  len is unchanged.
+//
+// One thread runs this, so the cost is the chain of dependent shared-memory round trips.  __adjust_heap always walks the
+// hole down to a leaf choosing the smaller child (ties: the right one), independent of the value that is re-inserted, so
+// TWO levels are resolved per round trip: the children (2h+1, 2h+2) and the grandchildren (4h+3 .. 4h+6) of the hole
+// are contiguous, and with &hs[1] / &hs[3] on 16-byte and &hl[1] / &hl[3] on 8- / 16-byte boundaries they are five
+// vector loads issued back to back (scores and slots together, so the slot moves never wait on their own loads).
+// `cap` = entries that may be READ (>= len; reads past the heap's end are clamped to it and their values unused).
+__host__ __device__ __forceinline__ void kg_heap_replace_top(double *hs, uint32_t *hl, int32_t len, int32_t cap, double v_new, uint32_t slot_new) {
 	if (len > 1) {
 		// __pop_heap: value = last element, *last = *first (discarded by pop_back), __adjust_heap(first, 0, len - 1, value)
 		const double v = hs[len - 1];
 		const uint32_t vs = hl[len - 1];
 		const int32_t n = len - 1;
-		int32_t hole = 0, child = 0;
-		while (child < (n - 1) / 2) {
-			child = 2 * (child + 1);
-			const double2 c2 = *reinterpret_cast<const double2 *>(hs + child - 1);   // (left, right)
-			if (c2.y > c2.x) child--;            // comp(first[child], first[child - 1]): the right one is larger -> take the left
-			hs[hole] = (child & 1) ? c2.x : c2.y;
-			hl[hole] = hl[child];
-			hole = child;
+		const int32_t lim = (n - 1) / 2;      // nodes below lim have both children inside [0, n)
+		const int32_t g_max = cap - 4;        // last index a 4-entry grandchild load may start at (cap >= 8, odd start kept below)
+		int32_t hole = 0;
+		while (hole < lim) {
+			const int32_t l = 2 * hole + 1;                           // children l, l + 1
+			int32_t g = 2 * l + 1;                                    // grandchildren g .. g + 3 (g = 3 mod 4)
+			g = g > g_max ? 3 : g;                                    // out of range: any valid aligned index (values unused)
+			const double2 s12 = *reinterpret_cast<const double2 *>(hs + l);
+			const uint2 l12 = *reinterpret_cast<const uint2 *>(hl + l);
+			const double2 s34 = *reinterpret_cast<const double2 *>(hs + g);
+			const double2 s56 = *reinterpret_cast<const double2 *>(hs + g + 2);
+			const uint4 l36 = *reinterpret_cast<const uint4 *>(hl + g);
+			// comp(first[right], first[left]) = right.score > left.score: take the left child, else (ties too) the right one
+			const bool left = KG_GT(s12.y, s12.x);
+			const int32_t c = left ? l : l + 1;
+			hs[hole] = left ? s12.x : s12.y;
+			hl[hole] = left ? l12.x : l12.y;
+			hole = c;
+			if (!(c < lim)) break;
+			const double a = left ? s34.x : s56.x, b = left ? s34.y : s56.y;
+			const uint32_t la = left ? l36.x : l36.z, lb = left ? l36.y : l36.w;
+			const bool left2 = KG_GT(b, a);
+			hs[c] = left2 ? a : b;
+			hl[c] = left2 ? la : lb;
+			hole = 2 * c + (left2 ? 1 : 2);
 		}
-		if ((n & 1) == 0 && child == (n - 2) / 2) {
-			child = 2 * (child + 1);
-			hs[hole] = hs[child - 1];
-			hl[hole] = hl[child - 1];
-			hole = child - 1;
+		if ((n & 1) == 0 && hole == (n - 2) / 2) {   // the last inner node has a left child only
+			const int32_t ch = 2 * hole + 1;
+			hs[hole] = hs[ch];
+			hl[hole] = hl[ch];
+			hole = ch;
 		}
 		kg_heap_push_up(hs, hl, hole, v, vs);
 	}
@@ -128,11 +179,15 @@ __device__ __forceinline__ void kg_bitonic_sort_u64(unsigned long long *buf, uin
 		}
 }
 
-// shared memory: [8 B pad][kmax_pad doubles][kmax_pad u32][scratch]; scratch = max(sort_smem * 8, KG_SEL_STAGE * 24)
-__host__ __device__ inline uint32_t kg_select_kmax_pad(uint32_t kmax) { return (kmax + 3u) & ~3u; }
+// shared memory: scores at byte 8 (kmax_pad doubles: &hs[1] and &hs[3] are 16-byte aligned), slots at byte
+// 20 + 8 kmax_pad (= 4 mod 16: &hl[1] is 8-byte and &hl[3] 16-byte aligned), then the scratch =
+// max(sort_smem * 8, KG_SEL_STAGE * 24).  kmax_pad = kmax rounded up to a multiple of 4, + 8 entries of read slack.
+__host__ __device__ inline uint32_t kg_select_kmax_pad(uint32_t kmax) { return ((kmax + 3u) & ~3u) + 8u; }
+__host__ __device__ inline size_t kg_select_hl_offset(uint32_t kmax) { return 20 + (size_t)kg_select_kmax_pad(kmax) * 8; }
+__host__ __device__ inline size_t kg_select_scratch_offset(uint32_t kmax) { return (kg_select_hl_offset(kmax) + (size_t)kg_select_kmax_pad(kmax) * 4 + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t kg_select_smem_bytes(uint32_t kmax, uint32_t sort_smem) {
 	const size_t scratch = (size_t)sort_smem * 8 > (size_t)KG_SEL_STAGE * sizeof(KgCand) ? (size_t)sort_smem * 8 : (size_t)KG_SEL_STAGE * sizeof(KgCand);
-	return 16 + (size_t)kg_select_kmax_pad(kmax) * 12 + 16 + scratch;
+	return kg_select_scratch_offset(kmax) + scratch;
 }
 
 // grid = P, block = KG_SEL_THREADS.  PRESORTED: the candidates are already in row order (merge of shard logs).
@@ -141,11 +196,10 @@ __global__ void __launch_bounds__(KG_SEL_THREADS) kg_select_replay_kernel(const 
 	extern __shared__ __align__(16) unsigned char kg_sel_smem[];
 	const uint32_t p = blockIdx.x;
 	if (!PRESORTED && prm.status[KG_SEL_ST_ROUND_OK] == 0ull) return;
-	const uint32_t kpad = kg_select_kmax_pad(prm.kmax);
+	const int32_t kpad = (int32_t)kg_select_kmax_pad(prm.kmax);
 	double *hs = reinterpret_cast<double *>(kg_sel_smem + 8);                       // &hs[1] is 16-byte aligned
-	uint32_t *hl = reinterpret_cast<uint32_t *>(kg_sel_smem + 16 + (size_t)kpad * 8);
-	unsigned char *scratch = kg_sel_smem + 16 + (size_t)kpad * 12;
-	scratch = reinterpret_cast<unsigned char *>(((uintptr_t)scratch + 15) & ~(uintptr_t)15);
+	uint32_t *hl = reinterpret_cast<uint32_t *>(kg_sel_smem + kg_select_hl_offset(prm.kmax));
+	unsigned char *scratch = kg_sel_smem + kg_select_scratch_offset(prm.kmax);
 
 	uint32_t n;
 	const KgCand *cand;
@@ -193,12 +247,18 @@ __global__ void __launch_bounds__(KG_SEL_THREADS) kg_select_replay_kernel(const 
 	uint32_t n_log = log ? prm.log_count[p] : 0;
 	const double floor_thr = prm.floor_thr ? prm.floor_thr[p] : -1.0;
 	unsigned long long pushes = 0, pops = 0;
+#ifdef KG_SEL_PROFILE
+	long long t_loop = 0, t_rep = 0, t_all0 = clock64();
+#endif
 	for (uint32_t b0 = 0; b0 < n; b0 += KG_SEL_STAGE) {
 		const uint32_t m = min((uint32_t)KG_SEL_STAGE, n - b0);
 		for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
 			stage[i] = cand[(PRESORTED || n == 1) ? b0 + i : order[b0 + i]];
 		__syncthreads();
 		if (threadIdx.x == 0) {
+#ifdef KG_SEL_PROFILE
+			const long long tl0 = clock64();
+#endif
 			for (uint32_t i = 0; i < m; i++) {
 				const double s = stage[i].score;
 				uint32_t slot;
@@ -210,7 +270,13 @@ __global__ void __launch_bounds__(KG_SEL_THREADS) kg_select_replay_kernel(const 
 				} else {
 					if (!(s > hs[0]) || s <= floor_thr) continue;   // :50 strict '>' against lowest_score = top
 					slot = hl[0];
-					kg_heap_replace_top(hs, hl, (int32_t)size, s, slot);
+#ifdef KG_SEL_PROFILE
+					const long long tr0 = clock64();
+#endif
+					kg_heap_replace_top(hs, hl, (int32_t)size, kpad, s, slot);
+#ifdef KG_SEL_PROFILE
+					t_rep += clock64() - tr0;
+#endif
 					pops++;
 				}
 				pushes++;
@@ -221,9 +287,20 @@ __global__ void __launch_bounds__(KG_SEL_THREADS) kg_select_replay_kernel(const 
 					n_log++;
 				}
 			}
+#ifdef KG_SEL_PROFILE
+			t_loop += clock64() - tl0;
+#endif
 		}
 		__syncthreads();
 	}
+#ifdef KG_SEL_PROFILE
+	if (threadIdx.x == 0 && p == 0) {
+		atomicAdd(prm.status + 10, (unsigned long long)t_loop);
+		atomicAdd(prm.status + 11, (unsigned long long)t_rep);
+		atomicAdd(prm.status + 12, (unsigned long long)(clock64() - t_all0));
+		atomicAdd(prm.status + 13, pops);
+	}
+#endif
 
 	// ---- heap: shared -> global; threshold for the scan kernels (only thread 0 knows the new size)
 	__shared__ uint32_t s_size;

@@ -276,6 +276,30 @@ extern "C" kg_status kg_select_sync(kg_ctx *c, uint64_t *rows_applied, uint64_t 
 	return KG_OK;
 }
 
+extern "C" kg_status kg_select_stats(kg_ctx *c, uint64_t *rounds, uint64_t *candidates, uint64_t *admitted, uint64_t *reorders) {
+	if (!c) return KG_ERR_INVALID;
+	if (!c->sel.active) KG_FAIL(c, KG_ERR_STATE, "kg_select_stats: call kg_select_begin first");
+	KG_CUDA(c, cudaSetDevice(c->device));
+	kg_status st = kg_sel_read_status(c);
+	if (st != KG_OK) return st;
+	KgSelState &s = c->sel;
+	if (rounds) *rounds = s.h_status[KG_SEL_ST_ROUNDS];
+	if (candidates) *candidates = s.h_status[KG_SEL_ST_CANDS];
+	if (reorders) *reorders = s.h_status[KG_SEL_ST_REORDERS];
+#ifdef KG_SEL_PROFILE
+	fprintf(stderr, "[kg select profile, phenotype 0] cycles: replay loop %llu, replace_top %llu, kernel after sort %llu; pops %llu\n",
+	        s.h_status[10], s.h_status[11], s.h_status[12], s.h_status[13]);
+#endif
+	if (admitted) {
+		std::vector<unsigned long long> hs(2 * (size_t)s.n_pheno);
+		KG_CUDA(c, cudaMemcpy(hs.data(), s.d_hstat, hs.size() * 8, cudaMemcpyDeviceToHost));
+		unsigned long long t = 0;
+		for (uint32_t p = 0; p < s.n_pheno; p++) t += hs[2 * p];
+		*admitted = t;
+	}
+	return KG_OK;
+}
+
 extern "C" size_t kg_select_state_len(const kg_ctx *c) { return c && c->sel.active ? kg_select_state_words(c->sel.n_pheno, c->sel.kmax) : 0; }
 extern "C" uint32_t kg_select_kmax(const kg_ctx *c) { return c && c->sel.active ? c->sel.kmax : 0; }
 

@@ -145,3 +145,16 @@ def test_bench_reference_arm_json_contract(tmp_path):
     assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_device_heap_algorithms_match_oracle_heap_on_host(tmp_path):
+    """kg_select.cuh's push_heap / pop_heap restatement (the code thread 0 of the replay kernel runs) is __host__
+    __device__: compile it for the host and replay random candidate streams with many ties against oracle.c's heap."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = tmp_path / "heap_host_check"
+    subprocess.check_call([nvcc, "-O1", "-o", str(exe), str(ROOT / "tests" / "heap_host_check.cu"), str(ROOT / "oracle" / "oracle.c"),
+                           "-Xcompiler", "-w"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout
