@@ -227,13 +227,36 @@ uint32_t kg_select_kmax(const kg_ctx *ctx);
  * with NCCL between kg_kinship_submit and kg_kinship_fetch); NULL = context-owned.
  * The buffer is zeroed. Layout: [n_used*n_used] Gram counts G[i][j] = #kept rows with both bits
  * set (lower triangle j<=i; the diagonal G[i][i] is the column count c[i]), then [1] kept rows M.
- * Every entry is a plain sum over rows, so shards add: all-reduce(sum) the whole buffer. */
+ * Every entry is a plain sum over rows, so shards add: all-reduce(sum) the whole buffer (kg_kinship_allreduce).
+ * A caller-owned buffer is current after kg_sync, kg_kinship_allreduce or kg_kinship_fetch (the tensor engine folds
+ * its per-tile counts into it lazily). */
 kg_status kg_kinship_begin(kg_ctx *ctx, uint64_t min_count, uint64_t *accum_dev);
 size_t kg_kinship_accum_len(const kg_ctx *ctx);
 kg_status kg_kinship_submit(kg_ctx *ctx, const uint64_t *rows, uint64_t n_rows);
 /* Wait; convert the (possibly all-reduced) accumulator into the reference's matrix:
  * ibs[i*n_used + j] = M - c[i] - c[j] + 2 G[i][j] for j < i (other entries 0), *kept_rows = M. */
 kg_status kg_kinship_fetch(kg_ctx *ctx, uint64_t *ibs, uint64_t *kept_rows);
+
+/* ---- NCCL all-reduce of the kinship accumulator (the path's only exchange step) ------------------
+ * The accumulator is a plain sum over rows (u64 Gram counts + kept rows), so row shards add exactly.  The library
+ * resolves NCCL at run time (dlopen of libnccl.so.2); it does not link it.
+ *   multi-process (one rank per GPU): rank 0 calls kg_comm_unique_id, ships the 128 bytes to the other ranks by any
+ *     means, every rank calls kg_comm_init_rank; then kg_kinship_allreduce between kg_kinship_submit and
+ *     kg_kinship_fetch (stream-ordered, asynchronous);
+ *   single process, several contexts: kg_comm_init_all once, then kg_kinship_allreduce_all (one NCCL group call).
+ * After the all-reduce every context's kg_kinship_fetch returns the matrix of the whole table. */
+kg_status kg_comm_unique_id(void *id128);
+kg_status kg_comm_init_rank(kg_ctx *ctx, const void *id128, int n_ranks, int rank);
+kg_status kg_comm_init_all(kg_ctx *const *ctxs, int n);
+kg_status kg_kinship_allreduce(kg_ctx *ctx);
+kg_status kg_kinship_allreduce_all(kg_ctx *const *ctxs, int n);
+
+/* ---- stream tickets ---------------------------------------------------------------------------
+ * kg_stream_mark returns a ticket for "everything submitted to this context so far" (copies and kernels);
+ * kg_stream_wait blocks until that point has passed.  For callers that recycle their host input buffers (the tile
+ * reader of MultipleKmersDataBases keeps three and waits for the ticket of the batch that used a buffer last). */
+kg_status kg_stream_mark(kg_ctx *ctx, uint64_t *ticket);
+kg_status kg_stream_wait(kg_ctx *ctx, uint64_t ticket);
 
 /* ---- pinned host memory ----------------------------------------------------------------------
  * Page-locked buffers for the host-side tile reader (so that it needs no CUDA headers); tiles handed

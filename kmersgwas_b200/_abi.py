@@ -33,6 +33,8 @@ ABI_SYMBOLS = [
     "kg_select_begin", "kg_select_end", "kg_select_sync", "kg_select_state_len", "kg_select_export", "kg_select_import",
     "kg_select_digest", "kg_select_thresholds", "kg_select_log_reset", "kg_select_log_counts", "kg_select_log_export",
     "kg_select_replay", "kg_select_set_floor", "kg_select_export_scores", "kg_select_kmax", "kg_probe_int8_peak", "kg_select_stats",
+    "kg_comm_unique_id", "kg_comm_init_rank", "kg_comm_init_all", "kg_kinship_allreduce", "kg_kinship_allreduce_all",
+    "kg_stream_mark", "kg_stream_wait",
 ]
 
 
@@ -112,10 +114,25 @@ def load():
     lib.kg_select_export_scores.argtypes = [vp, u64, vp]
     lib.kg_probe_int8_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.kg_select_stats.argtypes = [vp, u64p, u64p, u64p, u64p]
+    lib.kg_comm_unique_id.argtypes = [vp]
+    lib.kg_comm_init_rank.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.kg_comm_init_all.argtypes = [C.POINTER(vp), C.c_int]
+    lib.kg_kinship_allreduce.argtypes = [vp]
+    lib.kg_kinship_allreduce_all.argtypes = [C.POINTER(vp), C.c_int]
+    lib.kg_stream_mark.argtypes = [vp, u64p]
+    lib.kg_stream_wait.argtypes = [vp, u64]
     lib.kg_select_kmax.argtypes = [vp]
     lib.kg_select_kmax.restype = C.c_uint32
     _lib = lib
     return lib
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL unique id (rank 0 creates it and ships it to the other ranks)."""
+    buf = C.create_string_buffer(128)
+    if load().kg_comm_unique_id(buf) != KG_OK:
+        raise KgError(-1, load().kg_last_error(None).decode())
+    return buf.raw
 
 
 def kernel_times(handle) -> dict:
@@ -365,6 +382,13 @@ class Context:
         p = ibs.ctypes.data_as(C.POINTER(C.c_uint64)) if want_matrix else None
         self._chk(self._lib.kg_kinship_fetch(self._h, p, C.byref(m)))
         return ibs, int(m.value)
+
+    def kinship_allreduce(self):
+        self._chk(self._lib.kg_kinship_allreduce(self._h))
+
+    def comm_init_rank(self, id128: bytes, n_ranks: int, rank: int):
+        buf = C.create_string_buffer(bytes(id128), 128)
+        self._chk(self._lib.kg_comm_init_rank(self._h, buf, int(n_ranks), int(rank)))
 
     def probe_int8_peak(self) -> float:
         t = C.c_double(0)

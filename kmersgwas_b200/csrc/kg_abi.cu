@@ -102,6 +102,12 @@ struct kg_ctx {
 
 	int scan_engine = 0, kin_engine = 0;
 
+	// stream tickets (kg_stream_mark / kg_stream_wait): events on the copy and compute streams
+	struct Mark { cudaEvent_t copy_ev = nullptr, compute_ev = nullptr; };
+	std::vector<Mark> marks;
+	// NCCL communicator of this context (kg_comm_init_rank / kg_comm_init_all), opaque here
+	void *nccl_comm = nullptr;
+
 	// per-launch device timing (KG_OPT_KERNEL_TIMING)
 	bool timing = false;
 	struct TimedLaunch { cudaEvent_t beg, end; int cls; uint64_t rows; };
@@ -197,6 +203,8 @@ static kg_status release_tile(kg_ctx *c);
 static kg_status memory_view(kg_ctx *c, const uint64_t *dev, uint64_t n_rows, KgRowView *view);
 static kg_status kg_sel_finish_round(kg_ctx *c, uint64_t n_rows, uint64_t first_row_id, bool filter_counters);
 static const uint64_t kHostSubTileRows = 1ull << 20;
+
+static void kg_comm_destroy(kg_ctx *c);
 
 // tensor-core engine (needs kg_ctx and the macros above)
 #include "kg_tc.cuh"
@@ -332,6 +340,8 @@ extern "C" void kg_ctx_destroy(kg_ctx *c) {
 		if (c->slot_ready[i]) cudaEventDestroy(c->slot_ready[i]);
 		if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
 	}
+	for (kg_ctx::Mark &m : c->marks) { if (m.copy_ev) cudaEventDestroy(m.copy_ev); if (m.compute_ev) cudaEventDestroy(m.compute_ev); }
+	kg_comm_destroy(c);
 	for (const kg_ctx::TimedLaunch &t : c->timed_pending) { cudaEventDestroy(t.beg); cudaEventDestroy(t.end); }
 	for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -388,9 +398,43 @@ extern "C" kg_status kg_set_option(kg_ctx *c, int option, int64_t value) {
 extern "C" kg_status kg_sync(kg_ctx *c) {
 	if (!c) return KG_ERR_INVALID;
 	KG_CUDA(c, cudaSetDevice(c->device));
+	if (c->kin_active) {   // a caller-owned kinship accumulator is current after kg_sync
+		kg_status st = kg_tc_kinship_flush(c);
+		if (st != KG_OK) return st;
+	}
 	KG_CUDA(c, cudaStreamSynchronize(c->copy_stream));
 	KG_CUDA(c, cudaStreamSynchronize(c->stream));
 	timing_resolve(c);
+	return KG_OK;
+}
+
+// ---- stream tickets: "everything submitted so far" as a waitable point, for callers that recycle input buffers
+extern "C" kg_status kg_stream_mark(kg_ctx *c, uint64_t *ticket) {
+	if (!c || !ticket) return KG_ERR_INVALID;
+	KG_CUDA(c, cudaSetDevice(c->device));
+	// reuse a completed slot if there is one
+	size_t slot = c->marks.size();
+	for (size_t i = 0; i < c->marks.size(); i++)
+		if (cudaEventQuery(c->marks[i].copy_ev) == cudaSuccess && cudaEventQuery(c->marks[i].compute_ev) == cudaSuccess) { slot = i; break; }
+	cudaGetLastError();
+	if (slot == c->marks.size()) {
+		kg_ctx::Mark m;
+		KG_CUDA(c, cudaEventCreateWithFlags(&m.copy_ev, cudaEventDisableTiming));
+		KG_CUDA(c, cudaEventCreateWithFlags(&m.compute_ev, cudaEventDisableTiming));
+		c->marks.push_back(m);
+	}
+	KG_CUDA(c, cudaEventRecord(c->marks[slot].copy_ev, c->copy_stream));
+	KG_CUDA(c, cudaEventRecord(c->marks[slot].compute_ev, c->stream));
+	*ticket = slot;
+	return KG_OK;
+}
+
+extern "C" kg_status kg_stream_wait(kg_ctx *c, uint64_t ticket) {
+	if (!c) return KG_ERR_INVALID;
+	if (ticket >= c->marks.size()) KG_FAIL(c, KG_ERR_INVALID, "kg_stream_wait: unknown ticket");
+	KG_CUDA(c, cudaSetDevice(c->device));
+	KG_CUDA(c, cudaEventSynchronize(c->marks[ticket].copy_ev));
+	KG_CUDA(c, cudaEventSynchronize(c->marks[ticket].compute_ev));
 	return KG_OK;
 }
 
@@ -1099,6 +1143,10 @@ extern "C" kg_status kg_kinship_fetch(kg_ctx *c, uint64_t *ibs, uint64_t *kept_r
 	if (!c) return KG_ERR_INVALID;
 	if (!c->kin_active) KG_FAIL(c, KG_ERR_STATE, "kg_kinship_fetch: call kg_kinship_begin first");
 	KG_CUDA(c, cudaSetDevice(c->device));
+	{
+		kg_status st = kg_tc_kinship_flush(c);
+		if (st != KG_OK) return st;
+	}
 	KG_CUDA(c, cudaStreamSynchronize(c->stream));
 	const unsigned long long n2 = (unsigned long long)c->n_used * c->n_used;
 	unsigned long long M = 0;
@@ -1130,6 +1178,119 @@ extern "C" kg_status kg_synth_rows_device(kg_ctx *c, uint64_t seed, uint64_t fir
 	const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->sm_count * 32);
 	kg_synth_rows_kernel<<<std::max(grid, 1u), 256, 0, c->stream>>>(seed, first_row, n_rows, c->w_file, last_mask, rows_dev);
 	KG_LAUNCH_CHECK(c);
+	return KG_OK;
+}
+
+// ------------------------------------------------------------------------------------- NCCL (kinship all-reduce)
+// The library does not link NCCL: the symbols are resolved at run time from libnccl.so.2 (the copy the process
+// already has loaded -- e.g. PyTorch's -- or the system one).
+#include <dlfcn.h>
+#include <nccl.h>
+namespace {
+struct KgNccl {
+	void *lib = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	const char *(*GetErrorString)(ncclResult_t) = nullptr;
+	std::string err;
+	bool load() {
+		if (lib) return true;
+		for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+			lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+			if (lib) break;
+		}
+		if (!lib) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+#define KG_NCCL_SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(lib, name)); if (!field) { err = std::string("libnccl lacks ") + name; lib = nullptr; return false; }
+		KG_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+		KG_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+		KG_NCCL_SYM(CommInitAll, "ncclCommInitAll")
+		KG_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+		KG_NCCL_SYM(AllReduce, "ncclAllReduce")
+		KG_NCCL_SYM(GroupStart, "ncclGroupStart")
+		KG_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+		KG_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef KG_NCCL_SYM
+		return true;
+	}
+} g_nccl;
+}  // namespace
+
+#define KG_NCCL(ctx, expr)                                                                         \
+	do {                                                                                           \
+		ncclResult_t r_ = (expr);                                                                  \
+		if (r_ != ncclSuccess) KG_FAIL(ctx, KG_ERR_CUDA, "%s failed: %s", #expr, g_nccl.GetErrorString(r_)); \
+	} while (0)
+
+static void kg_comm_destroy(kg_ctx *c) {
+	if (c->nccl_comm && g_nccl.lib) g_nccl.CommDestroy(static_cast<ncclComm_t>(c->nccl_comm));
+	c->nccl_comm = nullptr;
+}
+
+extern "C" kg_status kg_comm_unique_id(void *id128) {
+	if (!id128) return KG_ERR_INVALID;
+	if (!g_nccl.load()) { g_create_error = g_nccl.err; return KG_ERR_CUDA; }
+	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+	ncclUniqueId id;
+	if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return KG_ERR_CUDA; }
+	memcpy(id128, &id, sizeof id);
+	return KG_OK;
+}
+
+extern "C" kg_status kg_comm_init_rank(kg_ctx *c, const void *id128, int n_ranks, int rank) {
+	if (!c || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return KG_ERR_INVALID;
+	if (!g_nccl.load()) KG_FAIL(c, KG_ERR_CUDA, "%s", g_nccl.err.c_str());
+	KG_CUDA(c, cudaSetDevice(c->device));
+	kg_comm_destroy(c);
+	ncclUniqueId id;
+	memcpy(&id, id128, sizeof id);
+	ncclComm_t comm = nullptr;
+	KG_NCCL(c, g_nccl.CommInitRank(&comm, n_ranks, id, rank));
+	c->nccl_comm = comm;
+	return KG_OK;
+}
+
+extern "C" kg_status kg_comm_init_all(kg_ctx *const *ctxs, int n) {
+	if (!ctxs || n < 1) return KG_ERR_INVALID;
+	kg_ctx *c0 = ctxs[0];
+	if (!g_nccl.load()) KG_FAIL(c0, KG_ERR_CUDA, "%s", g_nccl.err.c_str());
+	std::vector<int> devs(n);
+	for (int i = 0; i < n; i++) { devs[i] = ctxs[i]->device; kg_comm_destroy(ctxs[i]); }
+	std::vector<ncclComm_t> comms(n, nullptr);
+	KG_NCCL(c0, g_nccl.CommInitAll(comms.data(), n, devs.data()));
+	for (int i = 0; i < n; i++) ctxs[i]->nccl_comm = comms[i];
+	return KG_OK;
+}
+
+// sum the kinship accumulators ([n_used^2] Gram counts + kept rows, u64: exact) over the communicator's ranks, in place
+static kg_status kinship_allreduce_enqueue(kg_ctx *c) {
+	if (!c->kin_active) KG_FAIL(c, KG_ERR_STATE, "kg_kinship_allreduce: call kg_kinship_begin first");
+	if (!c->nccl_comm) KG_FAIL(c, KG_ERR_STATE, "kg_kinship_allreduce: no communicator (kg_comm_init_rank / kg_comm_init_all)");
+	KG_CUDA(c, cudaSetDevice(c->device));
+	kg_status st = kg_tc_kinship_flush(c);
+	if (st != KG_OK) return st;
+	KG_NCCL(c, g_nccl.AllReduce(c->d_accum, c->d_accum, kg_kinship_accum_len(c), ncclUint64, ncclSum, static_cast<ncclComm_t>(c->nccl_comm), c->stream));
+	return KG_OK;
+}
+
+extern "C" kg_status kg_kinship_allreduce(kg_ctx *c) {
+	if (!c) return KG_ERR_INVALID;
+	return kinship_allreduce_enqueue(c);
+}
+
+extern "C" kg_status kg_kinship_allreduce_all(kg_ctx *const *ctxs, int n) {
+	if (!ctxs || n < 1) return KG_ERR_INVALID;
+	if (!g_nccl.load()) KG_FAIL(ctxs[0], KG_ERR_CUDA, "%s", g_nccl.err.c_str());
+	KG_NCCL(ctxs[0], g_nccl.GroupStart());
+	kg_status st = KG_OK;
+	for (int i = 0; i < n && st == KG_OK; i++) st = kinship_allreduce_enqueue(ctxs[i]);
+	ncclResult_t r = g_nccl.GroupEnd();
+	if (st != KG_OK) return st;
+	if (r != ncclSuccess) KG_FAIL(ctxs[0], KG_ERR_CUDA, "ncclGroupEnd failed: %s", g_nccl.GetErrorString(r));
 	return KG_OK;
 }
 

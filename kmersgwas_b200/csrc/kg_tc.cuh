@@ -581,8 +581,15 @@ static kg_status kg_tc_filter_debug(kg_ctx *c, const uint64_t *dev_in, uint64_t 
 // ------------------------------------------------------------------------------------- kinship (tensor engine)
 static kg_status kg_tc_prepare_kinship(kg_ctx *c) {
 	KgTcState &tc = c->tc;
-	tc.kin_ready = false;
 	const uint32_t ld = 64 * c->w_file;
+	tc.kin_dirty = false;
+	if (tc.kin_ready && tc.kin_tables_w_file == c->w_file && tc.d_kin_delta) {
+		// same shape as the last kg_kinship_begin: the tile-group / CTA tables are still valid, only the delta restarts
+		KG_CUDA(c, cudaMemsetAsync(tc.d_kin_delta, 0, ((size_t)ld * ld + 1) * sizeof(unsigned long long), c->stream));
+		return KG_OK;
+	}
+	tc.kin_ready = false;
+	tc.kin_tables_w_file = 0;
 	const size_t smem = kg_kin_tc_smem_bytes(c->w_file);
 	if (smem > 227u * 1024) { tc.why_unavailable = "row block does not fit shared memory next to the operand stages"; return KG_OK; }
 	// tile groups over the lower triangle in file column order
@@ -599,10 +606,12 @@ static kg_status kg_tc_prepare_kinship(kg_ctx *c) {
 			groups.push_back(g);
 		}
 	}
-	if (groups.size() > (size_t)c->sm_count) { tc.why_unavailable = "more sample tile groups than SMs"; return KG_OK; }
-	// CTA table: one wave, row splits per group in proportion to its tiles (a 2-tile group does twice the MMAs)
+	// CTA table.  Up to one wave: every group gets row splits in proportion to its tiles (a 2-tile group does twice the
+	// MMAs).  More groups than SMs (wide tables): one CTA per group, the launch runs in several waves.
 	std::vector<KgKinCta> ctas;
-	{
+	if (groups.size() > (size_t)c->sm_count) {
+		for (uint32_t gi = 0; gi < groups.size(); gi++) ctas.push_back(KgKinCta{gi, 0, 1, 0});
+	} else {
 		uint32_t total_tiles = 0;
 		for (const KgKinGroup &g : groups) total_tiles += g.j2[1] >= 0 ? 2 : 1;
 		uint32_t left = (uint32_t)c->sm_count, tiles_left = total_tiles;
@@ -627,10 +636,31 @@ static kg_status kg_tc_prepare_kinship(kg_ctx *c) {
 	KG_CUDA(c, cudaMemcpy(tc.d_kin_groups, groups.data(), groups.size() * sizeof(KgKinGroup), cudaMemcpyHostToDevice));
 	e = cudaMalloc((void **)&tc.d_kin_delta, ((size_t)ld * ld + 1) * sizeof(unsigned long long));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc kinship delta: %s", cudaGetErrorString(e));
+	KG_CUDA(c, cudaMemsetAsync(tc.d_kin_delta, 0, ((size_t)ld * ld + 1) * sizeof(unsigned long long), c->stream));
 	KG_CUDA(c, cudaFuncSetAttribute(kg_kinship_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	tc.kin_groups = (uint32_t)groups.size();
 	tc.kin_smem = smem;
 	tc.kin_ready = true;
+	tc.kin_tables_w_file = c->w_file;
+	return KG_OK;
+}
+
+// Fold the tensor engine's co-presence delta (file column order, accumulated over every tile since the last flush) into
+// the caller-visible accumulator (memory order) and restart the delta.  Called before the accumulator is read or
+// all-reduced; the int32 TMEM sums are widened per launch, so the u64 delta itself never overflows.
+static kg_status kg_tc_kinship_flush(kg_ctx *c) {
+	KgTcState &tc = c->tc;
+	if (!tc.kin_dirty) return KG_OK;
+	const uint32_t ld = 64 * c->w_file;
+	const uint64_t n2 = (uint64_t)c->n_used * c->n_used;
+	const unsigned fg = (unsigned)std::min<uint64_t>((n2 + 255) / 256, (uint64_t)c->sm_count * 8);
+	timing_begin(c, KG_KERNEL_AUX, 0);
+	kg_kinship_fold_kernel<<<std::max(fg, 1u), 256, 0, c->stream>>>(tc.d_kin_delta, ld, c->d_map_mem, (uint32_t)c->n_used,
+	                                                                 c->d_accum, tc.d_kin_delta + (size_t)ld * ld);
+	timing_end(c);
+	KG_LAUNCH_CHECK(c);
+	KG_CUDA(c, cudaMemsetAsync(tc.d_kin_delta, 0, ((size_t)ld * ld + 1) * sizeof(unsigned long long), c->stream));
+	tc.kin_dirty = false;
 	return KG_OK;
 }
 
@@ -641,7 +671,6 @@ static kg_status kg_tc_kinship_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t 
 	kg_status st = kg_tc_aligned_tile(c, dev_in, n_rows, &dev);
 	if (st != KG_OK) return st;
 	const uint32_t ld = 64 * c->w_file;
-	KG_CUDA(c, cudaMemsetAsync(tc.d_kin_delta, 0, ((size_t)ld * ld + 1) * sizeof(unsigned long long), c->stream));
 	KgKinTcParams k;
 	memset(&k, 0, sizeof k);
 	k.rows = dev;
@@ -677,12 +706,6 @@ static kg_status kg_tc_kinship_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t 
 	kg_kinship_tc_kernel<<<tc.kin_ctas, KG_K_THREADS, tc.kin_smem, c->stream>>>(k);
 	timing_end(c);
 	KG_LAUNCH_CHECK(c);
-	const uint64_t n2 = (uint64_t)c->n_used * c->n_used;
-	const unsigned fg = (unsigned)std::min<uint64_t>((n2 + 255) / 256, (uint64_t)c->sm_count * 8);
-	timing_begin(c, KG_KERNEL_AUX, 0);
-	kg_kinship_fold_kernel<<<std::max(fg, 1u), 256, 0, c->stream>>>(tc.d_kin_delta, ld, c->d_map_mem, (uint32_t)c->n_used,
-	                                                                 c->d_accum, tc.d_kin_delta + (size_t)ld * ld);
-	timing_end(c);
-	KG_LAUNCH_CHECK(c);
+	tc.kin_dirty = true;
 	return KG_OK;
 }

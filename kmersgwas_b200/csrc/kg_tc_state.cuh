@@ -51,6 +51,8 @@ struct KgTcState {
 	unsigned long long *d_kin_delta = nullptr;
 	struct KgKinCta *d_kin_ctas = nullptr;
 	uint32_t kin_groups = 0, kin_ctas = 0;
+	bool kin_dirty = false;                // the delta holds counts that are not folded into the caller's accumulator yet
+	uint32_t kin_tables_w_file = 0;        // shape the kinship tables were built for (0 = none)
 	size_t kin_smem = 0;
 	void *d_scratch = nullptr;
 	// device twins of the host-side filter tables, for kg_filter_retune_kernel (device-selection mode)

@@ -6,8 +6,10 @@
 //     (MultipleKmersDataBases::add_kmers_to_heaps) instead of one CTPL task per phenotype;
 //     --parallel is accepted and ignored;
 //   * pass 2 does not re-stream the table: only the selected rows are read back for the PLINK files;
+//   * the best-K heaps live on the GPU (kg_select_*: exact libstdc++ heap replay on the device) whenever their capacity
+//     fits shared memory (the pipeline's -n 10001 does); larger capacities use the host replay path;
 //   * new flags: --gpus G (row-shard the table over G GPUs of this box, exact merge), --device D,
-//     --engine {0 auto, 1 exact, 2 tensor filter + exact refine}.
+//     --engine {0 auto, 1 exact, 2 tensor filter + exact refine}, --select {auto, device, host}.
 #include <cmath>
 #include <exception>
 #include <iostream>
@@ -27,12 +29,46 @@ using namespace std;
 namespace {
 struct Shard {
 	unique_ptr<MultipleKmersDataBases> db;
-	vector<BestAssociationsHeap> heaps;   // local heaps: only supply thresholds when sharded
+	vector<BestAssociationsHeap> heaps;   // host replay path: local heaps (only supply thresholds when sharded)
 	AssociationDriverState state;
 	exception_ptr error;
+	bool overflow = false;                // device path: a round overflowed (DeviceSelectionOverflow)
 };
 
-// ctx phenotypes are set once per shard; rows are scored batch by batch from the shard's file range.
+// Pass 1 of one shard through the DEVICE heaps (kg_select_*): batches are submitted asynchronously while the tile
+// reader loads ahead; nothing comes back to the host until the end.  Shards other than the first warm-start from
+// the first prefix_rows rows of the table and log what their heaps admit (merged on shard 0 afterwards).
+void run_shard_device(Shard &sh, size_t min_count, size_t batch_size, bool verbose, KmersSet *pattern_counter,
+                      uint64_t first, uint64_t count, uint64_t prefix_rows, bool is_first_shard) {
+	try {
+		MultipleKmersDataBases &db = *sh.db;
+		if (!is_first_shard) {
+			db.restrict_to_rows(0, prefix_rows);
+			while (db.load_kmers(batch_size, min_count)) db.add_loaded_kmers_to_device_heaps();
+			db.device_selection_log_reset();
+		}
+		db.restrict_to_rows(first, count);
+		double t0 = get_time(), t1;
+		size_t batch_index = 0;
+		while (db.load_kmers(batch_size, min_count)) {
+			t1 = get_time();
+			if (verbose) cerr << "Load [" << batch_index << "]\t" << (t1 - t0) / 60. << "min" << endl;
+			t0 = get_time();
+			if (pattern_counter) db.update_presence_absence_pattern_counter(*pattern_counter);
+			db.add_loaded_kmers_to_device_heaps();
+			t1 = get_time();
+			if (verbose) cerr << "Associations [" << batch_index << "]\t" << (t1 - t0) / 60. << "min" << endl;
+			t0 = get_time();
+			batch_index++;
+		}
+	} catch (const DeviceSelectionOverflow &) {
+		sh.overflow = true;
+	} catch (...) {
+		sh.error = current_exception();
+	}
+}
+
+// Pass 1 of one shard through the host replay path (any heap capacity): device candidates -> BestAssociationsHeap.
 void run_shard(Shard &sh, const vector<vector<float> > &y, size_t min_count, size_t batch_size, bool verbose,
                KmersSet *pattern_counter) {
 	try {
@@ -52,7 +88,7 @@ void run_shard(Shard &sh, const vector<vector<float> > &y, size_t min_count, siz
 			if (pattern_counter) sh.db->update_presence_absence_pattern_counter(*pattern_counter);
 			kgh_associate_rows(ctx, hp.data(), hp.size(), sh.db->loaded_rows(), sh.db->rows_loaded(), sh.db->row_offset(),
 			                   1 + sh.db->file_words(), sh.state);
-			// the batch buffer is reused by the next load_kmers: drain the round still in flight
+			// the batch buffer is reused by the reader: drain the round still in flight
 			kgh_associate_finish(ctx, hp.data(), hp.size(), sh.state);
 			t1 = get_time();
 			if (verbose) cerr << "Associations [" << batch_index << "]\t" << (t1 - t0) / 60. << "min" << endl;
@@ -83,6 +119,7 @@ int main(int argc, char *argv[]) {
 	options.add(0, "gpus", "Number of GPUs to shard the table over", false, "1");
 	options.add(0, "device", "First CUDA device ordinal", false, "0");
 	options.add(0, "engine", "Scan engine: 0 auto, 1 exact, 2 tensor filter + exact refine", false, "0");
+	options.add(0, "select", "Where the best-K heaps live: auto (device when every capacity fits), device, host", false, "auto");
 	options.add(0, "help", "print help", true);
 	try {
 		options.parse(argc, argv);
@@ -107,6 +144,9 @@ int main(int argc, char *argv[]) {
 		const size_t n_gpus = max<size_t>(1, options.as<size_t>("gpus"));
 		const int device0 = options.as<int>("device");
 		const int engine = options.as<int>("engine");
+		const string select_mode = options.str("select");
+		if (select_mode != "auto" && select_mode != "device" && select_mode != "host")
+			throw CliOptions::ParseError("--select must be auto, device or host");
 		const string table = options.str("kmers_table");
 
 		// phenotypes (reference :81-88)
@@ -134,36 +174,89 @@ int main(int argc, char *argv[]) {
 		const bool count_patterns = options.count("pattern_counter") > 0;
 
 		// ---- pass 1: association scan ----------------------------------------------------------
-		vector<Shard> shards(n_gpus);
+		vector<unique_ptr<Shard> > shard_ptrs(n_gpus);
+		for (auto &sp : shard_ptrs) sp.reset(new Shard());
+		auto shards = [&](size_t g) -> Shard & { return *shard_ptrs[g]; };
 		for (size_t g = 0; g < n_gpus; g++) {
 			// KMERSGWAS_SHARDS_ON_ONE_DEVICE=1 (tests): every shard gets its own context on the same GPU
 			const bool one_device = getenv("KMERSGWAS_SHARDS_ON_ONE_DEVICE") != nullptr;
 			MultipleKmersDataBases::set_device(one_device ? device0 : device0 + (int)g);
-			shards[g].db.reset(new MultipleKmersDataBases(table, p_list[0].first, kmer_length));
-			shards[g].db->set_scan_engine(engine);
+			shards(g).db.reset(new MultipleKmersDataBases(table, p_list[0].first, kmer_length));
+			shards(g).db->set_scan_engine(engine);
 		}
-		const uint64_t total_rows = shards[0].db->rows_in_file();
-		if (n_gpus == 1) {
-			Shard &sh = shards[0];
+		const uint64_t total_rows = shards(0).db->rows_in_file();
+		if (count_patterns && n_gpus > 1) throw logic_error("--pattern_counter is not supported together with --gpus > 1");
+		vector<size_t> capacities(phenotypes_n);
+		for (size_t j = 0; j < phenotypes_n; j++) capacities[j] = k_heap[j].capacity();
+
+		// device heaps (kg_select_*) when every capacity fits them (the pipeline's -n 10001 does); else host replay
+		bool device_heaps = select_mode != "host";
+		if (device_heaps)
+			for (size_t g = 0; g < n_gpus && device_heaps; g++)
+				device_heaps = shards(g).db->begin_device_selection(capacities, y, min_count, g > 0);
+		if (!device_heaps && select_mode == "device") throw logic_error("--select device: a heap capacity does not fit the device heaps");
+		bool done = false;
+		if (device_heaps) {
+			const uint64_t prefix_rows = min<uint64_t>(total_rows / n_gpus, max<uint64_t>(1, (uint64_t)8 << 20));
+			vector<thread> threads;
+			for (size_t g = 0; g < n_gpus; g++) {
+				const uint64_t first = total_rows * g / n_gpus, last = total_rows * (g + 1) / n_gpus;
+				threads.emplace_back(run_shard_device, ref(shards(g)), min_count, batch_size, g == 0,
+				                     (count_patterns && g == 0) ? &pa_patterns_counter : nullptr, first, last - first, prefix_rows, g == 0);
+			}
+			for (auto &t : threads) t.join();
+			bool overflow = false;
+			for (auto &sp : shard_ptrs) {
+				if (sp->error) rethrow_exception(sp->error);
+				overflow = overflow || sp->overflow;
+			}
+			try {
+				// exact merge: shard 0's heaps are the sequential heaps of its block; the later shards' logs are replayed
+				// through them in row order (kg_select_replay)
+				for (size_t g = 1; g < n_gpus && !overflow; g++) {
+					vector<uint64_t> off, ent;
+					uint64_t rows = 0, kept = 0;
+					shards(g).db->device_selection_log(off, ent, rows, kept);
+					shards(0).db->device_selection_replay(off, ent, rows, kept);
+				}
+				if (!overflow) {
+					shards(0).db->finish_device_selection(k_heap);
+					done = true;
+				}
+			} catch (const DeviceSelectionOverflow &) {
+				overflow = true;
+			}
+			if (overflow) {
+				cerr << "device heaps: a candidate segment overflowed (scores rising along the table); re-running pass 1 through the host replay path" << endl;
+				pa_patterns_counter.clear();
+				for (size_t g = 0; g < n_gpus; g++) {
+					MultipleKmersDataBases::set_device(shards(g).db->device());
+					shard_ptrs[g].reset(new Shard());
+					shards(g).db.reset(new MultipleKmersDataBases(table, p_list[0].first, kmer_length));
+					shards(g).db->set_scan_engine(engine);
+				}
+			}
+		}
+		if (!done && n_gpus == 1) {
+			Shard &sh = shards(0);
 			sh.heaps.swap(k_heap);
 			run_shard(sh, y, min_count, batch_size, true, count_patterns ? &pa_patterns_counter : nullptr);
 			if (sh.error) rethrow_exception(sh.error);
 			k_heap.swap(sh.heaps);
-		} else {
-			if (count_patterns) throw logic_error("--pattern_counter is not supported together with --gpus > 1");
+		} else if (!done) {
 			vector<thread> threads;
 			for (size_t g = 0; g < n_gpus; g++) {
 				const uint64_t first = total_rows * g / n_gpus, last = total_rows * (g + 1) / n_gpus;
-				shards[g].db->restrict_to_rows(first, last - first);
-				shards[g].heaps = k_heap;  // same capacities, empty
-				shards[g].state.log_hits = true;
-				threads.emplace_back(run_shard, ref(shards[g]), cref(y), min_count, batch_size, g == 0, nullptr);
+				shards(g).db->restrict_to_rows(first, last - first);
+				shards(g).heaps = k_heap;  // same capacities, empty
+				shards(g).state.log_hits = true;
+				threads.emplace_back(run_shard, ref(shards(g)), cref(y), min_count, batch_size, g == 0, nullptr);
 			}
 			for (auto &t : threads) t.join();
 			vector<AssociationDriverState *> states;
-			for (auto &sh : shards) {
-				if (sh.error) rethrow_exception(sh.error);
-				states.push_back(&sh.state);
+			for (auto &sp : shard_ptrs) {
+				if (sp->error) rethrow_exception(sp->error);
+				states.push_back(&sp->state);
 			}
 			vector<BestAssociationsHeap *> hp(phenotypes_n);
 			for (size_t j = 0; j < phenotypes_n; j++) hp[j] = &k_heap[j];
@@ -179,7 +272,7 @@ int main(int argc, char *argv[]) {
 			best_kmers.push_back(k_heap[j].get_kmers_for_output(kmer_length));
 			k_heap[j].empty_heap();
 		}
-		MultipleKmersDataBases &db0 = *shards[0].db;
+		MultipleKmersDataBases &db0 = *shards(0).db;
 		for (size_t j = 0; j < phenotypes_n; j++) {
 			const string base = fn_base + "." + std::to_string(j) + "." + phenotypes_info.first[j];
 			BedBimFilesHandle handle(base);

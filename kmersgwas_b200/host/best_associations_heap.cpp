@@ -3,6 +3,7 @@
 #include "best_associations_heap.h"
 
 #include <algorithm>
+#include <cstring>
 #include <iostream>
 
 using std::get;
@@ -26,6 +27,20 @@ void BestAssociationsHeap::add_association(const uint64_t &k, const double &scor
 
 void BestAssociationsHeap::add_hits(const kg_hit *hits, std::size_t n) {
 	for (std::size_t i = 0; i < n; i++) add_association(hits[i].kmer, hits[i].score, hits[i].row);
+}
+
+void BestAssociationsHeap::load_layout(const uint64_t *entries, std::size_t n, std::size_t tested, std::size_t pushes, std::size_t pops) {
+	empty_heap();
+	for (std::size_t i = 0; i < n; i++) {
+		double score;
+		static_assert(sizeof(double) == sizeof(uint64_t), "score bits");
+		memcpy(&score, &entries[3 * i + 1], sizeof score);
+		m_best_kmers.push(AssociationScoreHeap(entries[3 * i], score, (std::size_t)entries[3 * i + 2]));
+	}
+	cnt_kmers = tested;
+	cnt_push = pushes;
+	cnt_pops = pops;
+	lowest_score = m_best_kmers.empty() ? 0.0 : get<1>(m_best_kmers.top());
 }
 
 // Pops a copy of the queue in ascending score order, handing each entry and the queue size

@@ -38,6 +38,10 @@ class BestAssociationsHeap {
 		// All entries in pop order (ascending score), as output_to_file_with_scores would write them.
 		std::vector<AssociationScoreHeap> entries_in_pop_order() const;
 		std::size_t capacity() const { return m_n_res; }
+		// Adopt a heap kept on the device (kg_select_export): n entries {k-mer, score bits, row} in libstdc++ LAYOUT order
+		// (position 0 = top).  Pushing a valid heap array front to back moves no element (every parent <= its child), so the
+		// queue ends up with exactly the device's layout -- and therefore the reference's pop order under ties.
+		void load_layout(const uint64_t *entries, std::size_t n, std::size_t tested, std::size_t pushes, std::size_t pops);
 	private:
 		std::size_t m_n_res;
 		AssociationsPriorityQueue m_best_kmers;

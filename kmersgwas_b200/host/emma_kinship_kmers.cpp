@@ -2,8 +2,8 @@
 //
 // Same flags and output as the reference CLI (/root/reference/src/emma_kinship_kmers.cpp: flags :37-42,
 // normalisation and printing :95-111).  The accumulation (:89-92 ->
-// kmers_multiple_databases.cpp:418-438) runs on the GPU; new flags: --gpus G (row shards, integer
-// accumulators summed exactly), --device D, --engine {0 auto, 1 popcount, 2 tensor cores}.
+// kmers_multiple_databases.cpp:418-438) runs on the GPU; new flags: --gpus G (row shards on G GPUs, their integer
+// accumulators summed exactly by one NCCL all-reduce), --device D, --engine {0 auto, 1 popcount, 2 tensor cores}.
 #include <cmath>
 #include <exception>
 #include <iostream>
@@ -93,10 +93,18 @@ int main(int argc, char *argv[]) {
 		for (size_t g = 1; g < n_gpus; g++) threads.emplace_back(work, g);
 		work(0);
 		for (auto &t : threads) t.join();
-		for (size_t g = 0; g < n_gpus; g++) {
+		for (size_t g = 0; g < n_gpus; g++)
 			if (errors[g]) rethrow_exception(errors[g]);
-			dbs[g]->kinship_finish(K, n_snps);  // exact integer sums: shards add
+		if (n_gpus > 1) {
+			// the path's one exchange step: NCCL all-reduce (sum) of the u64 accumulators over NVLink; exact, shards add
+			vector<kg_ctx *> ctxs(n_gpus);
+			for (size_t g = 0; g < n_gpus; g++) ctxs[g] = dbs[g]->context();
+			if (kg_comm_init_all(ctxs.data(), (int)n_gpus) != KG_OK)
+				throw runtime_error(string("kg_comm_init_all: ") + kg_last_error(ctxs[0]));
+			if (kg_kinship_allreduce_all(ctxs.data(), (int)n_gpus) != KG_OK)
+				throw runtime_error(string("kg_kinship_allreduce_all: ") + kg_last_error(ctxs[0]));
 		}
+		dbs[0]->kinship_finish(K, n_snps);
 		cerr << "#" << n_snps << endl;
 
 		// normalise + print (reference :95-111): K/n_snps, symmetric, unit diagonal, default precision

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <iostream>
 #include <stdexcept>
+#include <thread>
 
 using std::string;
 using std::vector;
@@ -30,6 +31,27 @@ void read_fully(int fd, void *dst, size_t bytes, uint64_t offset, const string &
 		offset += (uint64_t)got;
 	}
 }
+
+// A batch is read by several threads, each pread-ing its own slice: one thread copies ~5 GB/s out of the page cache,
+// the PCIe link behind the pinned buffer takes ~55 GB/s.
+void read_parallel(int fd, void *dst, size_t bytes, uint64_t offset, const string &path) {
+	const size_t kSlice = 64u << 20;
+	unsigned n_thr = (unsigned)std::min<size_t>((bytes + kSlice - 1) / kSlice, 8);
+	if (const char *e = getenv("KMERSGWAS_READ_THREADS")) n_thr = std::max(1, atoi(e));
+	if (n_thr <= 1) { read_fully(fd, dst, bytes, offset, path); return; }
+	std::vector<std::thread> thr;
+	std::vector<std::exception_ptr> err(n_thr);
+	const size_t per = ((bytes + n_thr - 1) / n_thr + 4095) & ~(size_t)4095;
+	for (unsigned t = 0; t < n_thr; t++) {
+		const size_t b = std::min(bytes, (size_t)t * per), e = std::min(bytes, b + per);
+		if (b == e) continue;
+		thr.emplace_back([=, &err, &path] {
+			try { read_fully(fd, static_cast<char *>(dst) + b, e - b, offset + b, path); } catch (...) { err[t] = std::current_exception(); }
+		});
+	}
+	for (auto &t : thr) t.join();
+	for (auto &e : err) if (e) std::rethrow_exception(e);
+}
 }  // namespace
 
 void MultipleKmersDataBases::check(kg_status st, const char *what) const {
@@ -48,8 +70,10 @@ MultipleKmersDataBases::MultipleKmersDataBases(const string &kmers_table_base, c
       m_kmer_len(kmer_len),
       m_table_path(kmers_table_base + ".table"),
       m_fd(-1), m_kmer_number(0), m_first_row(0), m_kmer_loaded(0), m_row_offset(0),
-      m_batch(nullptr), m_batch_cap(0), m_rows_loaded(0), m_load_mac(0),
+      m_batch(nullptr), m_cur(0), m_prefetch_pending(false), m_prefetch_batch(0), m_prefetch_first(0),
+      m_device_selection(false), m_rows_submitted_sel(0), m_rows_loaded(0), m_load_mac(0),
       m_ctx(nullptr), m_pheno_min_cnt(0), m_kinship_streaming(false) {
+	for (int b = 0; b < kBuffers; b++) { m_buf[b] = nullptr; m_buf_cap[b] = 0; m_buf_ticket[b] = 0; m_buf_busy[b] = false; }
 	m_fd = open(m_table_path.c_str(), O_RDONLY);
 	if (m_fd < 0) throw std::logic_error("Couldn't open kmer table file: " + m_table_path);
 	struct stat sb;
@@ -76,12 +100,15 @@ MultipleKmersDataBases::MultipleKmersDataBases(const string &kmers_table_base, c
 	shape.n_used = m_accessions;
 	shape.map_word = m_map_word_index.data();
 	shape.map_bit = m_map_bit_index.data();
+	m_device = s_device;
 	kg_status st = kg_ctx_create(s_device, &shape, nullptr, &m_ctx);
 	if (st != KG_OK) throw std::runtime_error(string("kg_ctx_create: ") + kg_last_error(nullptr));
 }
 
 MultipleKmersDataBases::~MultipleKmersDataBases() {
-	if (m_batch) kg_host_free(m_ctx, m_batch);
+	try { cancel_prefetch(); } catch (...) {}
+	if (m_ctx) kg_sync(m_ctx);
+	for (int b = 0; b < kBuffers; b++) if (m_buf[b]) kg_host_free(m_ctx, m_buf[b]);
 	if (m_ctx) kg_ctx_destroy(m_ctx);
 	if (m_fd >= 0) close(m_fd);
 }
@@ -103,6 +130,9 @@ void MultipleKmersDataBases::create_map_from_all_DBs() {
 }
 
 void MultipleKmersDataBases::restrict_to_rows(uint64_t first, uint64_t count) {
+	cancel_prefetch();
+	if (m_file_rows == 0) m_file_rows = m_kmer_number;
+	m_kmer_number = m_file_rows;
 	if (first > m_kmer_number) first = m_kmer_number;
 	if (count > m_kmer_number - first) count = m_kmer_number - first;
 	m_first_row = first;
@@ -112,25 +142,67 @@ void MultipleKmersDataBases::restrict_to_rows(uint64_t first, uint64_t count) {
 	m_rows_loaded = 0;
 }
 
+// read file rows [first_row, first_row + n_rows) into pinned buffer b (waiting until the device is done with it)
+uint64_t MultipleKmersDataBases::read_batch_into(int b, uint64_t first_row, uint64_t n_rows) {
+	const size_t stride = 1 + m_hash_words_db_file;
+	if (m_buf_busy[b]) {
+		check(kg_stream_wait(m_ctx, m_buf_ticket[b]), "kg_stream_wait");
+		m_buf_busy[b] = false;
+	}
+	if (m_buf_cap[b] < n_rows) {
+		if (m_buf[b]) kg_host_free(m_ctx, m_buf[b]);
+		m_buf[b] = nullptr;
+		m_buf_cap[b] = 0;
+		void *p = nullptr;
+		check(kg_host_alloc(m_ctx, (size_t)n_rows * stride * 8, &p), "kg_host_alloc");
+		m_buf[b] = static_cast<uint64_t *>(p);
+		m_buf_cap[b] = n_rows;
+	}
+	read_parallel(m_fd, m_buf[b], (size_t)n_rows * stride * 8, kHeaderBytes + first_row * stride * 8, m_table_path);
+	return n_rows;
+}
+
+void MultipleKmersDataBases::start_prefetch(uint64_t batch_size) {
+	const uint64_t left = m_kmer_number - m_kmer_loaded;
+	if (left == 0 || getenv("KMERSGWAS_NO_PREFETCH")) return;
+	const uint64_t n = std::min<uint64_t>(batch_size, left);
+	const int b = (m_cur + 1) % kBuffers;
+	m_prefetch_batch = batch_size;
+	m_prefetch_first = m_kmer_loaded;
+	m_prefetch = std::async(std::launch::async, [this, b, n] { return read_batch_into(b, m_prefetch_first, n); });
+	m_prefetch_pending = true;
+}
+
+void MultipleKmersDataBases::cancel_prefetch() {
+	if (m_prefetch_pending) {
+		m_prefetch_pending = false;
+		m_prefetch.get();
+	}
+}
+
+// Same contract as the reference (:103-108, 145): true with a (possibly short) batch, false once the file is exhausted.
+// The rows are RAW file rows in a pinned buffer; the next batch is already being read in the background.
 bool MultipleKmersDataBases::load_kmers(const uint64_t &batch_size, const size_t &mac) {
 	m_row_offset = m_kmer_loaded;
 	m_rows_loaded = 0;
 	m_load_mac = mac;
 	const uint64_t left = m_kmer_number - m_kmer_loaded;
-	if (left == 0) return false;
+	if (left == 0) { cancel_prefetch(); return false; }
 	const uint64_t n = std::min<uint64_t>(batch_size, left);
-	const size_t stride = 1 + m_hash_words_db_file;
-	if (m_batch_cap < n) {
-		if (m_batch) kg_host_free(m_ctx, m_batch);
-		m_batch = nullptr;
-		void *p = nullptr;
-		check(kg_host_alloc(m_ctx, (size_t)n * stride * 8, &p), "kg_host_alloc");
-		m_batch = static_cast<uint64_t *>(p);
-		m_batch_cap = n;
+	const int b = (m_cur + 1) % kBuffers;
+	uint64_t got;
+	if (m_prefetch_pending && m_prefetch_batch == batch_size && m_prefetch_first == m_kmer_loaded) {
+		m_prefetch_pending = false;
+		got = m_prefetch.get();
+	} else {
+		cancel_prefetch();
+		got = read_batch_into(b, m_kmer_loaded, n);
 	}
-	read_fully(m_fd, m_batch, (size_t)n * stride * 8, kHeaderBytes + m_kmer_loaded * stride * 8, m_table_path);
-	m_kmer_loaded += n;
-	m_rows_loaded = n;
+	m_cur = b;
+	m_batch = m_buf[b];
+	m_kmer_loaded += got;
+	m_rows_loaded = got;
+	start_prefetch(batch_size);
 	return true;
 }
 
@@ -180,6 +252,75 @@ void MultipleKmersDataBases::add_kmers_to_heaps(vector<BestAssociationsHeap> &he
 	for (size_t j = 0; j < heaps.size(); j++) hp[j] = &heaps[j];
 	kgh_associate_rows(m_ctx, hp.data(), hp.size(), m_batch, m_rows_loaded, m_row_offset, 1 + m_hash_words_db_file, m_driver);
 	kgh_associate_finish(m_ctx, hp.data(), hp.size(), m_driver);
+}
+
+// ---- device-resident heaps --------------------------------------------------------------------------
+bool MultipleKmersDataBases::begin_device_selection(const vector<size_t> &capacities, const vector<vector<float> > &scores,
+                                                    const size_t &min_cnt, bool log_admissions) {
+	if (capacities.size() != scores.size()) throw std::logic_error("heaps and phenotypes differ in number");
+	ensure_phenotypes(scores, min_cnt);
+	vector<uint64_t> kb(capacities.begin(), capacities.end());
+	const kg_status st = kg_select_begin(m_ctx, kb.data(), (uint32_t)kb.size(), log_admissions ? KG_SELECT_LOG : 0);
+	if (st == KG_ERR_INVALID) return false;   // a heap does not fit the device: the caller uses the host replay path
+	check(st, "kg_select_begin");
+	m_device_selection = true;
+	m_rows_submitted_sel = 0;
+	return true;
+}
+
+void MultipleKmersDataBases::add_loaded_kmers_to_device_heaps() {
+	if (!m_device_selection) throw std::logic_error("add_loaded_kmers_to_device_heaps without begin_device_selection");
+	if (m_load_mac != m_pheno_min_cnt)
+		throw std::logic_error("GPU path: load_kmers' minor allele count and the selection's min_cnt must be equal");
+	if (m_rows_loaded == 0) return;
+	check(kg_scan_submit(m_ctx, m_batch, m_rows_loaded, m_row_offset), "kg_scan_submit");
+	// the reader may overwrite this buffer once everything submitted so far has left it
+	check(kg_stream_mark(m_ctx, &m_buf_ticket[m_cur]), "kg_stream_mark");
+	m_buf_busy[m_cur] = true;
+	m_rows_submitted_sel += m_rows_loaded;
+}
+
+void MultipleKmersDataBases::device_selection_log_reset() {
+	check(kg_select_log_reset(m_ctx), "kg_select_log_reset");
+	m_rows_submitted_sel = 0;
+}
+
+static void throw_if_overflow(kg_ctx *ctx, kg_status st, const char *what) {
+	if (st == KG_ERR_HITS_OVERFLOW) throw DeviceSelectionOverflow(string(what) + ": " + kg_last_error(ctx));
+	if (st != KG_OK) throw std::runtime_error(string(what) + ": " + kg_last_error(ctx));
+}
+
+void MultipleKmersDataBases::device_selection_log(vector<uint64_t> &offsets, vector<uint64_t> &entries, uint64_t &rows, uint64_t &kept) {
+	uint64_t applied = 0;
+	throw_if_overflow(m_ctx, kg_select_sync(m_ctx, &applied, &kept), "kg_select_sync");
+	rows = m_rows_submitted_sel;
+	const size_t P = m_pheno_flat.size() / m_accessions;
+	vector<uint64_t> counts(P);
+	check(kg_select_log_counts(m_ctx, counts.data()), "kg_select_log_counts");
+	offsets.assign(P + 1, 0);
+	for (size_t p = 0; p < P; p++) offsets[p + 1] = offsets[p] + counts[p];
+	entries.assign((size_t)offsets[P] * 3, 0);
+	check(kg_select_log_export(m_ctx, entries.data(), offsets.data()), "kg_select_log_export");
+}
+
+void MultipleKmersDataBases::device_selection_replay(const vector<uint64_t> &offsets, const vector<uint64_t> &entries, uint64_t rows, uint64_t kept) {
+	check(kg_select_replay(m_ctx, entries.data(), offsets.data(), rows, kept), "kg_select_replay");
+}
+
+void MultipleKmersDataBases::finish_device_selection(vector<BestAssociationsHeap> &heaps) {
+	uint64_t applied = 0, kept = 0;
+	throw_if_overflow(m_ctx, kg_select_sync(m_ctx, &applied, &kept), "kg_select_sync");
+	const size_t P = heaps.size();
+	vector<uint64_t> state(kg_select_state_len(m_ctx));
+	check(kg_select_export(m_ctx, state.data()), "kg_select_export");
+	const uint32_t kmax = kg_select_kmax(m_ctx);
+	for (size_t p = 0; p < P; p++) {
+		const uint64_t *hdr = state.data() + 4 * p;
+		const uint64_t *ent = state.data() + 4 * P + (size_t)p * kmax * 3;
+		heaps[p].load_layout(ent, (size_t)hdr[0], (size_t)kept, (size_t)hdr[1], (size_t)hdr[2]);
+	}
+	check(kg_select_end(m_ctx), "kg_select_end");
+	m_device_selection = false;
 }
 
 // ---- kinship ---------------------------------------------------------------------------------------

@@ -15,10 +15,19 @@
 #ifndef KGH_KMER_MULTIPLEDB_H
 #define KGH_KMER_MULTIPLEDB_H
 
+#include <future>
+#include <stdexcept>
+
 #include "association_driver.h"
 #include "best_associations_heap.h"
 #include "kmer_general.h"
 #include "kmersgwas_b200.h"
+
+// Thrown by finish_device_selection when a round overflowed a candidate segment on the device (scores rising along
+// the table): the caller re-runs the scan through the host replay path (add_kmers_to_heaps), which has no such limit.
+struct DeviceSelectionOverflow : public std::runtime_error {
+	explicit DeviceSelectionOverflow(const std::string &m) : std::runtime_error(m) {}
+};
 
 class MultipleKmersDataBases {
 	public:
@@ -40,6 +49,19 @@ class MultipleKmersDataBases {
 		// All phenotypes of the batch in one device pass; heaps[j] <-> scores[j].
 		void add_kmers_to_heaps(std::vector<BestAssociationsHeap> &heaps, const std::vector<std::vector<float> > &scores,
 		                        const std::size_t &min_cnt) const;
+
+		// ---- device-resident heaps (kg_select_*): the streaming form of add_kmers_to_heaps used by the CLI.  The heaps
+		// live on the GPU for the whole scan, batches are only submitted (asynchronously: the pinned tile reader keeps
+		// reading ahead), and the BestAssociationsHeap objects are filled once at the end, layout and all.
+		// Returns false (and changes nothing) when a capacity does not fit the device heaps: use add_kmers_to_heaps then.
+		bool begin_device_selection(const std::vector<std::size_t> &capacities, const std::vector<std::vector<float> > &scores,
+		                            const std::size_t &min_cnt, bool log_admissions);
+		void add_loaded_kmers_to_device_heaps();
+		void device_selection_log_reset();      // row shards > 0: forget the shared prefix's log entries and kept rows
+		// the shard's admission log, packed: offsets[P + 1], entries[3 * offsets[P]] {row, k-mer, score bits}; + kept rows
+		void device_selection_log(std::vector<uint64_t> &offsets, std::vector<uint64_t> &entries, uint64_t &rows, uint64_t &kept);
+		void device_selection_replay(const std::vector<uint64_t> &offsets, const std::vector<uint64_t> &entries, uint64_t rows, uint64_t kept);
+		void finish_device_selection(std::vector<BestAssociationsHeap> &heaps);
 
 		// K[i][j] += IBS count over the loaded batch for j < i; count += kept rows (:418-438).
 		void update_emma_kinshhip_calculation(std::vector<std::vector<uint64_t> > &K, uint64_t &count) const;
@@ -67,12 +89,13 @@ class MultipleKmersDataBases {
 
 		// B200 additions
 		static void set_device(int device) { s_device = device; }
-		uint64_t rows_in_file() const { return m_kmer_number; }
+		uint64_t rows_in_file() const { return m_file_rows ? m_file_rows : m_kmer_number; }
 		uint64_t rows_loaded() const { return m_rows_loaded; }
 		std::size_t file_words() const { return m_hash_words_db_file; }
 		uint64_t row_offset() const { return m_row_offset; }
 		const uint64_t *loaded_rows() const { return m_batch; }
 		kg_ctx *context() const { return m_ctx; }
+		int device() const { return m_device; }
 		void set_scan_engine(int engine) const;
 		void set_kinship_engine(int engine) const;
 		// Restrict this object to file rows [first, first + count): one shard of a multi-GPU run.
@@ -86,17 +109,34 @@ class MultipleKmersDataBases {
 		uint32_t m_kmer_len;
 		std::string m_table_path;
 		int m_fd;
+		uint64_t m_file_rows = 0; // rows in the whole file (set by the first restrict_to_rows)
 		uint64_t m_kmer_number;   // rows in (this shard of) the file
 		uint64_t m_first_row;     // first file row of this shard
 		uint64_t m_kmer_loaded;   // rows read so far (incl. current batch)
 		uint64_t m_row_offset;    // file row index of the first row of the current batch
-		uint64_t *m_batch;        // pinned host buffer with the raw rows of the current batch
-		std::size_t m_batch_cap;  // capacity in rows
+		uint64_t *m_batch;        // pinned host buffer with the raw rows of the current batch (= m_buf[m_cur])
+		// tile reader: three pinned buffers; while the device works on the current batch (and may still copy the previous
+		// one), a reader thread preads the next batch with several threads (load_kmers then only swaps buffers)
+		static const int kBuffers = 3;
+		uint64_t *m_buf[kBuffers];
+		std::size_t m_buf_cap[kBuffers];      // capacity in rows
+		uint64_t m_buf_ticket[kBuffers];      // kg_stream_mark of the last submit that read the buffer
+		bool m_buf_busy[kBuffers];
+		int m_cur;
+		std::future<uint64_t> m_prefetch;     // rows read into m_buf[(m_cur + 1) % kBuffers]
+		bool m_prefetch_pending;
+		uint64_t m_prefetch_batch, m_prefetch_first;
+		uint64_t read_batch_into(int b, uint64_t first_row, uint64_t n_rows);
+		void start_prefetch(uint64_t batch_size);
+		void cancel_prefetch();
+		bool m_device_selection;
+		uint64_t m_rows_submitted_sel;
 		uint64_t m_rows_loaded;   // rows in the current batch
 		std::size_t m_load_mac;   // MAC given to the last load_kmers
 		std::vector<uint32_t> m_map_word_index, m_map_bit_index;
 		std::vector<uint64_t> m_map_mask;
 		mutable kg_ctx *m_ctx;
+		int m_device = 0;
 		mutable std::vector<float> m_pheno_flat;   // phenotypes currently resident on the device
 		mutable std::size_t m_pheno_min_cnt;
 		mutable AssociationDriverState m_driver;   // rows scored since the phenotypes were set, hit buffer

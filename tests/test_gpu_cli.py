@@ -65,7 +65,9 @@ def test_associate_kmers_outputs_byte_identical(bins, tmp_path, name, extra):
         assert key in outs["ours"][1].stderr
 
 
-def test_associate_kmers_first_phenotype_best_and_small_batches(bins, tmp_path):
+@pytest.mark.parametrize("select", ["device", "host"])
+def test_associate_kmers_first_phenotype_best_and_small_batches(bins, tmp_path, select):
+    """both homes of the best-K heaps -- the device (kg_select_*) and the host replay path -- give the reference's files"""
     g = S.Golden("identity_n131")
     table, pheno = g.write_inputs(tmp_path)
     dirs = []
@@ -73,10 +75,28 @@ def test_associate_kmers_first_phenotype_best_and_small_batches(bins, tmp_path):
         out = tmp_path / tag
         out.mkdir()
         r = _run(exe, ["-p", pheno, "-b", "x", "-o", out, "--kmers_table", table, "-n", 40, "--first_phenotype_best", 90,
-                       "--kmer_len", 31, "--maf", 0.1, "--mac", 3, "--batch_size", 777, "--k_mers_scores"])
+                       "--kmer_len", 31, "--maf", 0.1, "--mac", 3, "--batch_size", 777, "--k_mers_scores"]
+                 + (["--select", select] if tag == "ours" else []))
         assert r.returncode == 0, r.stderr[-2000:]
         dirs.append(out)
     _same_dir(*dirs)
+
+
+def test_associate_kmers_default_capacity_uses_host_heaps(bins, tmp_path):
+    """the binary's default -n 1000000 does not fit the device heaps: --select auto falls back to the host replay path,
+    --select device refuses"""
+    g = S.Golden("plumbing_n64")
+    table, pheno = g.write_inputs(tmp_path)
+    dirs = []
+    for tag, exe in (("ref", S.REF_DIR / "associate_kmers"), ("ours", bins / "associate_kmers")):
+        out = tmp_path / tag
+        out.mkdir()
+        r = _run(exe, ["-p", pheno, "-b", "x", "-o", out, "--kmers_table", table, "--kmer_len", 31, "--k_mers_scores"])
+        assert r.returncode == 0, r.stderr[-2000:]
+        dirs.append(out)
+    _same_dir(*dirs)
+    r = _run(bins / "associate_kmers", ["-p", pheno, "-b", "x", "-o", tmp_path, "--kmers_table", table, "--kmer_len", 31, "--select", "device"])
+    assert r.returncode != 0
 
 
 def test_associate_kmers_errors_like_reference(bins, tmp_path):
@@ -118,10 +138,10 @@ def test_associate_kmers_two_shards_equal_one(bins, tmp_path):
     dirs = []
     if torch.cuda.device_count() < 2:
         os.environ["KMERSGWAS_SHARDS_ON_ONE_DEVICE"] = "1"
-    for tag, extra in (("one", []), ("two", ["--gpus", 2]), ("three", ["--gpus", 3])):
+    for tag, extra in (("one", []), ("two", ["--gpus", 2]), ("three", ["--gpus", 3]), ("two_host", ["--gpus", 2, "--select", "host"])):
         out = tmp_path / tag
         out.mkdir()
-        if tag == "three":
+        if tag in ("three", "two_host"):
             os.environ["KMERSGWAS_SHARDS_ON_ONE_DEVICE"] = "1"
         r = _run(bins / "associate_kmers", ["-p", pheno, "-b", "x", "-o", out, "--kmers_table", table, "-n", g.kbest,
                                            "--kmer_len", 31, "--maf", g.maf, "--mac", g.mac, "--batch_size", 500,
@@ -129,8 +149,8 @@ def test_associate_kmers_two_shards_equal_one(bins, tmp_path):
         assert r.returncode == 0, r.stderr[-2000:]
         dirs.append(out)
     os.environ.pop("KMERSGWAS_SHARDS_ON_ONE_DEVICE", None)
-    _same_dir(dirs[0], dirs[1])
-    _same_dir(dirs[0], dirs[2])
+    for d in dirs[1:]:
+        _same_dir(dirs[0], d)
 
 
 @pytest.mark.parametrize("name,batch,unique,rows_per_load", [
