@@ -66,7 +66,8 @@ typedef struct kg_hit {
 /* Options for kg_set_option */
 enum {
 	KG_OPT_SCAN_ENGINE = 1, /* 0 = auto, 1 = exact fp32-order kernel on every row, 2 = int8 tensor filter + exact refine */
-	KG_OPT_HIT_CAPACITY = 2, /* number of kg_hit the device hit buffer holds (default 1<<22); set before first submit */
+	KG_OPT_HIT_CAPACITY = 2, /* number of kg_hit a device hit interval holds (default 1<<22); may be changed whenever no
+	                            interval is open or waiting for kg_scan_fetch */
 	KG_OPT_KINSHIP_ENGINE = 3, /* 0 = auto, 1 = popcount kernel, 2 = int8 tensor-core Gram */
 	KG_OPT_KERNEL_TIMING = 4,  /* 1 = bracket every hot-path kernel launch with CUDA events on the context's stream
 	                              (read back with kg_kernel_time); 0 = off (default) */

@@ -68,7 +68,7 @@ struct kg_ctx {
 	uint64_t rows_seen_total = 0, kept_total = 0;   // over consumed intervals
 	cudaStream_t d2h_stream = nullptr;
 	// pinned staging ring for stream-ordered threshold updates (no host sync)
-	struct ThrStage { double *h_thr = nullptr; struct KgFilterGroupConst *h_gc = nullptr; cudaEvent_t ev = nullptr; } thr_stage[4];
+	struct ThrStage { double *h_thr = nullptr; cudaEvent_t ev = nullptr; } thr_stage[4];
 	int thr_next = 0;
 	size_t thr_stage_p = 0, thr_stage_g = 0;
 
@@ -324,7 +324,6 @@ extern "C" void kg_ctx_destroy(kg_ctx *c) {
 	}
 	for (int i = 0; i < 4; i++) {
 		if (c->thr_stage[i].h_thr) cudaFreeHost(c->thr_stage[i].h_thr);
-		if (c->thr_stage[i].h_gc) cudaFreeHost(c->thr_stage[i].h_gc);
 		if (c->thr_stage[i].ev) cudaEventDestroy(c->thr_stage[i].ev);
 	}
 	if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
@@ -358,7 +357,20 @@ extern "C" kg_status kg_set_option(kg_ctx *c, int option, int64_t value) {
 		return KG_OK;
 	case KG_OPT_HIT_CAPACITY:
 		if (value < 1) KG_FAIL(c, KG_ERR_INVALID, "hit capacity must be >= 1");
-		if (c->iv[0].d_hits) KG_FAIL(c, KG_ERR_STATE, "hit capacity must be set before the first submit");
+		if (c->iv[0].d_hits) {
+			// already allocated (kg_scan_set_phenotypes): only between intervals, after the device has drained
+			if (c->iv[0].closed || c->iv[1].closed || c->iv[c->cur].rows)
+				KG_FAIL(c, KG_ERR_STATE, "hit capacity can only change while no hit interval is open or waiting (fetch first)");
+			KG_CUDA(c, cudaSetDevice(c->device));
+			KG_CUDA(c, cudaStreamSynchronize(c->stream));
+			for (int i = 0; i < 2; i++) {
+				cudaFree(c->iv[i].d_hits);
+				c->iv[i].d_hits = nullptr;
+				cudaError_t me = cudaMalloc((void **)&c->iv[i].d_hits, (uint64_t)value * sizeof(kg_hit));
+				if (me != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc hit buffer: %s", cudaGetErrorString(me));
+			}
+			c->d_hits = c->iv[c->cur].d_hits;
+		}
 		c->hit_capacity = (uint64_t)value;
 		return KG_OK;
 	case KG_OPT_KINSHIP_ENGINE:
@@ -641,30 +653,23 @@ extern "C" kg_status kg_scan_set_phenotypes(kg_ctx *c, const float *y, uint32_t 
 	for (int i = 0; i < 4; i++) {
 		KG_CUDA(c, cudaEventSynchronize(c->thr_stage[i].ev));
 		if (c->thr_stage[i].h_thr) cudaFreeHost(c->thr_stage[i].h_thr);
-		if (c->thr_stage[i].h_gc) cudaFreeHost(c->thr_stage[i].h_gc);
 		c->thr_stage[i].h_thr = nullptr;
-		c->thr_stage[i].h_gc = nullptr;
 		KG_CUDA(c, cudaMallocHost((void **)&c->thr_stage[i].h_thr, (size_t)c->p_alloc * sizeof(double)));
-		KG_CUDA(c, cudaMallocHost((void **)&c->thr_stage[i].h_gc, 16 * 48 + 2 * (size_t)c->p_alloc * sizeof(float)));   // group slots + per-phenotype (alpha, kappa)
 	}
 	kg_status st = kg_tc_prepare_scan(c);
 	return st;
 }
 
-// Per-round constants travel as KERNEL ARGUMENTS (copied at launch, no staging buffer, no copy-engine round trip in front
-// of the filter launch): thresholds of the exact kernels + the filter's group slots and per-phenotype (alpha, kappa).
-// Used when they fit the 4 KB argument space (P <= 128); larger P goes through pinned staging + cudaMemcpyAsync.
+// Host-driven mode: the thresholds travel as KERNEL ARGUMENTS (copied at launch, no staging buffer, no copy-engine round
+// trip in front of the filter launch) when they fit the 4 KB argument space (P <= 128); more phenotypes go through
+// pinned staging + cudaMemcpyAsync.  The filter's bound constants are then recomputed on the device (kg_tc_retune).
 #define KG_RC_MAX_P 128
 struct KgRoundConsts {
 	double thr[KG_RC_MAX_P];
-	unsigned char gc[16 * 48 + 2 * KG_RC_MAX_P * sizeof(float)];   // 16 KgFilterGroupConst, then alpha[P], kappa[P]
-	uint32_t p_alloc, gc_bytes;
+	uint32_t p_alloc;
 };
-__global__ void kg_round_constants_kernel(const KgRoundConsts rc, double *__restrict__ d_thr, unsigned char *__restrict__ d_gconst) {
+__global__ void kg_round_constants_kernel(const KgRoundConsts rc, double *__restrict__ d_thr) {
 	for (uint32_t i = threadIdx.x; i < rc.p_alloc; i += blockDim.x) d_thr[i] = rc.thr[i];
-	if (d_gconst)
-		for (uint32_t i = threadIdx.x; i < rc.gc_bytes / 4; i += blockDim.x)
-			reinterpret_cast<uint32_t *>(d_gconst)[i] = reinterpret_cast<const uint32_t *>(rc.gc)[i];
 }
 
 extern "C" kg_status kg_scan_set_thresholds(kg_ctx *c, const double *thr, uint32_t n_pheno) {
@@ -674,33 +679,22 @@ extern "C" kg_status kg_scan_set_thresholds(kg_ctx *c, const double *thr, uint32
 	KG_CUDA(c, cudaSetDevice(c->device));
 	for (uint32_t p = 0; p < n_pheno; p++) c->h_thr[p] = thr[p];
 	if (c->p_alloc <= KG_RC_MAX_P) {
-		static_assert(sizeof(KgRoundConsts) <= 4000, "kernel argument space");
 		KgRoundConsts rc;
 		for (uint32_t p = 0; p < c->p_alloc; p++) rc.thr[p] = c->h_thr[p];
 		rc.p_alloc = c->p_alloc;
-		rc.gc_bytes = 0;
-		unsigned char *d_gc = nullptr;
-		if (c->tc.scan_ready) {
-			memset(rc.gc, 0, sizeof rc.gc);
-			kg_status st = kg_tc_update_thresholds(c, reinterpret_cast<KgFilterGroupConst *>(rc.gc), false);
-			if (st != KG_OK) return st;
-			rc.gc_bytes = (uint32_t)(16 * sizeof(KgFilterGroupConst) + 2 * (size_t)c->n_pheno * sizeof(float));
-			d_gc = reinterpret_cast<unsigned char *>(c->tc.d_gconst);
-		}
-		kg_round_constants_kernel<<<1, 256, 0, c->stream>>>(rc, c->d_thr, d_gc);
+		kg_round_constants_kernel<<<1, 128, 0, c->stream>>>(rc, c->d_thr);
 		KG_LAUNCH_CHECK(c);
-		return KG_OK;
+	} else {
+		// stream-ordered through a pinned staging slot: tiles already queued keep the thresholds they were submitted
+		// with, and the host never waits for the device here
+		kg_ctx::ThrStage &stg = c->thr_stage[c->thr_next];
+		c->thr_next = (c->thr_next + 1) & 3;
+		KG_CUDA(c, cudaEventSynchronize(stg.ev));
+		memcpy(stg.h_thr, c->h_thr.data(), (size_t)c->p_alloc * sizeof(double));
+		KG_CUDA(c, cudaMemcpyAsync(c->d_thr, stg.h_thr, (size_t)c->p_alloc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		KG_CUDA(c, cudaEventRecord(stg.ev, c->stream));
 	}
-	// stream-ordered through a pinned staging slot: tiles already queued keep the thresholds they were submitted
-	// with, and the host never waits for the device here
-	kg_ctx::ThrStage &stg = c->thr_stage[c->thr_next];
-	c->thr_next = (c->thr_next + 1) & 3;
-	KG_CUDA(c, cudaEventSynchronize(stg.ev));
-	memcpy(stg.h_thr, c->h_thr.data(), (size_t)c->p_alloc * sizeof(double));
-	KG_CUDA(c, cudaMemcpyAsync(c->d_thr, stg.h_thr, (size_t)c->p_alloc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-	kg_status st = kg_tc_update_thresholds(c, stg.h_gc);
-	KG_CUDA(c, cudaEventRecord(stg.ev, c->stream));
-	return st;
+	return kg_tc_retune(c, false);
 }
 
 template <int R, int PT, int MODE>

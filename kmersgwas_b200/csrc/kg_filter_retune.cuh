@@ -14,7 +14,7 @@ struct KgRetuneParams {
 	uint32_t n_used;             // N
 	uint32_t p_pad, sbo_b, b_bytes;
 	uint32_t m_half;             // N / 2: slack tables hold m = 0 .. m_half
-	uint32_t pass_first, pass_count;   // phenotypes [pass_first, pass_first + pass_count) belong to this pass (<= 127)
+	uint32_t cols_per_pass;      // pass (= blockIdx.x) owns the phenotypes [pass * cols_per_pass, ...) (<= 127 of them)
 	const double *thr;           // [P] current thresholds (-1: heap not full)
 	const double *scale;         // [P] quantisation step s_p
 	const float *kappa0;         // [P]
@@ -23,10 +23,10 @@ struct KgRetuneParams {
 	const uint32_t *kidx;        // [N] K index (byte inside the operand rows) of memory column i
 	const float *slack;          // [P][m_half + 1] F_p(m)
 	uint32_t *col_of;            // [P] in/out: B / accumulator column of phenotype p inside its pass (0 = not assigned yet)
-	float *group_lines;          // [16][8] in/out: 4 intercepts + 4 slopes per group
-	int8_t *yq_image;            // [b_bytes] out (on reorder)
-	int32_t *tile_pheno;         // [p_pad] out (on reorder)
-	KgFilterGroupConst *gconst;  // [16] group slots
+	float *group_lines;          // [n_pass][16][8] in/out: 4 intercepts + 4 slopes per group
+	int8_t *yq_image;            // [n_pass][b_bytes] out (on reorder)
+	int32_t *tile_pheno;         // [n_pass][p_pad] out (on reorder)
+	KgFilterGroupConst *gconst;  // [n_pass][16] group slots
 	float *alpha_out, *kappa_out;   // [P] per-phenotype constants of the per-column test
 	unsigned long long *status;  // KG_SEL_ST_* (reorder counter) or NULL
 	uint32_t force;              // 1: rebuild regardless of the tightness test
@@ -36,7 +36,14 @@ __device__ __forceinline__ size_t kg_retune_b_offset(uint32_t sbo_b, uint32_t n,
 	return (size_t)(n % 8) * 16 + (size_t)(n / 8) * sbo_b + (size_t)(k / 16) * 128 + (k % 16);
 }
 
-__global__ void __launch_bounds__(256) kg_filter_retune_kernel(const KgRetuneParams prm) {
+__global__ void __launch_bounds__(256) kg_filter_retune_kernel(const KgRetuneParams prm_in) {
+	// this CTA's pass: shift the per-pass tables
+	KgRetuneParams prm = prm_in;
+	const uint32_t pass = blockIdx.x;
+	prm.group_lines += (size_t)pass * 16 * 8;
+	prm.yq_image += (size_t)pass * prm.b_bytes;
+	prm.tile_pheno += (size_t)pass * prm.p_pad;
+	prm.gconst += (size_t)pass * 16;
 	__shared__ float s_alpha[128], s_kappa[128];
 	__shared__ uint32_t s_col_new[128], s_col_cur[128];
 	__shared__ float s_amin[2][16];
@@ -44,7 +51,7 @@ __global__ void __launch_bounds__(256) kg_filter_retune_kernel(const KgRetunePar
 	__shared__ int s_reorder;
 	__shared__ float s_red[256];
 	__shared__ float s_slope;
-	const uint32_t P0 = prm.pass_first, PC = prm.pass_count, N = prm.n_used;
+	const uint32_t P0 = pass * prm.cols_per_pass, PC = min(prm.cols_per_pass, prm.n_pheno - P0), N = prm.n_used;
 	const uint32_t n_groups = prm.p_pad / 16;
 	const uint32_t tid = threadIdx.x;
 
@@ -95,7 +102,7 @@ __global__ void __launch_bounds__(256) kg_filter_retune_kernel(const KgRetunePar
 	__syncthreads();
 	if (tid == 0) {
 		s_reorder = prm.force || s_tight[1] < 0.0 || s_tight[0] > 1.01 * s_tight[1];
-		if (s_reorder && prm.status) prm.status[KG_SEL_ST_REORDERS] += 1;
+		if (s_reorder && prm.status) atomicAdd(prm.status + KG_SEL_ST_REORDERS, 1ull);
 	}
 	__syncthreads();
 	const bool reorder = s_reorder != 0;

@@ -45,7 +45,7 @@
 #define KG_F_ROWS 128            // rows per block = UMMA M
 #define KG_F_MAX_A_STAGES 8      // A stages live in tensor memory next to the two accumulator buffers:
 #define KG_F_TMEM_COLS 512       //   2 x p_pad accumulator columns + a_stages x 16 a_words columns <= 512
-#define KG_F_RAW_STAGES 4
+#define KG_F_RAW_STAGES 4         // most raw row-block stages (KgFilterParams::raw_stages of them are used: 4, fewer for wide tables)
 #define KG_F_EXPAND_WARP0 1
 #ifndef KG_F_EXPAND_WARPS
 #define KG_F_EXPAND_WARPS 12        // KG_F_EXPAND_WARPS / 4 per TMEM lane quarter share a stage's words
@@ -86,6 +86,7 @@ struct KgFilterParams {
 	uint32_t w_file;           // presence words per row
 	uint32_t a_words;          // u64 presence words per A stage (16 TMEM columns, 2 MMAs of K = 32 each); as many as
 	                           // fit: every stage hand-off costs a barrier round trip, so few large stages win
+	uint32_t raw_stages;       // raw row-block stages in shared memory, 2 .. KG_F_RAW_STAGES
 	uint32_t a_stages;         // 2 .. KG_F_MAX_A_STAGES
 	uint32_t nc;               // A stages per row block = ceil(w_file / a_words)
 	uint32_t p_pad;            // UMMA N (multiple of 16, <= 256): column 0 = all-ones (row popcount), the phenotypes follow
@@ -112,8 +113,8 @@ struct KgFilterParams {
 };
 
 __host__ __device__ inline uint32_t kg_filter_raw_stage_bytes(uint32_t w_file) { return KG_F_ROWS * 8u * (w_file + 1); }
-__host__ __device__ inline size_t kg_filter_smem_bytes(uint32_t w_file, uint32_t b_bytes, uint32_t p_pad) {
-	return 1024 /*alignment slack*/ + (size_t)b_bytes + (size_t)KG_F_RAW_STAGES * kg_filter_raw_stage_bytes(w_file) + (size_t)(p_pad / 16) * sizeof(KgFilterGroupConst) + 320;
+__host__ __device__ inline size_t kg_filter_smem_bytes(uint32_t w_file, uint32_t b_bytes, uint32_t p_pad, uint32_t raw_stages) {
+	return 1024 /*alignment slack*/ + (size_t)b_bytes + (size_t)raw_stages * kg_filter_raw_stage_bytes(w_file) + (size_t)(p_pad / 16) * sizeof(KgFilterGroupConst) + 320;
 }
 // K index (byte inside the A / B operands) of file column `col`.  The expander (below) turns 16 presence bits into
 // 4 registers with 4 PRMTs: register b holds the samples 4 n + b (n = byte inside the register), i.e. inside every
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 	uint8_t *sB = base;
 	const uint32_t raw_stage_bytes = kg_filter_raw_stage_bytes(prm.w_file);
 	uint8_t *sRaw = sB + prm.b_bytes;
-	KgFilterGroupConst *sConst = reinterpret_cast<KgFilterGroupConst *>(sRaw + KG_F_RAW_STAGES * raw_stage_bytes);
+	KgFilterGroupConst *sConst = reinterpret_cast<KgFilterGroupConst *>(sRaw + prm.raw_stages * raw_stage_bytes);
 	uint64_t *bars = reinterpret_cast<uint64_t *>(sConst + prm.p_pad / 16);
 	uint64_t *raw_full = bars, *raw_empty = bars + KG_F_RAW_STAGES;
 	uint64_t *a_full = bars + 2 * KG_F_RAW_STAGES, *a_empty = a_full + KG_F_MAX_A_STAGES;
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 			}
 			uint32_t it = 0;
 			for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, it++) {
-				const uint32_t st = it % KG_F_RAW_STAGES, use = it / KG_F_RAW_STAGES;
+				const uint32_t st = it % prm.raw_stages, use = it / prm.raw_stages;
 				kg_mbar_wait(&raw_empty[st], (use & 1) ^ 1);
 				const uint64_t r0 = (uint64_t)blk * KG_F_ROWS;
 				const uint32_t valid = (uint32_t)min((uint64_t)KG_F_ROWS, prm.n_rows - r0);
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 			}
 			__syncwarp();
 			if (lane == 0) kg_mbar_arrive(&raw_empty[rst]);
-			if (++rst == KG_F_RAW_STAGES) { rst = 0; r_par ^= 1; }
+			if (++rst == prm.raw_stages) { rst = 0; r_par ^= 1; }
 		}
 	} else {
 		// ===================== epilogue: MAC filter + bound test =====================

@@ -127,41 +127,6 @@ extern "C" kg_status kg_select_begin(kg_ctx *c, const uint64_t *k_best, uint32_t
 	return KG_OK;
 }
 
-// re-tune the tensor filter from the device thresholds (no-op when the filter is unavailable for the shape)
-static kg_status kg_sel_retune(kg_ctx *c, bool force) {
-	KgTcState &tc = c->tc;
-	if (!tc.scan_ready) return KG_OK;
-	KgRetuneParams r;
-	memset(&r, 0, sizeof r);
-	r.n_pheno = c->n_pheno;
-	r.n_used = (uint32_t)c->n_used;
-	r.p_pad = tc.p_pad;
-	r.sbo_b = tc.sbo_b;
-	r.b_bytes = tc.b_bytes;
-	r.m_half = (uint32_t)c->n_used / 2;
-	r.pass_first = 0;
-	r.pass_count = c->n_pheno;
-	r.thr = c->d_thr;
-	r.scale = tc.d_scale;
-	r.kappa0 = tc.d_kappa0;
-	r.degenerate = tc.d_degenerate;
-	r.q = tc.d_q;
-	r.kidx = tc.d_kidx;
-	r.slack = tc.d_slack;
-	r.col_of = tc.d_col_of;
-	r.group_lines = tc.d_group_lines;
-	r.yq_image = tc.d_yq;
-	r.tile_pheno = tc.d_tile_pheno;
-	r.gconst = tc.d_gconst;
-	r.alpha_out = reinterpret_cast<float *>(tc.d_gconst + 16);
-	r.kappa_out = r.alpha_out + c->n_pheno;
-	r.status = c->sel.active ? c->sel.d_status : nullptr;
-	r.force = force ? 1u : 0u;
-	kg_filter_retune_kernel<<<1, 256, 0, c->stream>>>(r);
-	KG_LAUNCH_CHECK(c);
-	return KG_OK;
-}
-
 // after a round's scan kernels: bookkeeping, heap replay, filter constants for the next round
 static kg_status kg_sel_finish_round(kg_ctx *c, uint64_t n_rows, uint64_t first_row_id, bool filter_counters) {
 	KgSelState &s = c->sel;
@@ -173,7 +138,7 @@ static kg_status kg_sel_finish_round(kg_ctx *c, uint64_t n_rows, uint64_t first_
 	prm.first_row = first_row_id;
 	kg_select_replay_kernel<false><<<s.n_pheno, KG_SEL_THREADS, s.smem, c->stream>>>(prm);
 	KG_LAUNCH_CHECK(c);
-	kg_status st = kg_sel_retune(c, false);
+	kg_status st = kg_tc_retune(c, false);
 	timing_end(c);
 	return st;
 }
@@ -367,7 +332,7 @@ extern "C" kg_status kg_select_import(kg_ctx *c, const uint64_t *state, uint64_t
 	st_words[KG_SEL_ST_ROWS_APPLIED] = rows_applied;
 	st_words[KG_SEL_ST_KEPT] = rows_kept;
 	KG_CUDA(c, cudaMemcpyAsync(s.d_status, st_words, sizeof st_words, cudaMemcpyHostToDevice, c->stream));
-	kg_status st = kg_sel_retune(c, true);
+	kg_status st = kg_tc_retune(c, true);
 	if (st != KG_OK) return st;
 	KG_CUDA(c, cudaStreamSynchronize(c->stream));
 	s.rows_submitted = rows_applied;
@@ -490,7 +455,7 @@ extern "C" kg_status kg_select_replay(kg_ctx *c, const uint64_t *entries, const 
 	add[0] += s.h_status[KG_SEL_ST_ROWS_APPLIED];
 	add[1] += s.h_status[KG_SEL_ST_KEPT];
 	KG_CUDA(c, cudaMemcpyAsync(s.d_status + KG_SEL_ST_ROWS_APPLIED, add, sizeof add, cudaMemcpyHostToDevice, c->stream));
-	st = kg_sel_retune(c, false);
+	st = kg_tc_retune(c, false);
 	timing_end(c);
 	if (st != KG_OK) return st;
 	KG_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -3,6 +3,7 @@
 #pragma once
 #include <cfloat>
 
+#include "kg_filter_retune.cuh"
 #include "kg_kinship_tc.cuh"
 #include "kg_scan_filter.cuh"
 
@@ -20,16 +21,12 @@ static void kg_tc_free(KgTcState *tc) {
 	cudaFree(tc->d_col_of); cudaFree(tc->d_group_lines);
 	tc->d_scale = nullptr; tc->d_kappa0 = nullptr; tc->d_degenerate = nullptr; tc->d_q = nullptr; tc->d_kidx = nullptr;
 	tc->d_col_of = nullptr; tc->d_group_lines = nullptr;
-	for (int i = 0; i < 2; i++) {
-		if (tc->img_ev[i]) { cudaEventDestroy(tc->img_ev[i]); tc->img_ev[i] = nullptr; }
-		if (tc->h_img_pinned[i]) { cudaFreeHost(tc->h_img_pinned[i]); tc->h_img_pinned[i] = nullptr; }
-	}
 }
 static bool kg_tc_scan_available(const kg_ctx *c) { return c->tc.scan_ready; }
 static bool kg_tc_kinship_available(const kg_ctx *c) { return c->tc.kin_ready; }
 
-// Auto engine choice: the filter needs a threshold for every phenotype (heaps full); it then pays off unless
-// it fails to rule out most rows (every listed row is re-scored by the exact kernel anyway).
+// Auto engine choice (host-driven mode): the filter needs a threshold for every phenotype (heaps full); it then pays off
+// unless it fails to rule out most rows (every listed row is re-scored by the exact kernel anyway).
 static bool kg_tc_scan_profitable(const kg_ctx *c) {
 	if (!c->tc.scan_ready) return false;
 	for (uint32_t p = 0; p < c->n_pheno; p++)
@@ -42,140 +39,46 @@ static size_t kg_tc_b_offset(const KgTcState &tc, uint32_t n, uint32_t k) {
 	return (size_t)(n % 8) * 16 + (size_t)(n / 8) * tc.sbo_b + (size_t)(k / 16) * 128 + (k % 16);
 }
 
-static float kg_float_down(double x) {  // largest float <= x
-	float f = (float)x;
-	if ((double)f > x) f = nextafterf(f, -INFINITY);
-	return f;
-}
 static float kg_float_up(double x) {  // smallest float >= x
 	float f = (float)x;
 	if ((double)f < x) f = nextafterf(f, INFINITY);
 	return f;
 }
 
-// Column order + per-group (alpha, kappa) from the current thresholds, and the B image in that order
-// (see kg_scan_filter.cuh header).  Column 0 = all-ones (popcount); phenotypes follow sorted by alpha.
-// upload = false: the caller ships the group slots + per-phenotype constants itself (kg_round_constants_kernel)
-static kg_status kg_tc_update_thresholds(kg_ctx *c, KgFilterGroupConst *gc_pinned, bool upload = true) {
+// Bound constants of the tensor filter from the thresholds in d_thr: per-phenotype (alpha, kappa), the column order
+// sorted by alpha, the B operand image in that order, the per-group loosest constants and slack tangents.  All of it
+// is computed ON THE DEVICE (kg_filter_retune_kernel, one CTA per pass), stream-ordered behind whatever wrote d_thr
+// (kg_scan_set_thresholds in host-driven mode, the heap replay in device-selection mode).
+static kg_status kg_tc_retune(kg_ctx *c, bool force) {
 	KgTcState &tc = c->tc;
 	if (!tc.scan_ready) return KG_OK;
-	const uint32_t P = c->n_pheno, N = (uint32_t)c->n_used;
-	std::vector<float> alpha(P), kappa(P);
-	for (uint32_t p = 0; p < P; p++) {
-		const double thr = c->h_thr[p];
-		if (tc.degenerate[p] || !(thr >= 0.0) || !std::isfinite(thr)) {
-			alpha[p] = 0.0f;      // no bound: every kept row is listed
-			kappa[p] = 3.0e38f;
-		} else {
-			const double a = std::sqrt(thr) / ((double)N * tc.scale[p]) * (1.0 - 1e-6);
-			alpha[p] = kg_float_down(a * KG_F_ONE);
-			kappa[p] = kg_float_up((double)tc.kappa[p] * KG_F_ONE);
-		}
-	}
-	std::vector<uint32_t> order(P);
-	for (uint32_t p = 0; p < P; p++) order[p] = p;
-	std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return alpha[x] < alpha[y]; });
-	std::vector<uint32_t> col_of(P);
-	for (uint32_t k = 0; k < P; k++) col_of[order[k]] = 1 + k;
-	const uint32_t n_groups = tc.p_pad / 16;
-	// tightness of a column assignment = sum over phenotypes of the alpha their group tests with
-	auto tightness = [&](const std::vector<uint32_t> &cols) {
-		std::vector<float> amin(n_groups, INFINITY);
-		for (uint32_t p = 0; p < P; p++) amin[cols[p] / 16] = std::min(amin[cols[p] / 16], alpha[p]);
-		double t = 0.0;
-		for (uint32_t p = 0; p < P; p++) t += amin[cols[p] / 16];
-		return t;
-	};
-	// keep the uploaded column order while it is within 1 % of the sorted one (thresholds drift together)
-	const bool reorder = tc.col_of.size() != P || tightness(col_of) > 1.01 * tightness(tc.col_of);
-	if (!reorder) col_of = tc.col_of;
-	if (n_groups > 16) KG_FAIL(c, KG_ERR_STATE, "filter group constants exceed the staging slot");
-	if (reorder) {
-		// slack lines of every group for the new column assignment: upper tangents of
-		// U_g(m) = max over the group's phenotypes of F_p(m), m in [0, N/2]  (F_p: kg_tc_prepare_scan)
-		const uint32_t M = N / 2;
-		tc.group_lines.assign((size_t)n_groups * 8, 0.0f);
-		std::vector<double> U(M + 1);
-		for (uint32_t g = 0; g < n_groups; g++) {
-			std::fill(U.begin(), U.end(), 0.0);
-			bool any = false;
-			for (uint32_t p = 0; p < P; p++) {
-				if (col_of[p] / 16 != g || tc.degenerate[p]) continue;
-				any = true;
-				const float *F = tc.slack_table.data() + (size_t)p * (M + 1);
-				for (uint32_t m = 0; m <= M; m++) U[m] = std::max(U[m], (double)F[m]);
-			}
-			if (!any) continue;
-			const uint32_t anchor[4] = {std::max(1u, M / 16), std::max(1u, M / 5), std::max(1u, M / 2), std::max(1u, M - 1)};
-			for (int k = 0; k < 4; k++) {
-				const uint32_t m0 = std::min(anchor[k], M > 0 ? M - 1 : 0);
-				const double slope = M > 0 ? std::max(0.0, U[std::min(m0 + 1, M)] - U[m0]) : 0.0;
-				double icpt = 0.0;
-				for (uint32_t m = 0; m <= M; m++) icpt = std::max(icpt, U[m] - slope * (double)m);
-				tc.group_lines[(size_t)g * 8 + k] = kg_float_up(icpt * (1.0 + 1e-6) * KG_F_ONE);
-				tc.group_lines[(size_t)g * 8 + 4 + k] = kg_float_up(slope * (1.0 + 1e-6) * KG_F_ONE);
-			}
-		}
-	}
-	KgFilterGroupConst *gc = gc_pinned;
-	for (uint32_t g = 0; g < n_groups; g++) {
-		gc[g].alpha = INFINITY;
-		gc[g].kappa = 0.0f;
-		for (int k = 0; k < 4; k++) {
-			gc[g].line_a[k] = tc.group_lines[(size_t)g * 8 + k];
-			gc[g].line_b[k] = tc.group_lines[(size_t)g * 8 + 4 + k];
-		}
-		gc[g].pad_[0] = gc[g].pad_[1] = 0.0f;
-	}
-	for (uint32_t p = 0; p < P; p++) {
-		KgFilterGroupConst &g = gc[col_of[p] / 16];
-		g.alpha = std::min(g.alpha, alpha[p]);
-		g.kappa = std::max(g.kappa, kappa[p]);
-	}
-	if (reorder) {
-		// pinned image ring: the copy is stream-ordered behind the kernels still reading the old image
-		if (!tc.h_img_pinned[0]) {
-			for (int i = 0; i < 2; i++) {
-				KG_CUDA(c, cudaMallocHost((void **)&tc.h_img_pinned[i], tc.b_bytes + tc.p_pad * sizeof(int32_t) + P * sizeof(uint32_t) + 16 * 8 * sizeof(float)));
-				KG_CUDA(c, cudaEventCreateWithFlags(&tc.img_ev[i], cudaEventDisableTiming));
-			}
-			tc.img_bytes = tc.b_bytes;
-		}
-		const int slot = tc.img_next;
-		tc.img_next ^= 1;
-		KG_CUDA(c, cudaEventSynchronize(tc.img_ev[slot]));
-		int8_t *img = tc.h_img_pinned[slot];
-		memset(img, 0, tc.b_bytes);
-		// The A operand holds -1 (0xFF) for a set presence bit (kg_scan_filter.cuh), so B is stored NEGATED:
-		// (-1) * (-q) = q.  Column 0: -1 on every used file column -> accumulator = row popcount.
-		for (uint32_t i = 0; i < N; i++)
-			img[kg_tc_b_offset(tc, 0, kg_filter_k_of_column(c->map_word[i] * 64 + c->map_bit[i]))] = -1;
-		for (uint32_t p = 0; p < P; p++) {
-			const int8_t *q = tc.h_q.data() + (size_t)p * N;
-			for (uint32_t i = 0; i < N; i++)
-				img[kg_tc_b_offset(tc, col_of[p], kg_filter_k_of_column(c->map_word[i] * 64 + c->map_bit[i]))] = (int8_t)-q[i];   // |q| <= 127
-		}
-		tc.col_of = col_of;
-		// exact-kernel tiles of 8 filter columns -> phenotype index (staged at the tail of the pinned image slot)
-		int32_t *tp = reinterpret_cast<int32_t *>(img + tc.b_bytes);
-		for (uint32_t k = 0; k < tc.p_pad; k++) tp[k] = -1;
-		for (uint32_t p = 0; p < P; p++) tp[col_of[p]] = (int32_t)p;
-		KG_CUDA(c, cudaMemcpyAsync(tc.d_tile_pheno, tp, tc.p_pad * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-		KG_CUDA(c, cudaMemcpyAsync(tc.d_yq, img, tc.b_bytes, cudaMemcpyHostToDevice, c->stream));
-		// device twins of the column assignment (kg_filter_retune_kernel continues from them; the debug entry point reads them)
-		uint32_t *cd = reinterpret_cast<uint32_t *>(tp + tc.p_pad);
-		for (uint32_t p = 0; p < P; p++) cd[p] = col_of[p];
-		float *gl = reinterpret_cast<float *>(cd + P);
-		for (size_t i = 0; i < 16 * 8; i++) gl[i] = i < tc.group_lines.size() ? tc.group_lines[i] : 0.0f;
-		KG_CUDA(c, cudaMemcpyAsync(tc.d_col_of, cd, P * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-		KG_CUDA(c, cudaMemcpyAsync(tc.d_group_lines, gl, 16 * 8 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-		KG_CUDA(c, cudaEventRecord(tc.img_ev[slot], c->stream));
-	}
-	// per-phenotype constants of the per-column test follow the 16 group slots (same staging slot, one copy)
-	float *pc = reinterpret_cast<float *>(gc + 16);
-	for (uint32_t p = 0; p < P; p++) { pc[p] = alpha[p]; pc[P + p] = kappa[p]; }
-	if (upload)
-		KG_CUDA(c, cudaMemcpyAsync(tc.d_gconst, gc, 16 * sizeof(KgFilterGroupConst) + 2 * (size_t)P * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+	KgRetuneParams r;
+	memset(&r, 0, sizeof r);
+	r.n_pheno = c->n_pheno;
+	r.n_used = (uint32_t)c->n_used;
+	r.p_pad = tc.p_pad;
+	r.sbo_b = tc.sbo_b;
+	r.b_bytes = tc.b_bytes;
+	r.m_half = (uint32_t)c->n_used / 2;
+	r.cols_per_pass = tc.cols_per_pass;
+	r.thr = c->d_thr;
+	r.scale = tc.d_scale;
+	r.kappa0 = tc.d_kappa0;
+	r.degenerate = tc.d_degenerate;
+	r.q = tc.d_q;
+	r.kidx = tc.d_kidx;
+	r.slack = tc.d_slack;
+	r.col_of = tc.d_col_of;
+	r.group_lines = tc.d_group_lines;
+	r.yq_image = tc.d_yq;
+	r.tile_pheno = tc.d_tile_pheno;
+	r.gconst = tc.d_gconst;
+	r.alpha_out = reinterpret_cast<float *>(tc.d_gconst + 16 * (size_t)tc.n_pass);
+	r.kappa_out = r.alpha_out + c->n_pheno;
+	r.status = c->sel.active ? c->sel.d_status : nullptr;
+	r.force = force ? 1u : 0u;
+	kg_filter_retune_kernel<<<tc.n_pass, 256, 0, c->stream>>>(r);
+	KG_LAUNCH_CHECK(c);
 	return KG_OK;
 }
 
@@ -185,7 +88,6 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	tc.use_filter = true;
 	cudaFree(tc.d_yq); cudaFree(tc.d_gconst);
 	tc.d_yq = nullptr; tc.d_gconst = nullptr;
-	tc.col_of.clear();
 	// the filter's list buffers are sized for the phenotype count they were allocated with ([p_pad / 16][capacity]):
 	// a new phenotype set starts from scratch (kg_tc_ensure_row_list reallocates on the next tile)
 	cudaFree(tc.d_row_list); cudaFree(tc.d_group_list); cudaFree(tc.d_ent_q); cudaFree(tc.d_ent_n1); cudaFree(tc.d_pairs);
@@ -196,17 +98,30 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	cudaFree(tc.d_col_of); cudaFree(tc.d_group_lines);
 	tc.d_scale = nullptr; tc.d_kappa0 = nullptr; tc.d_degenerate = nullptr; tc.d_q = nullptr; tc.d_kidx = nullptr;
 	tc.d_col_of = nullptr; tc.d_group_lines = nullptr;
-	for (int i = 0; i < 2; i++) {
-		if (tc.img_ev[i]) { cudaEventSynchronize(tc.img_ev[i]); cudaEventDestroy(tc.img_ev[i]); tc.img_ev[i] = nullptr; }
-		if (tc.h_img_pinned[i]) { cudaFreeHost(tc.h_img_pinned[i]); tc.h_img_pinned[i] = nullptr; }
-	}
 	const uint32_t P = c->n_pheno, N = (uint32_t)c->n_used;
-	tc.p_pad = (P + 1 + 15) / 16 * 16;  // + the all-ones column
+	if (c->min_count < 1) { tc.why_unavailable = "min_count = 0 (rows with an empty group have no finite bound)"; return KG_OK; }
 	tc.sbo_b = ((c->w_file + 1) / 2) * 1024;       // K_pad = 128 * ceil(w_file / 2) bytes per B column, 1024 B per 128
+	if (tc.sbo_b > 0x3FFFu * 16) { tc.why_unavailable = "table too wide for the B descriptor stride"; return KG_OK; }
+	// Shape of a pass: P_pad = 16 .. 128 accumulator columns (column 0 = all-ones, so up to 127 phenotypes) whose B image
+	// (P_pad x K_pad int8) must fit shared memory next to 2 .. 4 raw row-block stages.  More phenotypes than a pass holds
+	// -> several passes over the same tile (BASELINE config 5: 1001 phenotypes; wide tables: few columns per pass).
+	const uint32_t pp_want = std::min<uint32_t>(128, (P + 1 + 15) / 16 * 16);
+	uint32_t best_pp = 0, best_rs = 0;
+	for (uint32_t rs = KG_F_RAW_STAGES; rs >= 2; rs--)
+		for (uint32_t pp = pp_want; pp >= 16; pp -= 16)
+			if (kg_filter_smem_bytes(c->w_file, (pp / 8) * tc.sbo_b, pp, rs) <= 227u * 1024) {
+				if (pp > best_pp) { best_pp = pp; best_rs = rs; }
+				break;
+			}
+	if (best_pp == 0) { tc.why_unavailable = "a 16-column phenotype tile (P_pad x K_pad int8) does not fit shared memory"; return KG_OK; }
+	tc.n_pass = (P + (best_pp - 1) - 1) / (best_pp - 1);
+	tc.cols_per_pass = (P + tc.n_pass - 1) / tc.n_pass;
+	tc.p_pad = (tc.cols_per_pass + 1 + 15) / 16 * 16;
+	tc.raw_stages = best_rs;
 	tc.b_bytes = (tc.p_pad / 8) * tc.sbo_b;
 	tc.tcols = tc.p_pad;
 	// tensor memory: 2 accumulator buffers + the A stages (16 columns per presence word); as few, as large stages as fit
-	if (tc.p_pad <= 128) {
+	{
 		const uint32_t a_cols = KG_F_TMEM_COLS - 2 * tc.p_pad;
 		tc.a_words = std::max(1u, std::min<uint32_t>(c->w_file, a_cols / 32));           // at least two stages (few large stages measured best)
 		tc.a_words = std::min<uint32_t>(tc.a_words, KG_F_MAX_WPT * KG_F_NSUB);            // register budget of the expanders
@@ -219,15 +134,7 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 		tc.a_stages = std::max(2u, std::min<uint32_t>(KG_F_MAX_A_STAGES, a_cols / (16 * tc.a_words)));
 		tc.nc = (c->w_file + tc.a_words - 1) / tc.a_words;
 	}
-	if (c->min_count < 1) { tc.why_unavailable = "min_count = 0 (rows with an empty group have no finite bound)"; return KG_OK; }
-	// TMEM budget: 2 accumulator buffers of tcols columns + 8 A stages of 32 columns in 512 columns
-	if (tc.p_pad > 128) { tc.why_unavailable = "more than 127 phenotype columns per pass"; return KG_OK; }
-	if (tc.sbo_b > 0x3FFFu * 16) { tc.why_unavailable = "table too wide for the B descriptor stride"; return KG_OK; }
-	const size_t smem = kg_filter_smem_bytes(c->w_file, tc.b_bytes, tc.p_pad);
-	if (smem > 227u * 1024) {
-		tc.why_unavailable = "phenotype tile (P_pad x K_pad int8) does not fit shared memory";
-		return KG_OK;
-	}
+	const size_t smem = kg_filter_smem_bytes(c->w_file, tc.b_bytes, tc.p_pad, tc.raw_stages);
 	tc.smem_bytes = smem;
 
 	// quantise: centred, symmetric int8 per phenotype
@@ -290,16 +197,16 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 		tc.scale[p] = s;
 		tc.kappa[p] = kg_float_up(kappa);
 	}
-	cudaError_t e = cudaMalloc((void **)&tc.d_yq, tc.b_bytes);
+	cudaError_t e = cudaMalloc((void **)&tc.d_yq, (size_t)tc.n_pass * tc.b_bytes);
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc quantised phenotypes: %s", cudaGetErrorString(e));
 	cudaFree(tc.d_tile_pheno); cudaFree(tc.d_group_count);
 	tc.d_tile_pheno = nullptr; tc.d_group_count = nullptr;
-	e = cudaMalloc((void **)&tc.d_tile_pheno, tc.p_pad * sizeof(int32_t));
+	e = cudaMalloc((void **)&tc.d_tile_pheno, (size_t)tc.n_pass * tc.p_pad * sizeof(int32_t));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc tile table: %s", cudaGetErrorString(e));
 	e = cudaMalloc((void **)&tc.d_group_count, (16 + 16) * sizeof(unsigned long long));   // + 32 u32 tile chunk counters
 	if (e == cudaSuccess) e = cudaMemset(tc.d_group_count, 0, (16 + 16) * sizeof(unsigned long long));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc group counters: %s", cudaGetErrorString(e));
-	e = cudaMalloc((void **)&tc.d_gconst, 16 * sizeof(KgFilterGroupConst) + 2 * (size_t)P * sizeof(float));
+	e = cudaMalloc((void **)&tc.d_gconst, (size_t)tc.n_pass * 16 * sizeof(KgFilterGroupConst) + 2 * (size_t)P * sizeof(float));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc filter constants: %s", cudaGetErrorString(e));
 	cudaFree(tc.d_slack);
 	tc.d_slack = nullptr;
@@ -312,7 +219,7 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 		std::vector<uint32_t> kidx(N);
 		for (uint32_t i = 0; i < N; i++) kidx[i] = kg_filter_k_of_column(c->map_word[i] * 64 + c->map_bit[i]);
 		std::vector<uint32_t> zero_cols(P, 0u);
-		std::vector<float> zero_lines(16 * 8, 0.0f);
+		std::vector<float> zero_lines((size_t)tc.n_pass * 16 * 8, 0.0f);
 		KG_CUDA(c, dev_alloc_copy(&tc.d_scale, tc.scale));
 		KG_CUDA(c, dev_alloc_copy(&tc.d_kappa0, tc.kappa));
 		KG_CUDA(c, dev_alloc_copy(&tc.d_degenerate, tc.degenerate));
@@ -335,10 +242,8 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	KG_CUDA(c, cudaFuncSetAttribute(kg_scan_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	tc.scan_ready = true;
 	tc.why_unavailable.clear();
-	kg_ctx::ThrStage &stg = c->thr_stage[c->thr_next];
-	c->thr_next = (c->thr_next + 1) & 3;
-	kg_status st = kg_tc_update_thresholds(c, stg.h_gc);
-	KG_CUDA(c, cudaEventRecord(stg.ev, c->stream));
+	// first images: every threshold is -1 (d_thr as kg_scan_set_phenotypes left it) -> alpha = 0, every kept row listed
+	kg_status st = kg_tc_retune(c, true);
 	KG_CUDA(c, cudaStreamSynchronize(c->stream));
 	return st;
 }
@@ -361,7 +266,7 @@ static kg_status kg_tc_aligned_tile(kg_ctx *c, const uint64_t *dev, uint64_t n_r
 	return KG_OK;
 }
 
-static KgFilterParams kg_tc_filter_params(kg_ctx *c, const uint64_t *dev, uint64_t n_rows) {
+static KgFilterParams kg_tc_filter_params(kg_ctx *c, const uint64_t *dev, uint64_t n_rows, uint32_t pass) {
 	KgTcState &tc = c->tc;
 	KgFilterParams f;
 	memset(&f, 0, sizeof f);
@@ -370,13 +275,14 @@ static KgFilterParams kg_tc_filter_params(kg_ctx *c, const uint64_t *dev, uint64
 	f.w_file = c->w_file;
 	f.nc = tc.nc;
 	f.a_words = tc.a_words;
+	f.raw_stages = tc.raw_stages;
 	f.a_stages = tc.a_stages;
 	f.p_pad = tc.p_pad;
 	f.tcols = tc.tcols;
-	f.yq_image = tc.d_yq;
+	f.yq_image = tc.d_yq + (size_t)pass * tc.b_bytes;
 	f.b_bytes = tc.b_bytes;
 	f.sbo_b = tc.sbo_b;
-	f.gconst = tc.d_gconst;
+	f.gconst = tc.d_gconst + (size_t)pass * 16;
 	f.n_used = (uint32_t)c->n_used;
 	f.min_count = (uint32_t)std::min<uint64_t>(c->min_count, 0xFFFFFFFFull);
 	f.row_list = tc.d_row_list;
@@ -387,7 +293,8 @@ static KgFilterParams kg_tc_filter_params(kg_ctx *c, const uint64_t *dev, uint64
 	f.ent_q = tc.d_ent_q;
 	f.ent_n1 = tc.d_ent_n1;
 	f.qcap = tc.use_pairs ? tc.qcap : 0;
-	f.kept_count = c->sel.active ? c->sel.d_status + KG_SEL_ST_ROUND_KEPT : c->d_counters + 1;
+	// kept rows are counted once per tile (pass 0); the other passes count into a scratch word
+	f.kept_count = pass != 0 ? c->d_counters + 4 : (c->sel.active ? c->sel.d_status + KG_SEL_ST_ROUND_KEPT : c->d_counters + 1);
 	f.n_issuers = tc.n_issuers ? tc.n_issuers : KG_F_MMA_WARPS;
 	f.dbg = tc.dbg_flags;
 	return f;
@@ -424,8 +331,8 @@ static kg_status kg_tc_ensure_row_list(kg_ctx *c, uint64_t n_rows) {
 	return KG_OK;
 }
 
-// End of a filtered tile: interval totals += the tile's counts ([5] listed rows, [6] (row, group) entries, [7] (row,
-// phenotype) pairs), then the per-tile counters are zeroed for the next tile (no memsets in front of the filter launch).
+// End of a filtered tile pass: interval totals += the tile's counts ([5] listed rows, [6] (row, group) entries, [7] (row,
+// phenotype) pairs), then the per-tile counters are zeroed for the next pass / tile (no memsets in front of the filter launch).
 __global__ void kg_tile_end_kernel(unsigned long long *interval_cnt, unsigned long long *tile_cnt, uint32_t n_groups) {
 	if (threadIdx.x == 0) {
 		unsigned long long t = 0;
@@ -439,7 +346,8 @@ __global__ void kg_tile_end_kernel(unsigned long long *interval_cnt, unsigned lo
 	if (threadIdx.x < 32) tile_cnt[threadIdx.x] = 0;
 }
 
-// filter the tile on the tensor cores, then re-score the rows it could not rule out with the exact kernel
+// filter the tile on the tensor cores (one pass per <= 127 phenotype columns), then re-score the (row, phenotype) pairs
+// it could not rule out with the exact kernels
 static kg_status kg_tc_scan_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_rows, uint64_t first_row_id) {
 	KgTcState &tc = c->tc;
 	const uint64_t *dev = nullptr;
@@ -451,85 +359,88 @@ static kg_status kg_tc_scan_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_r
 		st = ensure_squeeze_scratch(c, n_rows);
 		if (st != KG_OK) return st;
 	}
-	// per-tile counters (d_counters[2], tc.d_group_count[0..31]) are zero here: zeroed at allocation / interval open and
-	// by kg_tile_end_kernel after every tile
-	KgFilterParams f = kg_tc_filter_params(c, dev, n_rows);
 	const uint32_t n_blocks = (uint32_t)((n_rows + KG_F_ROWS - 1) / KG_F_ROWS);
 	const unsigned grid = std::max(1u, std::min<uint32_t>(n_blocks, (uint32_t)c->sm_count));
-	timing_begin(c, KG_KERNEL_SCAN_FILTER, n_rows);
-	kg_scan_filter_kernel<0><<<grid, KG_F_THREADS, tc.smem_bytes, c->stream>>>(f);
-	timing_end(c);
-	KG_LAUNCH_CHECK(c);
-
-	KgRowView view{dev, n_rows, c->w_file + 1, c->w_file};
-	uint32_t compact = 0;
-	if (!c->identity) {
-		// memory-order copies of the listed rows only
-		const unsigned sg = (unsigned)c->sm_count * 8;
-		timing_begin(c, KG_KERNEL_AUX, 0);
-		kg_squeeze_kernel<<<sg, 256, 0, c->stream>>>(view, c->d_map_mem, (uint32_t)c->n_used, c->w_mem, c->d_squeezed,
-		                                            tc.d_row_list, c->d_counters + 2);
+	const float *alpha_all = reinterpret_cast<const float *>(tc.d_gconst + 16 * (size_t)tc.n_pass);
+	for (uint32_t pass = 0; pass < tc.n_pass; pass++) {
+		// per-tile counters (d_counters[2], tc.d_group_count[0..31]) are zero here: zeroed at allocation / interval open and
+		// by kg_tile_end_kernel / kg_select_round_end_kernel after every pass
+		KgFilterParams f = kg_tc_filter_params(c, dev, n_rows, pass);
+		timing_begin(c, KG_KERNEL_SCAN_FILTER, n_rows);
+		kg_scan_filter_kernel<0><<<grid, KG_F_THREADS, tc.smem_bytes, c->stream>>>(f);
 		timing_end(c);
 		KG_LAUNCH_CHECK(c);
-		view = KgRowView{c->d_squeezed, n_rows, c->w_mem + 1, c->w_mem};
-		compact = 1;
-	}
-	KgScanParams prm = scan_params(c, view, first_row_id);
-	prm.row_list = tc.d_row_list;
-	prm.group_list = tc.d_group_list;
-	prm.group_count = tc.d_group_count;
-	prm.group_cap = tc.row_list_cap;
-	prm.tile_pheno = tc.d_tile_pheno;
-	prm.tile_chunk_counter = reinterpret_cast<unsigned int *>(tc.d_group_count + 16);
-	prm.list_compact = compact;
-	timing_begin(c, KG_KERNEL_SCAN_REFINE, 0);
-	if (tc.use_pairs && tc.pair_limit != 0) {
-		// short group lists: per-column re-test, then one phenotype per (row, phenotype) pair
-		unsigned long long *pair_count = tc.d_group_count + 24;   // [24] pairs [25] overflow flag (both zeroed above)
-		KgPairSelectParams ps;
-		memset(&ps, 0, sizeof ps);
-		ps.group_count = tc.d_group_count;
-		ps.group_list = tc.d_group_list;
-		ps.group_cap = tc.row_list_cap;
-		ps.ent_q = tc.d_ent_q;
-		ps.ent_n1 = tc.d_ent_n1;
-		ps.qcap = tc.qcap;
-		const uint64_t dense_limit = tc.pair_limit < 0 ? tc.qcap : std::min<uint64_t>(tc.qcap, (uint64_t)tc.pair_limit);
-		ps.dense_limit = dense_limit;
-		ps.n_groups = tc.p_pad / 16;
-		ps.n_used = (uint32_t)c->n_used;
-		ps.tile_pheno = tc.d_tile_pheno;
-		ps.alpha = reinterpret_cast<const float *>(tc.d_gconst + 16);
-		ps.kappa = ps.alpha + c->n_pheno;
-		ps.slack = tc.d_slack;
-		ps.pairs = tc.d_pairs;
-		ps.pair_count = pair_count;
-		ps.pair_cap = (uint64_t)ps.n_groups * tc.qcap * 16;
-		ps.overflow = pair_count + 1;
-		const uint64_t entries = std::min<uint64_t>((uint64_t)ps.n_groups * tc.qcap, (uint64_t)ps.n_groups * n_rows);
-		const unsigned sel_grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((entries + 255) / 256, (uint64_t)c->sm_count * 8));
-		kg_pair_select_kernel<<<sel_grid, 256, 0, c->stream>>>(ps);
+
+		KgRowView view{dev, n_rows, c->w_file + 1, c->w_file};
+		uint32_t compact = 0;
+		if (!c->identity) {
+			// memory-order copies of the listed rows only
+			const unsigned sg = (unsigned)c->sm_count * 8;
+			timing_begin(c, KG_KERNEL_AUX, 0);
+			kg_squeeze_kernel<<<sg, 256, 0, c->stream>>>(view, c->d_map_mem, (uint32_t)c->n_used, c->w_mem, c->d_squeezed,
+			                                            tc.d_row_list, c->d_counters + 2);
+			timing_end(c);
+			KG_LAUNCH_CHECK(c);
+			view = KgRowView{c->d_squeezed, n_rows, c->w_mem + 1, c->w_mem};
+			compact = 1;
+		}
+		KgScanParams prm = scan_params(c, view, first_row_id);
+		prm.row_list = tc.d_row_list;
+		prm.group_list = tc.d_group_list;
+		prm.group_count = tc.d_group_count;
+		prm.group_cap = tc.row_list_cap;
+		prm.tile_pheno = tc.d_tile_pheno + (size_t)pass * tc.p_pad;
+		prm.tile_chunk_counter = reinterpret_cast<unsigned int *>(tc.d_group_count + 16);
+		prm.list_compact = compact;
+		timing_begin(c, KG_KERNEL_SCAN_REFINE, 0);
+		if (tc.use_pairs && tc.pair_limit != 0) {
+			// short group lists: per-column re-test, then one phenotype per (row, phenotype) pair
+			unsigned long long *pair_count = tc.d_group_count + 24;   // [24] pairs [25] overflow flag (both zeroed above)
+			KgPairSelectParams ps;
+			memset(&ps, 0, sizeof ps);
+			ps.group_count = tc.d_group_count;
+			ps.group_list = tc.d_group_list;
+			ps.group_cap = tc.row_list_cap;
+			ps.ent_q = tc.d_ent_q;
+			ps.ent_n1 = tc.d_ent_n1;
+			ps.qcap = tc.qcap;
+			const uint64_t dense_limit = tc.pair_limit < 0 ? tc.qcap : std::min<uint64_t>(tc.qcap, (uint64_t)tc.pair_limit);
+			ps.dense_limit = dense_limit;
+			ps.n_groups = tc.p_pad / 16;
+			ps.n_used = (uint32_t)c->n_used;
+			ps.tile_pheno = prm.tile_pheno;
+			ps.alpha = alpha_all;
+			ps.kappa = ps.alpha + c->n_pheno;
+			ps.slack = tc.d_slack;
+			ps.pairs = tc.d_pairs;
+			ps.pair_count = pair_count;
+			ps.pair_cap = (uint64_t)ps.n_groups * tc.qcap * 16;
+			ps.overflow = pair_count + 1;
+			const uint64_t entries = std::min<uint64_t>((uint64_t)ps.n_groups * tc.qcap, (uint64_t)ps.n_groups * n_rows);
+			const unsigned sel_grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((entries + 255) / 256, (uint64_t)c->sm_count * 8));
+			kg_pair_select_kernel<<<sel_grid, 256, 0, c->stream>>>(ps);
+			KG_LAUNCH_CHECK(c);
+			prm.dense_limit = dense_limit;
+			prm.pairs = tc.d_pairs;
+			prm.pair_count = pair_count;
+			kg_scan_pair_kernel<<<(unsigned)c->sm_count * 8, 256, 0, c->stream>>>(prm);
+			KG_LAUNCH_CHECK(c);
+		}
+		st = launch_exact_list(c, prm, tc.p_pad / 8);
+		timing_end(c);
+		if (st != KG_OK) return st;
+		if (tc.print_stats) {   // diagnosis only: synchronises the stream
+			unsigned long long h[32];
+			cudaStreamSynchronize(c->stream);
+			cudaMemcpy(h, tc.d_group_count, sizeof h, cudaMemcpyDeviceToHost);
+			fprintf(stderr, "[kg filter] pass %u rows %llu qcap %llu groups:", pass, (unsigned long long)n_rows, (unsigned long long)tc.qcap);
+			for (uint32_t g = 0; g < tc.p_pad / 16; g++) fprintf(stderr, " %llu", h[g]);
+			fprintf(stderr, "  pairs %llu\n", h[24]);
+		}
+		if (c->sel.active && pass + 1 == tc.n_pass) return kg_sel_finish_round(c, n_rows, first_row_id, true);
+		kg_tile_end_kernel<<<1, 32, 0, c->stream>>>(c->d_counters, tc.d_group_count, tc.p_pad / 16);
 		KG_LAUNCH_CHECK(c);
-		prm.dense_limit = dense_limit;
-		prm.pairs = tc.d_pairs;
-		prm.pair_count = pair_count;
-		kg_scan_pair_kernel<<<(unsigned)c->sm_count * 8, 256, 0, c->stream>>>(prm);
-		KG_LAUNCH_CHECK(c);
 	}
-	st = launch_exact_list(c, prm, tc.p_pad / 8);
-	timing_end(c);
-	if (st != KG_OK) return st;
-	if (tc.print_stats) {   // diagnosis only: synchronises the stream
-		unsigned long long h[32];
-		cudaStreamSynchronize(c->stream);
-		cudaMemcpy(h, tc.d_group_count, sizeof h, cudaMemcpyDeviceToHost);
-		fprintf(stderr, "[kg filter] rows %llu qcap %llu groups:", (unsigned long long)n_rows, (unsigned long long)tc.qcap);
-		for (uint32_t g = 0; g < tc.p_pad / 16; g++) fprintf(stderr, " %llu", h[g]);
-		fprintf(stderr, "  pairs %llu\n", h[24]);
-	}
-	if (c->sel.active) return kg_sel_finish_round(c, n_rows, first_row_id, true);
-	kg_tile_end_kernel<<<1, 32, 0, c->stream>>>(c->d_counters, tc.d_group_count, tc.p_pad / 16);
-	KG_LAUNCH_CHECK(c);
 	return KG_OK;
 }
 
@@ -542,38 +453,41 @@ static kg_status kg_tc_filter_debug(kg_ctx *c, const uint64_t *dev_in, uint64_t 
 	if (st != KG_OK) return st;
 	st = kg_tc_ensure_row_list(c, n_rows);
 	if (st != KG_OK) return st;
-	KgFilterParams f = kg_tc_filter_params(c, dev, n_rows);
 	int32_t *d_q = nullptr;
 	cudaError_t e = cudaMalloc((void **)&d_q, (size_t)n_rows * tc.p_pad * sizeof(int32_t));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc debug sums: %s", cudaGetErrorString(e));
-	f.q_out = d_q;
-	f.kept_count = c->d_counters + 4;  // scratch counter: the debug pass must not change rows_kept
+	// the column assignment and the operand images as the device holds them (the re-tune kernel wrote them)
+	std::vector<uint32_t> col_of(c->n_pheno);
+	std::vector<int8_t> image((size_t)tc.n_pass * tc.b_bytes);
+	std::vector<int32_t> q((size_t)n_rows * tc.p_pad);
 	const uint32_t n_blocks = (uint32_t)((n_rows + KG_F_ROWS - 1) / KG_F_ROWS);
 	const unsigned grid = std::max(1u, std::min<uint32_t>(n_blocks, (uint32_t)c->sm_count));
-	kg_scan_filter_kernel<1><<<grid, KG_F_THREADS, tc.smem_bytes, c->stream>>>(f);
-	c->launches++;
-	cudaError_t e1 = cudaGetLastError();
-	cudaError_t e2 = cudaStreamSynchronize(c->stream);
-	std::vector<int32_t> q((size_t)n_rows * tc.p_pad);
-	cudaError_t e3 = cudaMemcpy(q.data(), d_q, q.size() * sizeof(int32_t), cudaMemcpyDeviceToHost);
+	cudaError_t e1 = cudaStreamSynchronize(c->stream);
+	cudaError_t e2 = cudaMemcpy(col_of.data(), tc.d_col_of, col_of.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+	cudaError_t e3 = cudaMemcpy(image.data(), tc.d_yq, image.size(), cudaMemcpyDeviceToHost);
+	for (uint32_t pass = 0; pass < tc.n_pass && e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess; pass++) {
+		KgFilterParams f = kg_tc_filter_params(c, dev, n_rows, pass);
+		f.q_out = d_q;
+		f.kept_count = c->d_counters + 4;  // scratch counter: the debug pass must not change rows_kept
+		kg_scan_filter_kernel<1><<<grid, KG_F_THREADS, tc.smem_bytes, c->stream>>>(f);
+		c->launches++;
+		e1 = cudaGetLastError();
+		if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(c->stream);
+		if (e1 == cudaSuccess) e1 = cudaMemcpy(q.data(), d_q, q.size() * sizeof(int32_t), cudaMemcpyDeviceToHost);
+		if (e1 != cudaSuccess) break;
+		const uint32_t p0 = pass * tc.cols_per_pass, p1 = std::min(c->n_pheno, p0 + tc.cols_per_pass);
+		for (uint64_t r = 0; r < n_rows; r++)
+			for (uint32_t p = p0; p < p1; p++) q_host[r * c->n_pheno + p] = q[r * tc.p_pad + col_of[p]];
+	}
 	cudaFree(d_q);
 	KG_CUDA(c, e1); KG_CUDA(c, e2); KG_CUDA(c, e3);
-	// the column assignment and the operand image as the device holds them (the host or the re-tune kernel wrote them)
-	std::vector<uint32_t> col_of(c->n_pheno);
-	std::vector<int8_t> image(tc.b_bytes);
-	KG_CUDA(c, cudaMemcpy(col_of.data(), tc.d_col_of, col_of.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-	KG_CUDA(c, cudaMemcpy(image.data(), tc.d_yq, image.size(), cudaMemcpyDeviceToHost));
-	for (uint64_t r = 0; r < n_rows; r++)
-		for (uint32_t p = 0; p < c->n_pheno; p++) {
-			const int32_t v = q[r * tc.p_pad + col_of[p]];
-			if (v % KG_F_ONE != 0) KG_FAIL(c, KG_ERR_STATE, "filter accumulator not a multiple of %d", KG_F_ONE);
-			q_host[r * c->n_pheno + p] = v / KG_F_ONE;
-		}
 	if (yq_host) {
 		const uint32_t kpad = 64 * c->w_file;
-		for (uint32_t p = 0; p < c->n_pheno; p++)
+		for (uint32_t p = 0; p < c->n_pheno; p++) {
+			const int8_t *img = image.data() + (size_t)(p / tc.cols_per_pass) * tc.b_bytes;
 			for (uint32_t col = 0; col < kpad; col++)
-				yq_host[(size_t)p * kpad + col] = (int8_t)-image[kg_tc_b_offset(tc, col_of[p], kg_filter_k_of_column(col))];
+				yq_host[(size_t)p * kpad + col] = (int8_t)-img[kg_tc_b_offset(tc, col_of[p], kg_filter_k_of_column(col))];
+		}
 	}
 	return KG_OK;
 }

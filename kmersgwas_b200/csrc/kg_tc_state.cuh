@@ -31,18 +31,12 @@ struct KgTcState {
 	int8_t *d_yq = nullptr;
 	struct KgFilterGroupConst *d_gconst = nullptr;   // [p_pad / 16] per column group, see kg_scan_filter.cuh
 	std::vector<float> slack_table;        // [P][N/2 + 1] F_p(m): largest |sum of rounding errors / s| over m samples
-	std::vector<float> group_lines;        // [p_pad / 16][8] upper tangents (4 intercepts, 4 slopes) of max_p F_p per group
-	std::vector<int8_t> h_yq_image;        // B image as uploaded (columns in the current alpha order)
 	std::vector<int8_t> h_q;               // [P][n_used] quantised phenotypes, memory (phenotype-file) order
-	std::vector<uint32_t> col_of;          // [P] B / accumulator column of phenotype p
-	int8_t *h_img_pinned[2] = {nullptr, nullptr};   // pinned staging of the B image (stream-ordered re-uploads)
-	cudaEvent_t img_ev[2] = {nullptr, nullptr};
-	int img_next = 0;
-	size_t img_bytes = 0;
 	std::vector<double> scale;             // [P] quantisation step s_p
 	std::vector<float> kappa;              // [P]
 	std::vector<uint8_t> degenerate;       // [P] phenotype column the bound cannot handle: always a candidate
 	uint32_t p_pad = 0, nc = 0, sbo_b = 0, b_bytes = 0, tcols = 0, a_words = 0, a_stages = 0;
+	uint32_t n_pass = 1, cols_per_pass = 0, raw_stages = 4;   // phenotype columns are scanned in passes of <= 127 (P_pad <= 128)
 	size_t smem_bytes = 0;
 	uint64_t *d_aligned = nullptr;         // realigned copy of a tile whose device pointer is not 16-byte aligned
 	size_t aligned_cap = 0;

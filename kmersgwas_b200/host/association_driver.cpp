@@ -21,7 +21,7 @@
 
 namespace {
 const uint64_t kMaxRoundRows = 1ull << 23;  // rows per round once the heaps are warm
-const uint64_t kMinWarmRound = 1ull << 16;
+const uint64_t kMinWarmRound = 1ull << 10;   // floor of a warm round (the hit budget decides above it)
 const uint64_t kHitBudget = 1ull << 21;     // expected hits per round (the device buffer holds 1 << 22 by default)
 
 uint64_t now_ns() {
@@ -239,18 +239,29 @@ static bool replay_in_flight(kg_ctx *ctx, BestAssociationsHeap *const *heaps, st
 	return true;
 }
 
+// Redo the round that overflowed the device hit buffer (it was dropped as a whole) in rounds a quarter as long.
+static void redo_flight(kg_ctx *ctx, BestAssociationsHeap *const *heaps, std::size_t P, AssociationDriverState &S) {
+	check(ctx, kg_scan_discard(ctx), "kg_scan_discard");
+	if (!S.flight_rows || S.flight_n == 0) throw std::runtime_error("hit buffer overflow and the round's rows are gone (raise KG_OPT_HIT_CAPACITY)");
+	if (S.shrink > (1ull << 40)) throw std::runtime_error("hit buffer overflow even with one-row rounds (raise KG_OPT_HIT_CAPACITY)");
+	const uint64_t *rows = S.flight_rows;
+	const uint64_t n = S.flight_n, first = S.flight_first_id;
+	const std::size_t stride = S.flight_stride;
+	S.rows_submitted -= n;
+	S.shrink *= 4;
+	S.flight_rows = nullptr;
+	S.flight_n = 0;
+	kgh_associate_rows(ctx, heaps, P, rows, n, first, stride, S);
+}
+
 void kgh_associate_finish(kg_ctx *ctx, BestAssociationsHeap *const *heaps, std::size_t P, AssociationDriverState &S) {
-	if (!replay_in_flight(ctx, heaps, P, S))
-		throw std::runtime_error("kgh_associate_finish: hit buffer overflow in the last round (raise KG_OPT_HIT_CAPACITY)");
+	while (!replay_in_flight(ctx, heaps, P, S)) redo_flight(ctx, heaps, P, S);
 }
 
 void kgh_associate_rows(kg_ctx *ctx, BestAssociationsHeap *const *heaps, std::size_t P, const uint64_t *rows,
                         uint64_t n_rows, uint64_t first_row_id, std::size_t stride, AssociationDriverState &S) {
 	S.thr.resize(P);
 	uint64_t done = 0;
-	uint64_t shrink = 1;          // after an overflow: divide the round size
-	uint64_t flight_begin = 0;    // first row (of this call) of the interval in flight, for the overflow redo
-	bool flight_is_ours = false;  // the interval in flight holds rows of THIS call
 	while (done < n_rows) {
 		std::size_t cold = 0, need = 0;
 		uint64_t kmax = 1;
@@ -264,8 +275,7 @@ void kgh_associate_rows(kg_ctx *ctx, BestAssociationsHeap *const *heaps, std::si
 		}
 		if (cold && S.in_flight) {
 			// cold heaps take every kept row: their thresholds must be exact, so no round stays in flight
-			if (!replay_in_flight(ctx, heaps, P, S)) throw std::runtime_error("kgh_associate_rows: hit overflow while filling the heaps");
-			flight_is_ours = false;
+			if (!replay_in_flight(ctx, heaps, P, S)) redo_flight(ctx, heaps, P, S);
 			continue;
 		}
 		uint64_t round;
@@ -277,7 +287,7 @@ void kgh_associate_rows(kg_ctx *ctx, BestAssociationsHeap *const *heaps, std::si
 			const double per_row = 2.0 * (double)(P * kmax) / (double)std::max<uint64_t>(S.rows_submitted, 1);
 			round = std::min<uint64_t>(std::max<uint64_t>((uint64_t)((double)kHitBudget / per_row), kMinWarmRound), kMaxRoundRows);
 		}
-		round = std::max<uint64_t>(round / shrink, 1);
+		round = std::max<uint64_t>(round / S.shrink, 1);
 		round = std::min<uint64_t>(round, n_rows - done);
 
 		const uint64_t t_sub = now_ns();
@@ -288,31 +298,21 @@ void kgh_associate_rows(kg_ctx *ctx, BestAssociationsHeap *const *heaps, std::si
 		S.ns_submit += now_ns() - t_sub;
 		// the device now works on this round; meanwhile replay the previous one
 		if (!replay_in_flight(ctx, heaps, P, S)) {
-			// overflow in the previous round: drop everything not replayed, redo from that round in smaller pieces
-			check(ctx, kg_scan_discard(ctx), "kg_scan_discard");
-			if (!flight_is_ours) throw std::runtime_error("kgh_associate_rows: hit overflow in a round of an earlier call");
-			S.rows_submitted -= done - flight_begin;
-			done = flight_begin;
-			shrink *= 4;
-			flight_is_ours = false;
+			// overflow in the PREVIOUS round: everything not replayed is dropped (this round too); redo the previous
+			// round in smaller pieces, then come back to this one with the shorter rounds
+			redo_flight(ctx, heaps, P, S);
 			continue;
 		}
 		check(ctx, kg_scan_mark(ctx), "kg_scan_mark");
 		S.in_flight = true;
 		S.in_flight_rows = round;
-		flight_begin = done;
-		flight_is_ours = true;
+		S.flight_rows = rows + done * stride;
+		S.flight_n = round;
+		S.flight_first_id = first_row_id + done;
+		S.flight_stride = stride;
 		S.rows_submitted += round;
 		done += round;
-		if (cold) {
-			if (!replay_in_flight(ctx, heaps, P, S)) {
-				check(ctx, kg_scan_discard(ctx), "kg_scan_discard");
-				S.rows_submitted -= done - flight_begin;
-				done = flight_begin;
-				shrink *= 4;
-			}
-			flight_is_ours = false;
-		}
+		if (cold && !replay_in_flight(ctx, heaps, P, S)) redo_flight(ctx, heaps, P, S);
 	}
 }
 

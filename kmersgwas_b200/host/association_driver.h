@@ -80,6 +80,12 @@ struct AssociationDriverState {
 	}
 
 	// ---- pipeline state
+	// the round in flight, so that a hit-buffer overflow found later (next call, or kgh_associate_finish) can be redone in
+	// smaller pieces: the caller keeps host rows valid until kgh_associate_finish anyway
+	const uint64_t *flight_rows = nullptr;
+	uint64_t flight_n = 0, flight_first_id = 0;
+	std::size_t flight_stride = 0;
+	uint64_t shrink = 1;             // divides the round length after an overflow (sticky for the rest of the scan)
 	bool in_flight = false;          // the open device interval holds submitted rows whose hits are not replayed yet
 	uint64_t in_flight_rows = 0;
 	uint64_t kept_seen = 0;          // rows_kept total reported by the last fetch

@@ -297,30 +297,51 @@ def test_kinship_external_accumulator(kg):
 
 
 # ------------------------------------------------------------------------------ shapes beyond the tensor engines
-def test_wide_table_falls_back_to_exact_and_popc_engines(kg):
-    """BASELINE config 5 shape (4096 samples): the phenotype tile of the int8 filter and the kinship operand stages do
-    not fit shared memory, so the auto engines must pick the exact score kernel / the popcount Gram and stay exact."""
-    n_file, n_rows, n_pheno = 4096, 700, 3
+def _check_session_heaps(kg, sess, table, keep_o, scores_o, kbest, phenos):
+    for j in phenos:
+        h = S.oracle_topk(table, keep_o, scores_o[j], kbest)
+        ko, so, ro = h.dump()
+        k, s, r = sess.heap(j)
+        assert np.array_equal(k, ko) and np.array_equal(_bits(s), _bits(so)) and np.array_equal(r, ro)
+
+
+@pytest.mark.parametrize("engine", [0, 2])
+def test_wide_table_on_the_tensor_path(kg, engine):
+    """BASELINE config 5 shape (4096 samples): the B tile of a pass shrinks to 16 columns and the raw ring to 2 stages so
+    that the int8 filter still runs (engine 2 forced, or the auto engine once the heaps are full); the kinship operand
+    stages do not fit next to 520-byte rows, so the auto kinship engine stays on the popcount Gram.  All exact."""
+    n_file, n_rows, n_pheno, kbest = 4096, 3000, 20, 50
     table = S.synth_table(91, n_rows, n_file)
     y = S.synth_phenotypes(92, n_file, n_pheno)
     mc = S.min_count_of(n_file, 0.05, 5)
     idx = np.arange(n_file)
     mw, mb = idx // 64, idx % 64
     keep_o, scores_o, kept_o = S.oracle_scan(table, n_file, mw, mb, y, mc)
-    sess = kg.Session(n_file, mw, mb, y, mc, 50)
-    sess.associate(table, n_rows, 0)
+    sess = kg.Session(n_file, mw, mb, y, mc, kbest, scan_engine=engine)
+    for r0 in range(0, n_rows, 1100):
+        n = min(1100, n_rows - r0)
+        sess.associate(np.ascontiguousarray(table[r0:r0 + n]), n, r0)
     assert sess.tested(0) == kept_o
-    for j in range(n_pheno):
-        h = S.oracle_topk(table, keep_o, scores_o[j], 50)
-        ko, so, ro = h.dump()
-        k, s, r = sess.heap(j)
-        assert np.array_equal(k, ko) and np.array_equal(_bits(s), _bits(so)) and np.array_equal(r, ro)
+    _check_session_heaps(kg, sess, table, keep_o, scores_o, kbest, range(n_pheno))
+    kt_rows = sess.kernel_times()
     sess.close()
+    # the filter's integer sums over two passes of <= 15 columns
     ctx = kg.Context.identity(n_file)
-    with pytest.raises(kg.KgError):          # forcing the tensor engines on this shape is refused, not emulated
-        ctx.set_option(kg.OPT_SCAN_ENGINE, 2)
-        ctx.set_phenotypes(y, mc)
-        ctx.scan_submit(table, n_rows)
+    ctx.set_phenotypes(y, mc)
+    q, yq = ctx.filter_sums(np.ascontiguousarray(table[:300]), 300)
+    bits = np.unpackbits(np.ascontiguousarray(table[:300, 1:]).view(np.uint8), axis=1, bitorder="little").astype(np.int64)
+    assert np.array_equal(q.astype(np.int64), bits @ yq.astype(np.int64).T)
+    # device heaps on the same shape
+    ctx.set_option(kg.OPT_SCAN_ENGINE, engine)
+    ctx.select_begin(kbest)
+    ctx.scan_submit(table, n_rows, 0)
+    assert ctx.select_sync() == (n_rows, kept_o)
+    for j, (k_, s_, r_) in enumerate(ctx.select_heaps()):
+        h = S.OracleHeap(kbest)
+        h.add_many(k_, s_, r_)
+        ko, so, ro = S.oracle_topk(table, keep_o, scores_o[j], kbest).dump()
+        kd, sd, rd = h.dump()
+        assert np.array_equal(kd, ko) and np.array_equal(_bits(sd), _bits(so)) and np.array_equal(rd, ro)
     ctx.close()
     ctx = kg.Context.identity(n_file)
     ctx.kinship_begin(mc)
@@ -331,25 +352,44 @@ def test_wide_table_falls_back_to_exact_and_popc_engines(kg):
     ctx.close()
 
 
-def test_many_phenotypes_auto_engine(kg):
-    """P = 140 > 127 columns: the filter is unavailable, the auto engine scores everything exactly."""
-    n_file, n_rows, n_pheno, kbest = 241, 6000, 140, 30
+@pytest.mark.parametrize("engine", [0, 2])
+def test_many_phenotypes_in_passes(kg, engine):
+    """P = 300 > 127 columns: the filter scans the tile in three passes of 100 phenotype columns (BASELINE config 5 has
+    1001 phenotypes); host replay path and device heaps, exact either way."""
+    n_file, n_rows, n_pheno, kbest = 241, 9000, 300, 30
     table = S.synth_table(93, n_rows, n_file)
     y = S.synth_phenotypes(94, n_file, n_pheno)
     mc = S.min_count_of(n_file, 0.05, 5)
     idx = np.arange(n_file)
     keep_o, scores_o, kept_o = S.oracle_scan(table, n_file, idx // 64, idx % 64, y, mc)
-    sess = kg.Session(n_file, idx // 64, idx % 64, y, mc, kbest)
+    sess = kg.Session(n_file, idx // 64, idx % 64, y, mc, kbest, scan_engine=engine)
+    sess.set_option(kg.OPT_KERNEL_TIMING, 1)
     for r0 in range(0, n_rows, 2500):
         n = min(2500, n_rows - r0)
         sess.associate(np.ascontiguousarray(table[r0:r0 + n]), n, r0)
     assert sess.tested(0) == kept_o
-    for j in (0, 69, 139):
-        h = S.oracle_topk(table, keep_o, scores_o[j], kbest)
-        ko, so, ro = h.dump()
-        k, s, r = sess.heap(j)
-        assert np.array_equal(k, ko) and np.array_equal(_bits(s), _bits(so)) and np.array_equal(r, ro)
+    _check_session_heaps(kg, sess, table, keep_o, scores_o, kbest, (0, 69, 139, 200, 299))
+    kt = sess.kernel_times()
+    assert kt["scan_filter"][1] > 0 and kt["scan_filter"][1] % 3 == 0      # three filter passes per filtered tile
     sess.close()
+    ctx = kg.Context.identity(n_file)
+    ctx.set_option(kg.OPT_SCAN_ENGINE, engine)
+    ctx.set_phenotypes(y, mc)
+    q, yq = ctx.filter_sums(np.ascontiguousarray(table[:500]), 500)
+    bits = np.unpackbits(np.ascontiguousarray(table[:500, 1:]).view(np.uint8), axis=1, bitorder="little").astype(np.int64)
+    assert np.array_equal(q.astype(np.int64), bits @ yq.astype(np.int64).T)
+    ctx.select_begin(kbest)
+    ctx.scan_submit(table, n_rows, 0)
+    assert ctx.select_sync() == (n_rows, kept_o)
+    heaps = ctx.select_heaps()
+    for j in (0, 99, 100, 199, 299):
+        k_, s_, r_ = heaps[j]
+        h = S.OracleHeap(kbest)
+        h.add_many(k_, s_, r_)
+        ko, so, ro = S.oracle_topk(table, keep_o, scores_o[j], kbest).dump()
+        kd, sd, rd = h.dump()
+        assert np.array_equal(kd, ko) and np.array_equal(_bits(sd), _bits(so)) and np.array_equal(rd, ro)
+    ctx.close()
 
 
 def test_ecoli_shape_through_the_pipeline(kg):

@@ -278,3 +278,20 @@ def test_context_reuse_with_more_phenotypes(kg):
             sel = keep_o & (scores_o[j] > thr[j])
             assert np.array_equal(hits["row"][hits["pheno"] == j], np.nonzero(sel)[0])
     ctx.close()
+
+
+def test_host_replay_recovers_from_hit_buffer_overflow(kg):
+    """a device hit interval that overflows is dropped as a whole; the association driver redoes that
+    round in shorter rounds -- also when it was the last round of a call (kgh_associate_finish) -- instead of failing"""
+    n_file, n_pheno, n_rows, kbest = 130, 40, 20000, 2000
+    table, y, mc, keep, scores, kept = _case(n_file, n_pheno, n_rows, 61)
+    want = _oracle_heaps(table, keep, scores, kbest)
+    idx = np.arange(n_file)
+    sess = kg.Session(n_file, (idx // 64).astype(np.uint32), (idx % 64).astype(np.uint32), y, mc, kbest)
+    sess.set_option(kg.OPT_HIT_CAPACITY, 3000)      # far below n_pheno x kbest: the fill rounds and the first warm rounds overflow
+    sess.associate(table, n_rows, 0)
+    assert sess.tested(0) == kept
+    for j in range(n_pheno):
+        k, s, r = sess.heap(j)
+        assert np.array_equal(k, want[j][0]) and np.array_equal(_bits(s), _bits(want[j][1])) and np.array_equal(r, want[j][2])
+    sess.close()
