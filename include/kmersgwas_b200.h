@@ -238,6 +238,23 @@ kg_status kg_kinship_submit(kg_ctx *ctx, const uint64_t *rows, uint64_t n_rows);
  * ibs[i*n_used + j] = M - c[i] - c[j] + 2 G[i][j] for j < i (other entries 0), *kept_rows = M. */
 kg_status kg_kinship_fetch(kg_ctx *ctx, uint64_t *ibs, uint64_t *kept_rows);
 
+/* ---- distinct presence/absence patterns (--pattern_counter) -----------------------------------------
+ * Replaces MultipleKmersDataBases::update_presence_absence_pattern_counter
+ * (/root/reference/src/kmers_multiple_databases.cpp:367-380): every row that passes the MAC filter is hashed over its
+ * memory-order words exactly as the reference does (Hash64 + boost-style combine) and the 64-bit hashes are kept in a
+ * device hash set that grows as needed; the count equals the reference's KmersSet::size().
+ * expected: number of distinct patterns to make room for up front (0 = grow on demand).  Shards: export the keys of one
+ * context (kg_patterns_export with keys = NULL returns the count) and kg_patterns_insert them into another. */
+kg_status kg_patterns_begin(kg_ctx *ctx, uint64_t expected);
+kg_status kg_patterns_submit(kg_ctx *ctx, const uint64_t *rows, uint64_t n_rows, uint64_t min_count);
+/* Count the patterns of every tile kg_scan_submit sees from now on as well (same device copy of the rows: the table
+ * is not transferred twice).  max_rows: rows that will be submitted while attached (room is made for all of them up
+ * front, so the scan stays asynchronous); 0 detaches. */
+kg_status kg_patterns_attach(kg_ctx *ctx, uint64_t min_count, uint64_t max_rows);
+kg_status kg_patterns_count(kg_ctx *ctx, uint64_t *distinct, uint64_t *rows_kept);
+kg_status kg_patterns_export(kg_ctx *ctx, uint64_t *keys, uint64_t cap, uint64_t *n);
+kg_status kg_patterns_insert(kg_ctx *ctx, const uint64_t *keys, uint64_t n);
+
 /* ---- NCCL all-reduce of the kinship accumulator (the path's only exchange step) ------------------
  * The accumulator is a plain sum over rows (u64 Gram counts + kept rows), so row shards add exactly.  The library
  * resolves NCCL at run time (dlopen of libnccl.so.2); it does not link it.

@@ -35,6 +35,7 @@ ABI_SYMBOLS = [
     "kg_select_replay", "kg_select_set_floor", "kg_select_export_scores", "kg_select_kmax", "kg_probe_int8_peak", "kg_select_stats",
     "kg_comm_unique_id", "kg_comm_init_rank", "kg_comm_init_all", "kg_kinship_allreduce", "kg_kinship_allreduce_all",
     "kg_stream_mark", "kg_stream_wait",
+    "kg_patterns_begin", "kg_patterns_attach", "kg_patterns_submit", "kg_patterns_count", "kg_patterns_export", "kg_patterns_insert",
 ]
 
 
@@ -119,6 +120,12 @@ def load():
     lib.kg_comm_init_all.argtypes = [C.POINTER(vp), C.c_int]
     lib.kg_kinship_allreduce.argtypes = [vp]
     lib.kg_kinship_allreduce_all.argtypes = [C.POINTER(vp), C.c_int]
+    lib.kg_patterns_begin.argtypes = [vp, u64]
+    lib.kg_patterns_submit.argtypes = [vp, vp, u64, u64]
+    lib.kg_patterns_attach.argtypes = [vp, u64, u64]
+    lib.kg_patterns_count.argtypes = [vp, u64p, u64p]
+    lib.kg_patterns_export.argtypes = [vp, vp, u64, u64p]
+    lib.kg_patterns_insert.argtypes = [vp, vp, u64]
     lib.kg_stream_mark.argtypes = [vp, u64p]
     lib.kg_stream_wait.argtypes = [vp, u64]
     lib.kg_select_kmax.argtypes = [vp]
@@ -382,6 +389,34 @@ class Context:
         p = ibs.ctypes.data_as(C.POINTER(C.c_uint64)) if want_matrix else None
         self._chk(self._lib.kg_kinship_fetch(self._h, p, C.byref(m)))
         return ibs, int(m.value)
+
+    # ---- distinct presence/absence patterns
+    def patterns_begin(self, expected: int = 0):
+        self._chk(self._lib.kg_patterns_begin(self._h, int(expected)))
+
+    def patterns_submit(self, rows, n_rows: int, min_count: int):
+        self._keepalive = rows
+        self._chk(self._lib.kg_patterns_submit(self._h, _rows_ptr(rows), int(n_rows), int(min_count)))
+
+    def patterns_attach(self, min_count: int, max_rows: int):
+        self._chk(self._lib.kg_patterns_attach(self._h, int(min_count), int(max_rows)))
+
+    def patterns_count(self):
+        d, k = C.c_uint64(0), C.c_uint64(0)
+        self._chk(self._lib.kg_patterns_count(self._h, C.byref(d), C.byref(k)))
+        return int(d.value), int(k.value)
+
+    def patterns_export(self):
+        n = C.c_uint64(0)
+        self._chk(self._lib.kg_patterns_export(self._h, None, 0, C.byref(n)))
+        keys = np.zeros(int(n.value), dtype=np.uint64)
+        if n.value:
+            self._chk(self._lib.kg_patterns_export(self._h, keys.ctypes.data, int(n.value), C.byref(n)))
+        return keys
+
+    def patterns_insert(self, keys):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        self._chk(self._lib.kg_patterns_insert(self._h, keys.ctypes.data, len(keys)))
 
     def kinship_allreduce(self):
         self._chk(self._lib.kg_kinship_allreduce(self._h))

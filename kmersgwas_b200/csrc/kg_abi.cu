@@ -10,6 +10,7 @@
 
 #include "kg_common.cuh"
 #include "kg_kinship_popc.cuh"
+#include "kg_patterns.cuh"
 #include "kg_probe.cuh"
 #include "kg_scan_exact.cuh"
 #include "kg_synth.cuh"
@@ -101,6 +102,12 @@ struct kg_ctx {
 	KgSelState sel;
 
 	int scan_engine = 0, kin_engine = 0;
+
+	// distinct presence/absence patterns (kg_patterns_*)
+	unsigned long long *d_pat_table = nullptr, *d_pat_counters = nullptr;
+	uint64_t pat_slots = 0, pat_count = 0;
+	bool pat_attached = false;             // kg_patterns_attach: every tile of kg_scan_submit is counted as well
+	uint64_t pat_min_count = 0, pat_budget = 0;   // rows the table still has guaranteed room for
 
 	// stream tickets (kg_stream_mark / kg_stream_wait): events on the copy and compute streams
 	struct Mark { cudaEvent_t copy_ev = nullptr, compute_ev = nullptr; };
@@ -202,6 +209,7 @@ static kg_status acquire_tile(kg_ctx *c, const uint64_t *rows, uint64_t n_rows, 
 static kg_status release_tile(kg_ctx *c);
 static kg_status memory_view(kg_ctx *c, const uint64_t *dev, uint64_t n_rows, KgRowView *view);
 static kg_status kg_sel_finish_round(kg_ctx *c, uint64_t n_rows, uint64_t first_row_id, bool filter_counters);
+static kg_status patterns_attached_tile(kg_ctx *c, const uint64_t *dev, uint64_t n_rows);
 static const uint64_t kHostSubTileRows = 1ull << 20;
 
 static void kg_comm_destroy(kg_ctx *c);
@@ -332,6 +340,7 @@ extern "C" void kg_ctx_destroy(kg_ctx *c) {
 	if (c->own_accum) cudaFree(c->d_accum);
 	kg_tc_free(&c->tc);
 	kg_sel_free(&c->sel);
+	cudaFree(c->d_pat_table); cudaFree(c->d_pat_counters);
 	for (int i = 0; i < 2; i++) {
 		cudaFree(c->d_tile[i]);
 		if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
@@ -809,6 +818,10 @@ static kg_status scan_submit_one(kg_ctx *c, const uint64_t *rows, uint64_t n_row
 	const uint64_t *dev = nullptr;
 	kg_status st = acquire_tile(c, rows, n_rows, &dev);
 	if (st != KG_OK) return st;
+	if (c->pat_attached) {
+		st = patterns_attached_tile(c, dev, n_rows);
+		if (st != KG_OK) return st;
+	}
 	bool use_tc = false;
 	if (c->scan_engine == 2) use_tc = true;
 	else if (c->scan_engine == 0) use_tc = kg_tc_scan_profitable(c);
@@ -1172,6 +1185,189 @@ extern "C" kg_status kg_synth_rows_device(kg_ctx *c, uint64_t seed, uint64_t fir
 	const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->sm_count * 32);
 	kg_synth_rows_kernel<<<std::max(grid, 1u), 256, 0, c->stream>>>(seed, first_row, n_rows, c->w_file, last_mask, rows_dev);
 	KG_LAUNCH_CHECK(c);
+	return KG_OK;
+}
+
+// ------------------------------------------------------------------------------------- distinct patterns
+static kg_status patterns_read_counters(kg_ctx *c, unsigned long long *h3) {
+	KG_CUDA(c, cudaMemcpyAsync(h3, c->d_pat_counters, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+	KG_CUDA(c, cudaStreamSynchronize(c->stream));
+	c->pat_count = h3[0] + h3[1];
+	return KG_OK;
+}
+
+// make room for `extra` more keys at a load factor <= 1/2 (rehash into a larger table if needed)
+static kg_status patterns_reserve(kg_ctx *c, uint64_t extra) {
+	uint64_t need = 2 * (c->pat_count + extra) + 1024;
+	if (need <= c->pat_slots) return KG_OK;
+	uint64_t slots = std::max<uint64_t>(c->pat_slots, 1ull << 16);
+	while (slots < need) slots <<= 1;
+	unsigned long long *nt = nullptr;
+	cudaError_t e = cudaMalloc((void **)&nt, slots * 8);
+	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc pattern set (%llu slots): %s", (unsigned long long)slots, cudaGetErrorString(e));
+	KG_CUDA(c, cudaMemsetAsync(nt, 0xFF, slots * 8, c->stream));
+	if (c->d_pat_table) {
+		KG_CUDA(c, cudaMemsetAsync(c->d_pat_counters, 0, sizeof(unsigned long long), c->stream));   // distinct is rebuilt; the other two stay
+		const unsigned grid = (unsigned)std::min<uint64_t>((c->pat_slots + 255) / 256, (uint64_t)c->sm_count * 16);
+		kg_patterns_rehash_kernel<<<grid, 256, 0, c->stream>>>(c->d_pat_table, c->pat_slots, nt, slots, c->d_pat_counters);
+		KG_LAUNCH_CHECK(c);
+		KG_CUDA(c, cudaStreamSynchronize(c->stream));
+		cudaFree(c->d_pat_table);
+	}
+	c->d_pat_table = nt;
+	c->pat_slots = slots;
+	return KG_OK;
+}
+
+extern "C" kg_status kg_patterns_begin(kg_ctx *c, uint64_t expected) {
+	if (!c) return KG_ERR_INVALID;
+	KG_CUDA(c, cudaSetDevice(c->device));
+	KG_CUDA(c, cudaStreamSynchronize(c->stream));
+	cudaFree(c->d_pat_table);
+	c->d_pat_table = nullptr;
+	c->pat_slots = 0;
+	c->pat_count = 0;
+	if (!c->d_pat_counters) KG_CUDA(c, cudaMalloc((void **)&c->d_pat_counters, 4 * sizeof(unsigned long long)));
+	KG_CUDA(c, cudaMemsetAsync(c->d_pat_counters, 0, 4 * sizeof(unsigned long long), c->stream));
+	return patterns_reserve(c, expected);
+}
+
+extern "C" kg_status kg_patterns_submit(kg_ctx *c, const uint64_t *rows, uint64_t n_rows, uint64_t min_count) {
+	if (!c) return KG_ERR_INVALID;
+	if (!c->d_pat_counters) KG_FAIL(c, KG_ERR_STATE, "kg_patterns_submit: call kg_patterns_begin first");
+	if (n_rows == 0) return KG_OK;
+	if (!rows) KG_FAIL(c, KG_ERR_INVALID, "kg_patterns_submit: null rows");
+	if (n_rows >= (1ull << 31)) KG_FAIL(c, KG_ERR_INVALID, "kg_patterns_submit: tile too large (max 2^31-1 rows)");
+	KG_CUDA(c, cudaSetDevice(c->device));
+	unsigned long long h3[3];
+	kg_status st = patterns_read_counters(c, h3);   // exact fill before the tile (the previous tile has completed)
+	if (st != KG_OK) return st;
+	st = patterns_reserve(c, n_rows);
+	if (st != KG_OK) return st;
+	const uint64_t *dev = nullptr;
+	st = acquire_tile(c, rows, n_rows, &dev);
+	if (st != KG_OK) return st;
+	KgRowView view;
+	st = memory_view(c, dev, n_rows, &view);
+	if (st != KG_OK) return st;
+	const uint64_t *mask = c->identity ? c->d_file_mask : c->d_mem_mask;
+	const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_rows + 255) / 256, (uint64_t)c->sm_count * 16));
+	timing_begin(c, KG_KERNEL_AUX, n_rows);
+	kg_patterns_rows_kernel<<<grid, 256, 0, c->stream>>>(view, mask, c->w_mem, (uint32_t)c->n_used,
+	                                                    (uint32_t)std::min<uint64_t>(min_count, 0xFFFFFFFFull), c->d_pat_table, c->pat_slots, c->d_pat_counters);
+	timing_end(c);
+	KG_LAUNCH_CHECK(c);
+	return release_tile(c);
+}
+
+// the tile of a kg_scan_submit, already on the device: count its patterns too (no growth here: kg_patterns_attach
+// made room for every row it was promised)
+static kg_status patterns_attached_tile(kg_ctx *c, const uint64_t *dev, uint64_t n_rows) {
+	if (n_rows > c->pat_budget)
+		KG_FAIL(c, KG_ERR_STATE, "kg_patterns_attach: more rows submitted than the pattern set was sized for");
+	c->pat_budget -= n_rows;
+	KgRowView view;
+	kg_status st = memory_view(c, dev, n_rows, &view);
+	if (st != KG_OK) return st;
+	const uint64_t *mask = c->identity ? c->d_file_mask : c->d_mem_mask;
+	const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_rows + 255) / 256, (uint64_t)c->sm_count * 16));
+	timing_begin(c, KG_KERNEL_AUX, n_rows);
+	kg_patterns_rows_kernel<<<grid, 256, 0, c->stream>>>(view, mask, c->w_mem, (uint32_t)c->n_used,
+	                                                    (uint32_t)std::min<uint64_t>(c->pat_min_count, 0xFFFFFFFFull), c->d_pat_table, c->pat_slots, c->d_pat_counters);
+	timing_end(c);
+	KG_LAUNCH_CHECK(c);
+	return KG_OK;
+}
+
+extern "C" kg_status kg_patterns_attach(kg_ctx *c, uint64_t min_count, uint64_t max_rows) {
+	if (!c) return KG_ERR_INVALID;
+	if (!c->d_pat_counters) KG_FAIL(c, KG_ERR_STATE, "kg_patterns_attach: call kg_patterns_begin first");
+	KG_CUDA(c, cudaSetDevice(c->device));
+	if (max_rows == 0) { c->pat_attached = false; return KG_OK; }
+	unsigned long long h3[3];
+	kg_status st = patterns_read_counters(c, h3);
+	if (st != KG_OK) return st;
+	st = patterns_reserve(c, max_rows);
+	if (st != KG_OK) return st;
+	c->pat_attached = true;
+	c->pat_min_count = min_count;
+	c->pat_budget = max_rows;
+	return KG_OK;
+}
+
+extern "C" kg_status kg_patterns_count(kg_ctx *c, uint64_t *distinct, uint64_t *rows_kept) {
+	if (!c) return KG_ERR_INVALID;
+	if (!c->d_pat_counters) KG_FAIL(c, KG_ERR_STATE, "kg_patterns_count: call kg_patterns_begin first");
+	KG_CUDA(c, cudaSetDevice(c->device));
+	unsigned long long h3[3];
+	kg_status st = patterns_read_counters(c, h3);
+	if (st != KG_OK) return st;
+	if (distinct) *distinct = h3[0] + h3[1];
+	if (rows_kept) *rows_kept = h3[2];
+	return KG_OK;
+}
+
+extern "C" kg_status kg_patterns_export(kg_ctx *c, uint64_t *keys, uint64_t cap, uint64_t *n) {
+	if (!c || !n) return KG_ERR_INVALID;
+	if (!c->d_pat_counters) KG_FAIL(c, KG_ERR_STATE, "kg_patterns_export: call kg_patterns_begin first");
+	KG_CUDA(c, cudaSetDevice(c->device));
+	unsigned long long h3[3];
+	kg_status st = patterns_read_counters(c, h3);
+	if (st != KG_OK) return st;
+	*n = h3[0] + h3[1];
+	if (!keys || cap < *n) return KG_OK;   // size query
+	unsigned long long *dst = reinterpret_cast<unsigned long long *>(keys);
+	const bool dev = is_device_pointer(keys);
+	unsigned long long *tmp = nullptr;
+	if (!dev) {
+		KG_CUDA(c, cudaMalloc((void **)&tmp, std::max<uint64_t>(*n, 1) * 8));
+		dst = tmp;
+	}
+	KG_CUDA(c, cudaMemsetAsync(c->d_pat_counters + 3, 0, sizeof(unsigned long long), c->stream));
+	const unsigned grid = (unsigned)std::min<uint64_t>((c->pat_slots + 255) / 256, (uint64_t)c->sm_count * 16);
+	kg_patterns_export_kernel<<<grid, 256, 0, c->stream>>>(c->d_pat_table, c->pat_slots, dst, h3[0], c->d_pat_counters + 3);
+	c->launches++;
+	cudaError_t e0 = cudaGetLastError();
+	cudaError_t e1 = cudaStreamSynchronize(c->stream);
+	cudaError_t e2 = cudaSuccess;
+	if (!dev && e0 == cudaSuccess && e1 == cudaSuccess) {
+		e2 = cudaMemcpy(keys, tmp, h3[0] * 8, cudaMemcpyDeviceToHost);
+		if (h3[1]) keys[h3[0]] = KG_PAT_EMPTY;
+	} else if (dev && h3[1]) {
+		const unsigned long long k = KG_PAT_EMPTY;
+		e2 = cudaMemcpy(dst + h3[0], &k, 8, cudaMemcpyHostToDevice);
+	}
+	cudaFree(tmp);
+	KG_CUDA(c, e0); KG_CUDA(c, e1); KG_CUDA(c, e2);
+	return KG_OK;
+}
+
+extern "C" kg_status kg_patterns_insert(kg_ctx *c, const uint64_t *keys, uint64_t n) {
+	if (!c) return KG_ERR_INVALID;
+	if (!c->d_pat_counters) KG_FAIL(c, KG_ERR_STATE, "kg_patterns_insert: call kg_patterns_begin first");
+	if (n == 0) return KG_OK;
+	if (!keys) KG_FAIL(c, KG_ERR_INVALID, "kg_patterns_insert: null keys");
+	KG_CUDA(c, cudaSetDevice(c->device));
+	unsigned long long h3[3];
+	kg_status st = patterns_read_counters(c, h3);
+	if (st != KG_OK) return st;
+	st = patterns_reserve(c, n);
+	if (st != KG_OK) return st;
+	const unsigned long long *src = reinterpret_cast<const unsigned long long *>(keys);
+	unsigned long long *tmp = nullptr;
+	if (!is_device_pointer(keys)) {
+		KG_CUDA(c, cudaMalloc((void **)&tmp, n * 8));
+		cudaError_t e = cudaMemcpyAsync(tmp, keys, n * 8, cudaMemcpyHostToDevice, c->stream);
+		if (e != cudaSuccess) { cudaFree(tmp); KG_CUDA(c, e); }
+		src = tmp;
+	}
+	const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)c->sm_count * 16));
+	kg_patterns_keys_kernel<<<grid, 256, 0, c->stream>>>(src, n, c->d_pat_table, c->pat_slots, c->d_pat_counters);
+	c->launches++;
+	cudaError_t e0 = cudaGetLastError();
+	cudaError_t e1 = cudaStreamSynchronize(c->stream);
+	cudaFree(tmp);
+	KG_CUDA(c, e0); KG_CUDA(c, e1);
 	return KG_OK;
 }
 

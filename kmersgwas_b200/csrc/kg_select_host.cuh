@@ -181,6 +181,10 @@ static kg_status kg_sel_submit(kg_ctx *c, const uint64_t *rows, uint64_t n_rows,
 	const size_t stride = (size_t)c->w_file + 1;
 	if (is_device_pointer(rows)) {
 		c->cur_slot = -1;
+		if (c->pat_attached) {
+			kg_status st = patterns_attached_tile(c, rows, n_rows);
+			if (st != KG_OK) return st;
+		}
 		for (uint64_t off = 0; off < n_rows;) {
 			const uint64_t n = kg_sel_next_round(c->sel, n_rows - off);
 			kg_status st = kg_sel_round(c, rows + off * stride, n, first_row_id + off);
@@ -195,6 +199,10 @@ static kg_status kg_sel_submit(kg_ctx *c, const uint64_t *rows, uint64_t n_rows,
 		const uint64_t *dev = nullptr;
 		kg_status st = acquire_tile(c, rows + off * stride, nt, &dev);
 		if (st != KG_OK) return st;
+		if (c->pat_attached) {
+			st = patterns_attached_tile(c, dev, nt);
+			if (st != KG_OK) return st;
+		}
 		for (uint64_t o2 = 0; o2 < nt;) {
 			const uint64_t n = kg_sel_next_round(c->sel, nt - o2);
 			st = kg_sel_round(c, dev + o2 * stride, n, first_row_id + off + o2);

@@ -38,7 +38,7 @@ struct Shard {
 // Pass 1 of one shard through the DEVICE heaps (kg_select_*): batches are submitted asynchronously while the tile
 // reader loads ahead; nothing comes back to the host until the end.  Shards other than the first warm-start from
 // the first prefix_rows rows of the table and log what their heaps admit (merged on shard 0 afterwards).
-void run_shard_device(Shard &sh, size_t min_count, size_t batch_size, bool verbose, KmersSet *pattern_counter,
+void run_shard_device(Shard &sh, size_t min_count, size_t batch_size, bool verbose, bool count_patterns,
                       uint64_t first, uint64_t count, uint64_t prefix_rows, bool is_first_shard) {
 	try {
 		MultipleKmersDataBases &db = *sh.db;
@@ -48,13 +48,13 @@ void run_shard_device(Shard &sh, size_t min_count, size_t batch_size, bool verbo
 			db.device_selection_log_reset();
 		}
 		db.restrict_to_rows(first, count);
+		if (count_patterns) db.pattern_counter_begin(count, min_count);   // this shard's own rows only (not the shared prefix)
 		double t0 = get_time(), t1;
 		size_t batch_index = 0;
 		while (db.load_kmers(batch_size, min_count)) {
 			t1 = get_time();
 			if (verbose) cerr << "Load [" << batch_index << "]\t" << (t1 - t0) / 60. << "min" << endl;
 			t0 = get_time();
-			if (pattern_counter) db.update_presence_absence_pattern_counter(*pattern_counter);
 			db.add_loaded_kmers_to_device_heaps();
 			t1 = get_time();
 			if (verbose) cerr << "Associations [" << batch_index << "]\t" << (t1 - t0) / 60. << "min" << endl;
@@ -185,7 +185,6 @@ int main(int argc, char *argv[]) {
 			shards(g).db->set_scan_engine(engine);
 		}
 		const uint64_t total_rows = shards(0).db->rows_in_file();
-		if (count_patterns && n_gpus > 1) throw logic_error("--pattern_counter is not supported together with --gpus > 1");
 		vector<size_t> capacities(phenotypes_n);
 		for (size_t j = 0; j < phenotypes_n; j++) capacities[j] = k_heap[j].capacity();
 
@@ -195,14 +194,15 @@ int main(int argc, char *argv[]) {
 			for (size_t g = 0; g < n_gpus && device_heaps; g++)
 				device_heaps = shards(g).db->begin_device_selection(capacities, y, min_count, g > 0);
 		if (!device_heaps && select_mode == "device") throw logic_error("--select device: a heap capacity does not fit the device heaps");
-		bool done = false;
+		bool done = false, have_device_patterns = false;
+		uint64_t device_patterns = 0;
 		if (device_heaps) {
 			const uint64_t prefix_rows = min<uint64_t>(total_rows / n_gpus, max<uint64_t>(1, (uint64_t)8 << 20));
 			vector<thread> threads;
 			for (size_t g = 0; g < n_gpus; g++) {
 				const uint64_t first = total_rows * g / n_gpus, last = total_rows * (g + 1) / n_gpus;
-				threads.emplace_back(run_shard_device, ref(shards(g)), min_count, batch_size, g == 0,
-				                     (count_patterns && g == 0) ? &pa_patterns_counter : nullptr, first, last - first, prefix_rows, g == 0);
+				threads.emplace_back(run_shard_device, ref(shards(g)), min_count, batch_size, g == 0, count_patterns,
+				                     first, last - first, prefix_rows, g == 0);
 			}
 			for (auto &t : threads) t.join();
 			bool overflow = false;
@@ -220,6 +220,16 @@ int main(int argc, char *argv[]) {
 					shards(0).db->device_selection_replay(off, ent, rows, kept);
 				}
 				if (!overflow) {
+					if (count_patterns) {
+						// distinct patterns of the whole table: union of the shards' device sets (by hash key)
+						for (size_t g = 1; g < n_gpus; g++) {
+							vector<uint64_t> keys;
+							shards(g).db->pattern_counter_export(keys);
+							shards(0).db->pattern_counter_insert(keys);
+						}
+						device_patterns = shards(0).db->pattern_counter_size();
+						have_device_patterns = true;
+					}
 					shards(0).db->finish_device_selection(k_heap);
 					done = true;
 				}
@@ -244,6 +254,7 @@ int main(int argc, char *argv[]) {
 			if (sh.error) rethrow_exception(sh.error);
 			k_heap.swap(sh.heaps);
 		} else if (!done) {
+			if (count_patterns) throw logic_error("--pattern_counter with --gpus > 1 needs the device heaps (--select auto|device and -n <= ~14000)");
 			vector<thread> threads;
 			for (size_t g = 0; g < n_gpus; g++) {
 				const uint64_t first = total_rows * g / n_gpus, last = total_rows * (g + 1) / n_gpus;
@@ -262,7 +273,8 @@ int main(int argc, char *argv[]) {
 			for (size_t j = 0; j < phenotypes_n; j++) hp[j] = &k_heap[j];
 			kgh_merge_shards(states, hp.data(), hp.size());
 		}
-		if (count_patterns) cerr << "Total patterns\t" << pa_patterns_counter.size() << endl;
+		const uint64_t n_patterns = have_device_patterns ? device_patterns : (uint64_t)pa_patterns_counter.size();
+		if (count_patterns) cerr << "Total patterns\t" << n_patterns << endl;
 
 		// ---- outputs (reference :155-205) --------------------------------------------------------
 		vector<kmers_output_list> best_kmers;
@@ -284,7 +296,7 @@ int main(int argc, char *argv[]) {
 		cerr << endl;
 		if (count_patterns) {
 			ofstream fout(fn_base + ".pattern_counter");
-			fout << pa_patterns_counter.size() << endl;
+			fout << n_patterns << endl;
 		}
 		ofstream fout(fn_base + ".tested_kmers");
 		fout << k_heap[0].number_of_insertion() << endl;

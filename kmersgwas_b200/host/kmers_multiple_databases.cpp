@@ -429,6 +429,29 @@ uint64_t MultipleKmersDataBases::presence_absence_pattern_hash_loaded_row(size_t
 	return seed;
 }
 
+// ---- presence/absence pattern counter on the device ------------------------------------------------------
+void MultipleKmersDataBases::pattern_counter_begin(uint64_t max_rows, const size_t &min_count) {
+	check(kg_patterns_begin(m_ctx, 0), "kg_patterns_begin");
+	check(kg_patterns_attach(m_ctx, min_count, max_rows), "kg_patterns_attach");
+}
+
+uint64_t MultipleKmersDataBases::pattern_counter_size() {
+	uint64_t n = 0;
+	check(kg_patterns_count(m_ctx, &n, nullptr), "kg_patterns_count");
+	return n;
+}
+
+void MultipleKmersDataBases::pattern_counter_export(vector<uint64_t> &keys) {
+	uint64_t n = 0;
+	check(kg_patterns_export(m_ctx, nullptr, 0, &n), "kg_patterns_export");
+	keys.assign(n, 0);
+	if (n) check(kg_patterns_export(m_ctx, keys.data(), n, &n), "kg_patterns_export");
+}
+
+void MultipleKmersDataBases::pattern_counter_insert(const vector<uint64_t> &keys) {
+	check(kg_patterns_insert(m_ctx, keys.data(), keys.size()), "kg_patterns_insert");
+}
+
 // ---- presence/absence pattern counter (:367-380), host implementation ("next" row of SURVEY 8(f)) -----
 void MultipleKmersDataBases::update_presence_absence_pattern_counter(KmersSet &pa_pattern_counter) const {
 	static const Hash64 hasher;

@@ -77,6 +77,12 @@ class MultipleKmersDataBases {
 		void output_plink_bed_file_selected(BedBimFilesHandle &f, const std::vector<AssociationOutputInfo> &kmer_list);
 
 		void update_presence_absence_pattern_counter(KmersSet &pa_pattern_counter) const;
+		// Device form of the same counter (kg_patterns_*): the hashes of the kept rows go into a device hash set while the
+		// scan's own copy of the rows is on the GPU (no second transfer); legal with row shards (sets are merged by key).
+		void pattern_counter_begin(uint64_t max_rows, const std::size_t &min_count);   // counts every row submitted to the scan from now on
+		uint64_t pattern_counter_size();
+		void pattern_counter_export(std::vector<uint64_t> &keys);
+		void pattern_counter_insert(const std::vector<uint64_t> &keys);
 
 		// kmers_table_to_bed (reference :204-216, :262-272): PLINK output of EVERY row load_kmers keeps.  The reference's
 		// load_kmers stops after batch_size KEPT rows; here a batch is a range of raw file rows, so the caller walks the

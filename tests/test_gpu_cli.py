@@ -145,12 +145,21 @@ def test_associate_kmers_two_shards_equal_one(bins, tmp_path):
             os.environ["KMERSGWAS_SHARDS_ON_ONE_DEVICE"] = "1"
         r = _run(bins / "associate_kmers", ["-p", pheno, "-b", "x", "-o", out, "--kmers_table", table, "-n", g.kbest,
                                            "--kmer_len", 31, "--maf", g.maf, "--mac", g.mac, "--batch_size", 500,
-                                           "--k_mers_scores"] + extra)
+                                           "--k_mers_scores"] + extra + ([] if tag == "two_host" else ["--pattern_counter"]))
         assert r.returncode == 0, r.stderr[-2000:]
         dirs.append(out)
     os.environ.pop("KMERSGWAS_SHARDS_ON_ONE_DEVICE", None)
-    for d in dirs[1:]:
-        _same_dir(dirs[0], d)
+    for d in dirs[1:3]:
+        _same_dir(dirs[0], d)              # incl. x.pattern_counter: the shards' device pattern sets are merged by key
+    (dirs[0] / "x.pattern_counter").unlink()
+    _same_dir(dirs[0], dirs[3])
+    # and the single-GPU count is the reference's
+    ref = tmp_path / "ref"
+    ref.mkdir()
+    r = _run(S.REF_DIR / "associate_kmers", ["-p", pheno, "-b", "x", "-o", ref, "--kmers_table", table, "-n", g.kbest, "--kmer_len", 31,
+                                            "--maf", g.maf, "--mac", g.mac, "--batch_size", 500, "--k_mers_scores", "--pattern_counter"])
+    assert r.returncode == 0
+    assert (ref / "x.pattern_counter").read_text() == (dirs[1] / "x.pattern_counter").read_text()
 
 
 @pytest.mark.parametrize("name,batch,unique,rows_per_load", [

@@ -431,3 +431,59 @@ def test_mac_filter_matches_numpy(kg):
         want = (cnt >= mc) & (cnt <= len(used) - mc)
         assert np.array_equal(keep, want) and kept == int(want.sum())
     ctx.close()
+
+
+# ------------------------------------------------------------------------------ distinct patterns on the device
+def _pattern_hashes(table, n_file, used, min_count):
+    """reference hash of every kept row (kmers_multiple_databases.cpp:367-374; Hash64 = kmer_general.h:32-41), numpy"""
+    bits = np.unpackbits(np.ascontiguousarray(table[:, 1:]).view(np.uint8), axis=1, bitorder="little")[:, used]
+    cnt = bits.sum(axis=1)
+    keep = (cnt >= min_count) & (cnt <= len(used) - min_count)
+    w_mem = S.w_mem_of(len(used))
+    padded = np.zeros((table.shape[0], 64 * w_mem), dtype=np.uint8)
+    padded[:, :len(used)] = bits
+    words = np.packbits(padded, axis=1, bitorder="little").view(np.uint64)
+    seed = np.zeros(table.shape[0], dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for w in range(w_mem):
+            k = words[:, w].copy()
+            k = (k ^ (k >> np.uint64(33))) * np.uint64(0xff51afd7ed558ccd)
+            k = (k ^ (k >> np.uint64(33))) * np.uint64(0xc4ceb9fe1a85ec53)
+            k = k ^ (k >> np.uint64(33))
+            seed ^= k + np.uint64(0x9e3779b97f4a7c15) + (seed << np.uint64(6)) + (seed >> np.uint64(2))
+    return seed[keep], int(keep.sum())
+
+
+@pytest.mark.parametrize("subset", [False, True])
+def test_pattern_counter_on_device(kg, subset):
+    n_file, n_rows, mc = 300, 40000, 11
+    rng = np.random.default_rng(5)
+    used = rng.permutation(n_file)[:211] if subset else np.arange(n_file)
+    table = S.synth_table(23, n_rows, n_file)
+    table[:, 1:] = table[np.arange(n_rows) % 9001, 1:].copy()           # many repeated patterns
+    want, kept = _pattern_hashes(table, n_file, used, mc)
+    ctx = kg.Context(n_file, (used // 64).astype(np.uint32), (used % 64).astype(np.uint32))
+    ctx.patterns_begin(0)                                                # grow on demand: several rehashes
+    for r0 in range(0, n_rows, 7000):
+        n = min(7000, n_rows - r0)
+        ctx.patterns_submit(np.ascontiguousarray(table[r0:r0 + n]), n, mc)
+    distinct, dkept = ctx.patterns_count()
+    assert dkept == kept and distinct == len(np.unique(want))
+    keys = ctx.patterns_export()
+    assert np.array_equal(np.sort(keys), np.unique(want))
+    # union with another shard's keys; attached to a scan (the scan's own device copy of the rows is hashed)
+    other = kg.Context(n_file, (used // 64).astype(np.uint32), (used % 64).astype(np.uint32))
+    other.patterns_begin(0)
+    extra = S.synth_table(29, 5000, n_file)
+    y = S.synth_phenotypes(7, len(used), 3)
+    other.set_phenotypes(y, mc)
+    other.select_begin(20)
+    other.patterns_attach(mc, 5000)
+    other.scan_submit(extra, 5000, n_rows)
+    other.select_sync()
+    want2, kept2 = _pattern_hashes(extra, n_file, used, mc)
+    assert other.patterns_count() == (len(np.unique(want2)), kept2)
+    ctx.patterns_insert(other.patterns_export())
+    assert ctx.patterns_count()[0] == len(np.unique(np.concatenate([want, want2])))
+    ctx.close()
+    other.close()
