@@ -238,6 +238,25 @@ kg_status kg_kinship_submit(kg_ctx *ctx, const uint64_t *rows, uint64_t n_rows);
  * ibs[i*n_used + j] = M - c[i] - c[j] + 2 G[i][j] for j < i (other entries 0), *kept_rows = M. */
 kg_status kg_kinship_fetch(kg_ctx *ctx, uint64_t *ibs, uint64_t *kept_rows);
 
+/* ---- table construction -------------------------------------------------------------------------------
+ * Replaces MultipleKmersDataBasesMerger::load_kmers (/root/reference/src/kmers_merge_multiple_databaes.cpp:85-121) for one
+ * range of the sorted list of all k-mers: table row i = {all_kmers[i], presence words}, bit a set iff all_kmers[i] is
+ * in accession a's sorted list.  packed: the accessions' k-mers of the range back to back, accession a =
+ * packed[offsets[a] .. offsets[a + 1]) (k-mers that are not in all_kmers are ignored); everything host memory;
+ * table: n_all x (1 + ceil(n_acc / 64)) u64 -- the bytes MultipleKmersDataBasesMerger::output_to_table (:60-73) writes. */
+kg_status kg_table_build(int device, const uint64_t *all_kmers, uint64_t n_all, uint32_t n_acc, const uint64_t *packed,
+                         const uint64_t *offsets, uint64_t *table);
+
+/* ---- SNP twin of the scan -------------------------------------------------------------------------------
+ * Replaces the scoring loop of MultipleSNPsDataBases::get_most_associated_snps
+ * (/root/reference/src/snps_multiple_databases.cpp:225-236 with calculate_grammmar_approx_association :143-158 and the
+ * bit-plane construction of the ctor :95-135) for all phenotypes at once.  bed: the PLINK .bed payload after its 3-byte
+ * magic, n_snps rows of bytes_per_snp bytes (host); sample i of the phenotype order sits in byte map_byte[i] at bit
+ * map_shift[i] (:205-221); y: [n_pheno][n_samples] un-permuted; scores: host [n_pheno][n_snps], bit-identical to the
+ * reference (0 for SNPs that fail the minor-allele-count test).  No kg_ctx needed; error text via kg_last_error(NULL). */
+kg_status kg_snps_scores(int device, const uint8_t *bed, uint64_t n_snps, uint32_t bytes_per_snp, const uint32_t *map_byte,
+                         const uint32_t *map_shift, uint32_t n_samples, const float *y, uint32_t n_pheno, double mac, double *scores);
+
 /* ---- distinct presence/absence patterns (--pattern_counter) -----------------------------------------
  * Replaces MultipleKmersDataBases::update_presence_absence_pattern_counter
  * (/root/reference/src/kmers_multiple_databases.cpp:367-380): every row that passes the MAC filter is hashed over its

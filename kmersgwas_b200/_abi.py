@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "kg_select_digest", "kg_select_thresholds", "kg_select_log_reset", "kg_select_log_counts", "kg_select_log_export",
     "kg_select_replay", "kg_select_set_floor", "kg_select_export_scores", "kg_select_kmax", "kg_probe_int8_peak", "kg_select_stats",
     "kg_comm_unique_id", "kg_comm_init_rank", "kg_comm_init_all", "kg_kinship_allreduce", "kg_kinship_allreduce_all",
-    "kg_stream_mark", "kg_stream_wait",
+    "kg_stream_mark", "kg_stream_wait", "kg_snps_scores", "kg_table_build",
     "kg_patterns_begin", "kg_patterns_attach", "kg_patterns_submit", "kg_patterns_count", "kg_patterns_export", "kg_patterns_insert",
 ]
 
@@ -126,6 +126,8 @@ def load():
     lib.kg_patterns_count.argtypes = [vp, u64p, u64p]
     lib.kg_patterns_export.argtypes = [vp, vp, u64, u64p]
     lib.kg_patterns_insert.argtypes = [vp, vp, u64]
+    lib.kg_snps_scores.argtypes = [C.c_int, vp, u64, C.c_uint32, vp, vp, C.c_uint32, vp, C.c_uint32, C.c_double, vp]
+    lib.kg_table_build.argtypes = [C.c_int, vp, u64, C.c_uint32, vp, vp, vp]
     lib.kg_stream_mark.argtypes = [vp, u64p]
     lib.kg_stream_wait.argtypes = [vp, u64]
     lib.kg_select_kmax.argtypes = [vp]
@@ -140,6 +142,21 @@ def comm_unique_id() -> bytes:
     if load().kg_comm_unique_id(buf) != KG_OK:
         raise KgError(-1, load().kg_last_error(None).decode())
     return buf.raw
+
+
+def snps_scores(bed_rows: np.ndarray, map_byte, map_shift, y: np.ndarray, mac: float, device: int = 0) -> np.ndarray:
+    """bed_rows: uint8 [n_snps, bytes_per_snp]; y: float32 [P, n_samples] -> float64 [P, n_snps] (kg_snps_scores)"""
+    lib = load()
+    bed_rows = np.ascontiguousarray(bed_rows, dtype=np.uint8)
+    mb = np.ascontiguousarray(map_byte, dtype=np.uint32)
+    ms = np.ascontiguousarray(map_shift, dtype=np.uint32)
+    y = np.ascontiguousarray(y, dtype=np.float32)
+    out = np.zeros((y.shape[0], bed_rows.shape[0]), dtype=np.float64)
+    st = lib.kg_snps_scores(device, bed_rows.ctypes.data, bed_rows.shape[0], bed_rows.shape[1], mb.ctypes.data, ms.ctypes.data,
+                            len(mb), y.ctypes.data, y.shape[0], float(mac), out.ctypes.data)
+    if st != KG_OK:
+        raise KgError(st, lib.kg_last_error(None).decode())
+    return out
 
 
 def kernel_times(handle) -> dict:

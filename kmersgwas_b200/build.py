@@ -5,6 +5,8 @@
   bin/associate_kmers        CLI with the reference's flags (host C++ over the C ABI)
   bin/emma_kinship_kmers     CLI with the reference's flags
   bin/kmers_table_to_bed     CLI with the reference's flags (table -> PLINK conversion)
+  bin/associate_snps         CLI with the reference's arguments (SNP twin of the scan)
+  bin/build_kmers_table      CLI with the reference's flags (table construction from sorted k-mer lists)
 
 `python -m kmersgwas_b200.build` builds everything that is stale.
 """
@@ -78,13 +80,14 @@ def build_host(force=False, verbose=False):
     if not HOST.exists():
         return None
     build_cuda(force=False, verbose=verbose)
-    lib_srcs = [p for p in sorted(HOST.glob("*.cpp")) if p.name not in ("associate_kmers.cpp", "emma_kinship_kmers.cpp", "kmers_table_to_bed.cpp")]
+    clis = ("associate_kmers", "emma_kinship_kmers", "kmers_table_to_bed", "associate_snps", "build_kmers_table")
+    lib_srcs = [p for p in sorted(HOST.glob("*.cpp")) if p.stem not in clis]
     hdrs = sorted(HOST.glob("*.h")) + [ROOT / "include" / "kmersgwas_b200.h"]
     out = host_lib_path()
     link = ["-L", LIB, "-lkmersgwas_b200", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../lib"]
     if lib_srcs and (force or _stale(out, lib_srcs + hdrs + [cuda_lib_path()])):
         _run(["g++"] + CXX_FLAGS + ["-shared", "-I", ROOT / "include", "-o", out] + lib_srcs + link, verbose)
-    for cli in ("associate_kmers", "emma_kinship_kmers", "kmers_table_to_bed"):
+    for cli in clis:
         src = HOST / f"{cli}.cpp"
         if not src.exists():
             continue

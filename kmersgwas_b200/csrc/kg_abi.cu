@@ -13,7 +13,9 @@
 #include "kg_patterns.cuh"
 #include "kg_probe.cuh"
 #include "kg_scan_exact.cuh"
+#include "kg_snps.cuh"
 #include "kg_synth.cuh"
+#include "kg_table_build.cuh"
 #include "kg_tc_state.cuh"
 
 // ------------------------------------------------------------------------------------- context
@@ -1481,6 +1483,101 @@ extern "C" kg_status kg_kinship_allreduce_all(kg_ctx *const *ctxs, int n) {
 	ncclResult_t r = g_nccl.GroupEnd();
 	if (st != KG_OK) return st;
 	if (r != ncclSuccess) KG_FAIL(ctxs[0], KG_ERR_CUDA, "ncclGroupEnd failed: %s", g_nccl.GetErrorString(r));
+	return KG_OK;
+}
+
+// ------------------------------------------------------------------------------------- SNP twin of the scan
+extern "C" kg_status kg_snps_scores(int device, const uint8_t *bed, uint64_t n_snps, uint32_t bytes_per_snp, const uint32_t *map_byte,
+                                    const uint32_t *map_shift, uint32_t n_samples, const float *y, uint32_t n_pheno, double mac, double *scores) {
+	auto fail = [](const char *what, cudaError_t e) { g_create_error = std::string(what) + ": " + cudaGetErrorString(e); return KG_ERR_CUDA; };
+	if (!bed || !map_byte || !map_shift || !y || !scores || n_samples == 0 || n_pheno == 0) { g_create_error = "kg_snps_scores: bad arguments"; return KG_ERR_INVALID; }
+	if (n_snps == 0) return KG_OK;
+	int n_dev = 0;
+	cudaError_t e = cudaGetDeviceCount(&n_dev);
+	if (e != cudaSuccess || n_dev == 0) { g_create_error = "kg_snps_scores: no CUDA device; this library has no CPU fallback"; return KG_ERR_CUDA; }
+	if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+	const uint32_t nb = (n_samples + 127) / 128, w_mem = 2 * nb;
+	for (uint32_t i = 0; i < n_samples; i++)
+		if (map_byte[i] >= bytes_per_snp || map_shift[i] > 6) { g_create_error = "kg_snps_scores: sample map out of range"; return KG_ERR_INVALID; }
+	// phenotypes in lane order (permute_scores, kmer_general.cpp:155-167): y_lane[(4 b + L) * 32 + t] = y[128 b + 32 L + 31 - t]
+	std::vector<float> y_lane((size_t)n_pheno * nb * 128, 0.0f);
+	for (uint32_t p = 0; p < n_pheno; p++)
+		for (uint32_t i = 0; i < n_samples; i++) {
+			const uint32_t blk = i / 128, L = (i % 128) / 32, t = 31 - (i % 32);
+			y_lane[(size_t)p * nb * 128 + (size_t)(blk * 4 + L) * 32 + t] = y[(size_t)p * n_samples + i];
+		}
+	uint8_t *d_bed = nullptr;
+	uint32_t *d_mb = nullptr, *d_ms = nullptr;
+	uint64_t *d_planes = nullptr;
+	double *d_sums = nullptr, *d_scores = nullptr;
+	float *d_y = nullptr;
+	kg_status st = KG_OK;
+	auto cleanup = [&] { cudaFree(d_bed); cudaFree(d_mb); cudaFree(d_ms); cudaFree(d_planes); cudaFree(d_sums); cudaFree(d_scores); cudaFree(d_y); };
+#define KG_SNP_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { st = fail(#expr, e_); cleanup(); return st; } } while (0)
+	KG_SNP_TRY(cudaMalloc((void **)&d_bed, n_snps * bytes_per_snp));
+	KG_SNP_TRY(cudaMemcpy(d_bed, bed, n_snps * bytes_per_snp, cudaMemcpyHostToDevice));
+	KG_SNP_TRY(cudaMalloc((void **)&d_mb, n_samples * 4));
+	KG_SNP_TRY(cudaMalloc((void **)&d_ms, n_samples * 4));
+	KG_SNP_TRY(cudaMemcpy(d_mb, map_byte, n_samples * 4, cudaMemcpyHostToDevice));
+	KG_SNP_TRY(cudaMemcpy(d_ms, map_shift, n_samples * 4, cudaMemcpyHostToDevice));
+	KG_SNP_TRY(cudaMalloc((void **)&d_planes, 3 * n_snps * w_mem * 8));
+	KG_SNP_TRY(cudaMalloc((void **)&d_sums, 3 * n_snps * 8));
+	KG_SNP_TRY(cudaMalloc((void **)&d_scores, (size_t)n_pheno * n_snps * 8));
+	KG_SNP_TRY(cudaMalloc((void **)&d_y, y_lane.size() * 4));
+	KG_SNP_TRY(cudaMemcpy(d_y, y_lane.data(), y_lane.size() * 4, cudaMemcpyHostToDevice));
+	uint64_t *d_pa = d_planes, *d_nm = d_planes + n_snps * w_mem, *d_het = d_planes + 2 * n_snps * w_mem;
+	double *d_sg = d_sums, *d_sn = d_sums + n_snps, *d_sg2 = d_sums + 2 * n_snps;
+	const unsigned g1 = (unsigned)std::min<uint64_t>((n_snps + 127) / 128, 148 * 16);
+	kg_snp_planes_kernel<<<std::max(g1, 1u), 128>>>(d_bed, n_snps, bytes_per_snp, d_mb, d_ms, n_samples, w_mem, d_pa, d_nm, d_het, d_sg, d_sn, d_sg2);
+	KG_SNP_TRY(cudaGetLastError());
+	const unsigned g2 = (unsigned)std::min<uint64_t>((n_snps * 4 + 255) / 256, 148 * 8);
+	const size_t smem = (size_t)nb * 128 * sizeof(float);
+	KG_SNP_TRY(cudaFuncSetAttribute(kg_snp_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	kg_snp_scores_kernel<<<std::max(g2, 1u), 256, smem>>>(d_pa, d_nm, d_het, d_sg, d_sn, d_sg2, n_snps, nb, d_y, n_pheno, mac, d_scores);
+	KG_SNP_TRY(cudaGetLastError());
+	KG_SNP_TRY(cudaDeviceSynchronize());
+	KG_SNP_TRY(cudaMemcpy(scores, d_scores, (size_t)n_pheno * n_snps * 8, cudaMemcpyDeviceToHost));
+#undef KG_SNP_TRY
+	cleanup();
+	return KG_OK;
+}
+
+// ------------------------------------------------------------------------------------- table construction
+extern "C" kg_status kg_table_build(int device, const uint64_t *all_kmers, uint64_t n_all, uint32_t n_acc, const uint64_t *packed,
+                                    const uint64_t *offsets, uint64_t *table) {
+	auto fail = [](const char *what, cudaError_t e) { g_create_error = std::string(what) + ": " + cudaGetErrorString(e); return KG_ERR_CUDA; };
+	if (n_all == 0) return KG_OK;
+	if (!all_kmers || !offsets || !table || n_acc == 0) { g_create_error = "kg_table_build: bad arguments"; return KG_ERR_INVALID; }
+	const uint64_t total = offsets[n_acc];
+	if (total && !packed) { g_create_error = "kg_table_build: null k-mer lists"; return KG_ERR_INVALID; }
+	int n_dev = 0;
+	cudaError_t e = cudaGetDeviceCount(&n_dev);
+	if (e != cudaSuccess || n_dev == 0) { g_create_error = "kg_table_build: no CUDA device; this library has no CPU fallback"; return KG_ERR_CUDA; }
+	if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+	const uint32_t w = (n_acc + 63) / 64;
+	uint64_t *d_all = nullptr, *d_packed = nullptr, *d_off = nullptr, *d_table = nullptr;
+	kg_status st = KG_OK;
+	auto cleanup = [&] { cudaFree(d_all); cudaFree(d_packed); cudaFree(d_off); cudaFree(d_table); };
+#define KG_TB_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { st = fail(#expr, e_); cleanup(); return st; } } while (0)
+	KG_TB_TRY(cudaMalloc((void **)&d_all, n_all * 8));
+	KG_TB_TRY(cudaMemcpy(d_all, all_kmers, n_all * 8, cudaMemcpyHostToDevice));
+	KG_TB_TRY(cudaMalloc((void **)&d_off, (size_t)(n_acc + 1) * 8));
+	KG_TB_TRY(cudaMemcpy(d_off, offsets, (size_t)(n_acc + 1) * 8, cudaMemcpyHostToDevice));
+	KG_TB_TRY(cudaMalloc((void **)&d_packed, std::max<uint64_t>(total, 1) * 8));
+	if (total) KG_TB_TRY(cudaMemcpy(d_packed, packed, total * 8, cudaMemcpyHostToDevice));
+	KG_TB_TRY(cudaMalloc((void **)&d_table, n_all * (uint64_t)(w + 1) * 8));
+	const unsigned g1 = (unsigned)std::min<uint64_t>((n_all * (w + 1) + 255) / 256, 148 * 16);
+	kg_table_init_kernel<<<std::max(g1, 1u), 256>>>(d_all, n_all, w, d_table);
+	KG_TB_TRY(cudaGetLastError());
+	if (total) {
+		const unsigned g2 = (unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 16);
+		kg_table_mark_kernel<<<std::max(g2, 1u), 256>>>(d_all, n_all, d_packed, d_off, n_acc, w, reinterpret_cast<unsigned long long *>(d_table));
+		KG_TB_TRY(cudaGetLastError());
+	}
+	KG_TB_TRY(cudaDeviceSynchronize());
+	KG_TB_TRY(cudaMemcpy(table, d_table, n_all * (uint64_t)(w + 1) * 8, cudaMemcpyDeviceToHost));
+#undef KG_TB_TRY
+	cleanup();
 	return KG_OK;
 }
 

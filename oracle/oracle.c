@@ -326,3 +326,52 @@ void kgo_synth_rows(uint64_t seed, uint64_t first_row, uint64_t n_rows, uint64_t
 		}
 	}
 }
+
+/* ---------------------------------------------------------------------------------------
+ * SNP twin (src/snps_multiple_databases.cpp): bit planes of one .bed row over the used samples
+ * (ctor :95-135), the three SSE4-order dot products (dot_product_SSE4 :41-61) and
+ * calculate_grammmar_approx_association (:143-158).  y_perm: permuted, zero-padded phenotypes.
+ * ------------------------------------------------------------------------------------- */
+static float dot_lane_order(const uint64_t *row, size_t w_mem, const float *y_perm) {
+	float lane[4] = {0.f, 0.f, 0.f, 0.f};
+	for (size_t b = 0; b < w_mem / 2; b++) {
+		uint32_t m[4];
+		memcpy(m, row + 2 * b, 16);
+		for (int t = 0; t < 32; t++)
+			for (int L = 0; L < 4; L++) {
+				float add = (m[L] & (0x80000000u >> t)) ? y_perm[128 * b + 4 * t + L] : 0.0f;
+				lane[L] = lane[L] + add;
+			}
+	}
+	return ((lane[0] + lane[1]) + lane[2]) + lane[3];
+}
+
+void kgo_snp_scores(const uint8_t *bed, uint64_t n_snps, size_t bytes_per_snp, const uint32_t *map_byte,
+                    const uint32_t *map_shift, size_t n, const float *y, double mac, double *scores) {
+	size_t w_mem = 2 * ((n + 127) / 128), n_pad = 64 * w_mem;
+	float *y_perm = (float *)malloc(n_pad * sizeof(float));
+	kgo_update_scores_and_sum(y, n, n_pad, y_perm);
+	uint64_t *pa = (uint64_t *)malloc(w_mem * 8), *nm = (uint64_t *)malloc(w_mem * 8), *het = (uint64_t *)malloc(w_mem * 8);
+	for (uint64_t i = 0; i < n_snps; i++) {
+		const uint8_t *row = bed + i * bytes_per_snp;
+		memset(pa, 0, w_mem * 8); memset(nm, 0, w_mem * 8); memset(het, 0, w_mem * 8);
+		double S = 0, S2 = 0, N = 0;
+		static const double to_cnt[4] = {0, 0, 0.5, 1};
+		for (size_t si = 0; si < n; si++) {
+			unsigned d = (row[map_byte[si]] >> map_shift[si]) & 3u;
+			S += to_cnt[d];
+			S2 += to_cnt[d] * to_cnt[d];
+			N += (d != 1u) ? 1.0 : 0.0;
+			pa[si >> 6] |= (uint64_t)(d == 3u) << (si & 63);
+			nm[si >> 6] |= (uint64_t)(d != 1u) << (si & 63);
+			het[si >> 6] |= (uint64_t)(d == 2u) << (si & 63);
+		}
+		if (mac > S || mac > N - S) { scores[i] = 0; continue; }
+		double yigi = (double)dot_lane_order(pa, w_mem, y_perm) + (double)dot_lane_order(het, w_mem, y_perm) * 0.5;
+		double ss = (double)dot_lane_order(nm, w_mem, y_perm);
+		double r = N * yigi - S * ss;
+		r = r * r;
+		scores[i] = r / (N * (N * S2 - S * S));
+	}
+	free(y_perm); free(pa); free(nm); free(het);
+}

@@ -50,6 +50,10 @@ void kgo_heap_dump(const kgo_heap *h, uint64_t *kmers, double *scores, uint64_t 
  * implemented on the device in kmersgwas_b200/csrc/kg_synth.cuh; tests check they agree. */
 void kgo_synth_rows(uint64_t seed, uint64_t first_row, uint64_t n_rows, uint64_t n_file, uint64_t *out);
 
+/* SNP twin: scores of every SNP of a .bed payload for ONE phenotype (src/snps_multiple_databases.cpp:95-158). */
+void kgo_snp_scores(const uint8_t *bed, uint64_t n_snps, size_t bytes_per_snp, const uint32_t *map_byte,
+                    const uint32_t *map_shift, size_t n, const float *y, double mac, double *scores);
+
 #ifdef __cplusplus
 }
 #endif

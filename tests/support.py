@@ -63,6 +63,7 @@ def oracle():
     lib.kgo_heap_insertions.restype = C.c_uint64
     lib.kgo_heap_dump.argtypes = [C.c_void_p, _u64p, _f64p, _u64p]
     lib.kgo_synth_rows.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _u64p]
+    lib.kgo_snp_scores.argtypes = [_u8p, C.c_uint64, C.c_size_t, _u32p, _u32p, C.c_size_t, _f32p, C.c_double, _f64p]
     _oracle = lib
     return lib
 
@@ -272,3 +273,65 @@ class Golden:
         write_table(d / "t", self.table, self.n_file, self.names)
         write_pheno(d / "p.tsv", self.used, self.y)
         return d / "t", d / "p.tsv"
+
+
+# ----------------------------------------------------------------------------- SNP twin / table construction
+def synth_plink(d, n_samples: int, n_snps: int, seed: int):
+    """Random PLINK bed/bim/fam triple with all four genotype codes (00 a/a, 01 missing, 10 A/a, 11 A/A).
+    -> (base path, bed payload uint8 [n_snps, bytes_per_snp], sample names)"""
+    rng = np.random.default_rng(seed)
+    names = [f"s{i}" for i in range(n_samples)]
+    bps = (n_samples + 3) // 4
+    g = rng.choice(4, size=(n_snps, bps * 4), p=[0.45, 0.05, 0.15, 0.35]).astype(np.uint8)
+    g[:, n_samples:] = 0
+    # rarer alleles for some SNPs so that the minor-allele-count test rejects them (zero scores: heap ties)
+    rare = rng.random(n_snps) < 0.2
+    g[rare] = np.where(rng.random((int(rare.sum()), bps * 4)) < 0.97, 0, g[rare])
+    bed = (g[:, 0::4] | (g[:, 1::4] << 2) | (g[:, 2::4] << 4) | (g[:, 3::4] << 6)).astype(np.uint8)
+    base = str(Path(d) / "snps")
+    with open(base + ".bed", "wb") as f:
+        f.write(bytes([0x6C, 0x1B, 0x01]))
+        f.write(np.ascontiguousarray(bed).tobytes())
+    with open(base + ".fam", "w") as f:
+        for n in names:
+            f.write(f"{n} {n} 0 0 0 -9\n")
+    with open(base + ".bim", "w") as f:
+        for i in range(n_snps):
+            f.write(f"1\tsnp{i}\t0\t{100 + i}\tA\tC\n")
+    return base, bed, names
+
+
+def oracle_snp_scores(bed: np.ndarray, map_byte, map_shift, y1: np.ndarray, mac: float) -> np.ndarray:
+    bed = np.ascontiguousarray(bed, dtype=np.uint8)
+    mb = np.ascontiguousarray(map_byte, dtype=np.uint32)
+    ms = np.ascontiguousarray(map_shift, dtype=np.uint32)
+    y1 = np.ascontiguousarray(y1, dtype=np.float32)
+    out = np.zeros(bed.shape[0], dtype=np.float64)
+    oracle().kgo_snp_scores(_ptr(bed, _u8p), bed.shape[0], bed.shape[1], _ptr(mb, _u32p), _ptr(ms, _u32p), len(mb),
+                            _ptr(y1, _f32p), float(mac), _ptr(out, _f64p))
+    return out
+
+
+def synth_kmer_lists(d, n_acc: int, n_all: int, seed: int):
+    """Sorted k-mer list files for build_kmers_table: all_kmers (sorted, unique, < 2^62) and per accession a sorted
+    subset + some k-mers that are not in all_kmers, with random strand flags in the two top bits.
+    -> (list file, all_kmers file, names, all k-mers, membership [n_all, n_acc] bool)"""
+    rng = np.random.default_rng(seed)
+    pool = np.unique(rng.integers(0, 1 << 62, size=int(n_all * 1.3), dtype=np.uint64))
+    rng.shuffle(pool)
+    all_k = np.sort(pool[:n_all])
+    extra = pool[n_all:]
+    member = rng.random((len(all_k), n_acc)) < rng.random(n_acc)[None, :]
+    d = Path(d)
+    all_k.tofile(d / "all_kmers")
+    names = [f"acc{i}" for i in range(n_acc)]
+    with open(d / "list.txt", "w") as f:
+        for a in range(n_acc):
+            own = np.concatenate([all_k[member[:, a]], extra[rng.random(len(extra)) < 0.1]])
+            if len(own) == 0:
+                own = extra[:1]
+            own = np.sort(own)
+            flags = rng.integers(0, 4, size=len(own), dtype=np.uint64) << np.uint64(62)
+            (own | flags).tofile(d / f"kmers_{a}")
+            f.write(f"{d / ('kmers_%d' % a)}\t{names[a]}\n")
+    return d / "list.txt", d / "all_kmers", names, all_k, member

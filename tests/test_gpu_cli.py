@@ -192,3 +192,63 @@ def test_kmers_table_to_bed_outputs_byte_identical(bins, tmp_path, name, batch, 
     files = _same_dir(*dirs)
     assert "conv.0.bed" in files and "conv.0.fam" in files
 
+
+
+# ------------------------------------------------------------------------------ SNP twin, table construction
+@pytest.mark.parametrize("n_samples,n_snps,n_pheno,subset", [(64, 500, 1, False), (131, 3000, 4, True), (300, 2000, 3, True)])
+def test_associate_snps_outputs_byte_identical(bins, tmp_path, n_samples, n_snps, n_pheno, subset):
+    """SNP twin of the scan: same best-N SNP selection (incl. the zero-score ties of SNPs that fail the MAC test) and the
+    same PLINK files as the reference's associate_snps"""
+    if not (bins / "associate_snps").exists() or not (S.REF_DIR / "associate_snps").exists():
+        pytest.skip("associate_snps not built")
+    base, bed, names = S.synth_plink(tmp_path, n_samples, n_snps, 40 + n_samples)
+    rng = np.random.default_rng(3)
+    used = [names[i] for i in (rng.permutation(n_samples)[: n_samples - 17] if subset else range(n_samples))]
+    y = S.synth_phenotypes(9, len(used), n_pheno)
+    S.write_pheno(tmp_path / "p.tsv", used, y)
+    dirs = []
+    for tag, exe in (("ref", S.REF_DIR / "associate_snps"), ("ours", bins / "associate_snps")):
+        out = tmp_path / tag
+        out.mkdir()
+        r = _run(exe, [tmp_path / "p.tsv", base, out / "best", 57, 0.05, 5])
+        assert r.returncode == 0, r.stderr[-2000:]
+        dirs.append(out)
+    files = _same_dir(*dirs)
+    assert len(files) == 2 * n_pheno
+    assert (dirs[1] / files[0]).stat().st_size > 0
+    # bit-identical scores against the C restatement of the reference (oracle.c), all phenotypes in one device pass
+    import kmersgwas_b200._abi as abi
+    idx = np.array([names.index(u) for u in used])
+    mb, ms = idx // 4, (idx % 4) * 2
+    got = abi.snps_scores(bed, mb, ms, y, 7.0)
+    for j in range(n_pheno):
+        want = S.oracle_snp_scores(bed, mb, ms, y[j], 7.0)
+        assert np.array_equal(got[j].view(np.uint64), want.view(np.uint64))
+    assert (got == 0).any() and (got > 0).any()
+
+
+@pytest.mark.parametrize("n_acc,n_all,rng_rows", [(3, 2000, 4194304), (70, 30000, 7001), (130, 5000, 1)])
+def test_build_kmers_table_byte_identical(bins, tmp_path, n_acc, n_all, rng_rows):
+    """table construction from sorted k-mer lists: .table / .names byte-identical to the reference's build_kmers_table"""
+    if not (bins / "build_kmers_table").exists() or not (S.REF_DIR / "build_kmers_table").exists():
+        pytest.skip("build_kmers_table not built")
+    if rng_rows == 1:
+        n_all = 300
+    lst, allk, names, all_k, member = S.synth_kmer_lists(tmp_path, n_acc, n_all, 70 + n_acc)
+    outs = []
+    for tag, exe in (("ref", S.REF_DIR / "build_kmers_table"), ("ours", bins / "build_kmers_table")):
+        out = tmp_path / tag
+        out.mkdir()
+        args = ["-l", lst, "-k", 31, "-a", allk, "-o", out / "t"]
+        if tag == "ours":
+            args += ["--range_kmers", rng_rows]
+        r = _run(exe, args)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(out)
+    _same_dir(*outs)
+    # and the table says what the generator put in
+    raw = np.fromfile(outs[1] / "t.table", dtype=np.uint8)
+    rows = raw[16:].view(np.uint64).reshape(len(all_k), 1 + (n_acc + 63) // 64)
+    assert np.array_equal(rows[:, 0], all_k)
+    bits = np.unpackbits(np.ascontiguousarray(rows[:, 1:]).view(np.uint8), axis=1, bitorder="little")[:, :n_acc]
+    assert np.array_equal(bits.astype(bool), member)

@@ -105,3 +105,28 @@ def test_heap_ties_and_cli_scores_file(tmp_path):
         raw = np.fromfile(out / f"r.{j}.best_kmers.scores", dtype=np.dtype([("kmer", "<u8"), ("score", "<f8")]))
         assert np.array_equal(raw["kmer"], k)
         assert np.array_equal(raw["score"].view(np.uint64), s.view(np.uint64))
+
+
+@pytest.mark.parametrize("n_samples,subset", [(64, False), (131, True), (260, True)])
+def test_snp_twin_selection_equals_reference(tmp_path, n_samples, subset):
+    """oracle.c's SNP score restatement + the oracle heap select the SNPs the reference's associate_snps writes
+    (zero-score ties included: every SNP goes through the heap, src/snps_multiple_databases.cpp:230-234)"""
+    import subprocess
+    if not (S.REF_DIR / "associate_snps").exists():
+        pytest.skip("oracle/_ref/associate_snps not built")
+    n_snps, n_best, mac = 1500, 40, 6.0
+    base, bed, names = S.synth_plink(tmp_path, n_samples, n_snps, 17 + n_samples)
+    rng = np.random.default_rng(2)
+    idx = rng.permutation(n_samples)[: n_samples - 9] if subset else np.arange(n_samples)
+    used = [names[i] for i in idx]
+    y = S.synth_phenotypes(3, len(used), 2)
+    S.write_pheno(tmp_path / "p.tsv", used, y)
+    subprocess.run([str(S.REF_DIR / "associate_snps"), str(tmp_path / "p.tsv"), base, str(tmp_path / "best"), str(n_best), "0.01", str(mac)],
+                   check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    for j, pname in enumerate(["phenotype_value", "P1"]):
+        got = [int(l.split("\t")[1][3:]) for l in open(tmp_path / f"best.{pname}.bim")]
+        scores = S.oracle_snp_scores(bed, idx // 4, (idx % 4) * 2, y[j], mac)
+        h = S.OracleHeap(n_best)
+        h.add_many(np.zeros(n_snps, dtype=np.uint64), scores, np.arange(n_snps, dtype=np.uint64))
+        want = np.sort(h.dump()[2])
+        assert got == want.tolist()
