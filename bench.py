@@ -565,17 +565,22 @@ def parity_block(args, kg, torch, dist, ctx, rank, world, local, n, p, y, mc, st
 
 
 def kinship_leg(args, kg, torch, dist, rank, world, local, n, stride, row_bytes):
-    """emma_kinship_kmers Gram pass on --kinship-rows rows per GPU per step, resident in HBM; N > 1 adds the
-    one NCCL all-reduce of the accumulator (timed separately)."""
+    """emma_kinship_kmers Gram pass on --kinship-rows rows per GPU per step, resident in HBM; N > 1 adds the path's one
+    exchange step, the NCCL all-reduce of the u64 accumulator, issued by the LIBRARY (kg_kinship_allreduce over its own
+    communicator) and timed separately after a warm-up all-reduce."""
     Rk = args.kinship_rows
     if Rk <= 0:
         return None
+    from kmersgwas_b200 import _abi
     stream = torch.cuda.Stream()
     ctx = kg.Context.identity(n, device=local, stream=stream.cuda_stream)
     ctx.set_option(kg.OPT_KERNEL_TIMING, 1)
     ctx.set_option(kg.OPT_KINSHIP_ENGINE, args.kinship_engine)
     mc = int(math.ceil(n * MAF))
-    acc = torch.zeros(ctx.kinship_accum_len(), dtype=torch.int64, device="cuda")
+    if world > 1:
+        ids = [_abi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init_rank(ids[0], world, rank)
     steps, warm = max(1, min(args.steps, 5)), 2
     with torch.cuda.stream(stream):
         bufs = []
@@ -583,10 +588,13 @@ def kinship_leg(args, kg, torch, dist, rank, world, local, n, stride, row_bytes)
             b = torch.empty(Rk * stride, dtype=torch.int64, device="cuda")
             ctx.synth_rows_device(SEED_TABLE + 1, (s * world + rank) * Rk, Rk, b.data_ptr())
             bufs.append(b)
-        ctx.kinship_begin(mc, acc.data_ptr())
+        ctx.kinship_begin(mc)
         for s in range(warm):
             ctx.kinship_submit(bufs[s % 2].data_ptr(), Rk)
+        if world > 1:
+            ctx.kinship_allreduce()           # warm-up: the first collective on a communicator pays its lazy set-up
         ctx.sync()
+        ctx.kinship_begin(mc)
         ctx.kernel_times_reset()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if world > 1:
@@ -602,24 +610,58 @@ def kinship_leg(args, kg, torch, dist, rank, world, local, n, stride, row_bytes)
         ar_ms = None
         if world > 1:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            stream.wait_stream(torch.cuda.current_stream())
+            dist.barrier()
+            torch.cuda.synchronize()
             e0.record(stream)
-            dist.all_reduce(acc)
+            ctx.kinship_allreduce()
             e1.record(stream)
             torch.cuda.synchronize()
             ar_ms = e0.elapsed_time(e1)
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            t = torch.tensor([ms, ar_ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            ms, ar_ms = float(t[0].item()), float(t[1].item())
         _, kept = ctx.kinship_fetch(want_matrix=False)
+    int8_peak = ctx.probe_int8_peak()
     ctx.close()
     hbm_peak, _ = measured_peaks()
     rows = Rk * steps * world
     gbs = rows * row_bytes / (ms * 1e-3) / 1e9
-    return {"metric": "kinship Gram table GB/s", "rows_per_s": rows / (ms * 1e-3), "gb_per_s": gbs,
-            "frac_of_hbm_peak": gbs / hbm_peak / world, "rows_per_step_per_gpu": Rk, "steps": steps,
-            "ms_per_step": ms / steps, "kernel_ms": kt["kinship"][0], "aux_ms": kt["aux"][0],
-            "int_ops_per_row": 2 * n * n, "allreduce_ms": ar_ms, "engine": args.kinship_engine}
+    k_ms, k_launches, k_rows = kt["kinship"]
+    k_pad = 128 * ((64 * ((n + 63) // 64) + 127) // 128)
+    # tensor work the engine issues per row: lower-triangle tiles of 128 x 256 samples, 2 x 128 x 256 int8 ops each
+    n_i = k_pad // 128
+    tiles = sum(i // 2 + 1 for i in range(n_i))
+    ops_row = 2.0 * 128 * 256 * tiles
+    tops = ops_row * k_rows / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    out = {"metric": "kinship Gram table GB/s", "rows_per_s": rows / (ms * 1e-3), "gb_per_s": gbs,
+           "frac_of_hbm_peak": gbs / hbm_peak / world, "rows_per_step_per_gpu": Rk, "steps": steps,
+           "ms_per_step": ms / steps, "kernel_ms": k_ms, "aux_ms": kt["aux"][0],
+           "int_ops_per_row": 2 * n * n, "allreduce_ms": ar_ms, "allreduce_bytes": 8 * (n * n + 1) if world > 1 else None,
+           "allreduce_path": "kg_kinship_allreduce (library-owned NCCL communicator, u64 sum)" if world > 1 else None,
+           "engine": args.kinship_engine, "rows_kept": kept,
+           "roofline": {"bound": "tensor_int8", "achieved": tops, "peak": int8_peak, "unit": "TOP/s",
+                        "frac": tops / int8_peak if int8_peak > 0 else None, "issued_int8_ops_per_row": ops_row,
+                        "peak_source": "measured live: kg_probe_int8_peak"}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = kinship_cpu_baseline(args)
+    return out
+
+
+def kinship_cpu_baseline(args):
+    """The unmodified reference emma_kinship_kmers (oracle/_ref, single-threaded by construction) on a bounded sample."""
+    _, exe = _ref_paths()
+    if not exe.exists():
+        return {"value": None, "unit": "rows/s", "cores": 1, "kind": "reference", "sample": "oracle/_ref/emma_kinship_kmers missing"}
+    n_rows = args.kinship_cpu_rows
+    with tempfile.TemporaryDirectory(prefix="kgkin_") as td:
+        base, _ = _write_ref_inputs(Path(td), n_rows, args.samples, 1)
+        t0 = time.perf_counter()
+        r = subprocess.run([str(exe), "-t", str(base), "-k", "31", "--maf", str(MAF)], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+        wall = time.perf_counter() - t0
+    if r.returncode != 0:
+        return {"value": None, "unit": "rows/s", "cores": 1, "kind": "reference", "sample": "emma_kinship_kmers failed: " + r.stderr[-200:]}
+    return {"value": n_rows / wall, "unit": "rows/s", "cores": 1, "kind": "reference",
+            "sample": f"{n_rows} rows x {args.samples} samples through oracle/_ref/emma_kinship_kmers --maf {MAF}: {wall:.2f} s wall (load + accumulate + print)"}
 
 
 def cpu_baseline(args):
@@ -682,6 +724,7 @@ def main():
     ap.add_argument("--kinship-rows", type=int, default=1 << 20)
     ap.add_argument("--e2e-buffers", type=int, default=3)
     ap.add_argument("--cpu-rows", type=int, default=400000, help="rows of the cpu_baseline sample")
+    ap.add_argument("--kinship-cpu-rows", type=int, default=15000, help="rows of the kinship cpu_baseline sample")
     ap.add_argument("--ref-rows", type=int, default=200000, help="rows per step of --impl reference")
     ap.add_argument("--warmup-ref", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
