@@ -281,6 +281,16 @@ def our_arm(args):
         ctx.select_sync()
         flags = kg.SELECT_LOG if (world > 1 and rank > 0) else 0
         ctx.select_begin(args.kbest, flags)
+        merge_cap = args.merge_log_cap * p
+        if world > 1:
+            # merge buffers (entries of 3 x u64) and a warm-up of the collectives the merge uses: the first large
+            # all-gather on a communicator pays NCCL's lazy channel set-up, which is not part of the job
+            merge_mine = torch.zeros(merge_cap * 3, dtype=torch.int64, device="cuda")
+            merge_all = torch.empty(world * merge_cap * 3, dtype=torch.int64, device="cuda")
+            for _ in range(2):
+                dist.all_gather_into_tensor(merge_all, merge_mine)
+                dist.all_gather_into_tensor(torch.zeros(world * p, dtype=torch.int64, device="cuda"), torch.zeros(p, dtype=torch.int64, device="cuda"))
+            torch.cuda.synchronize()
         ctx.kernel_times_reset()
         launches0 = ctx.launches
         step_ms, seg_ms = [], []
@@ -326,10 +336,11 @@ def our_arm(args):
             # ---- N > 1: exact merge, inside the job: the logs of ranks 1 .. N-1 (what their heaps admitted, in row order)
             # are gathered on every rank and replayed in rank order through rank 0's heaps, which are exact for its
             # own block -> the sequential reference heaps of the whole N x J-row table (kg_select_replay)
-            merge_ms, log_entries = None, None
+            merge_ms, log_entries, merge_phases = None, None, None
             if world > 1:
                 barrier()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                tph = [time.perf_counter()]
                 e0.record(stream)
                 counts = torch.zeros(p, dtype=torch.int64, device="cuda")
                 if rank > 0:
@@ -339,28 +350,32 @@ def our_arm(args):
                 all_counts = all_counts.cpu().numpy().reshape(world, p)
                 totals = all_counts.sum(axis=1)
                 mx = int(totals.max())
-                mine = torch.zeros(max(mx, 1) * 3, dtype=torch.int64, device="cuda")
+                tph.append(time.perf_counter())
+                assert mx <= merge_cap, f"shard log of {mx} entries exceeds the merge buffer ({merge_cap}): raise --merge-log-cap"
                 if rank > 0 and totals[rank] > 0:
-                    off = np.zeros(p + 1, dtype=np.uint64)
-                    off[1:] = np.cumsum(all_counts[rank]).astype(np.uint64)
-                    ctx.select_log(dev_ptr=mine.data_ptr())
-                gathered = torch.empty(world * max(mx, 1) * 3, dtype=torch.int64, device="cuda")
+                    ctx.select_log(dev_ptr=merge_mine.data_ptr())
                 kept_t = torch.tensor([kept, applied], dtype=torch.int64, device="cuda")
                 kept_all = torch.zeros(2 * world, dtype=torch.int64, device="cuda")
                 stream.synchronize()
-                dist.all_gather_into_tensor(gathered, mine)
+                tph.append(time.perf_counter())
+                # one all-gather of the (padded) logs: 24 B per entry over NVLink
+                n_send = max(mx, 1) * 3
+                dist.all_gather_into_tensor(merge_all[: world * n_send], merge_mine[:n_send])
                 dist.all_gather_into_tensor(kept_all, kept_t)
                 torch.cuda.synchronize()
+                tph.append(time.perf_counter())
                 kept_all = kept_all.cpu().numpy().reshape(world, 2)
                 if rank == 0:
                     for r in range(1, world):
                         off = np.zeros(p + 1, dtype=np.uint64)
                         off[1:] = np.cumsum(all_counts[r]).astype(np.uint64)
-                        ctx.select_replay(gathered.data_ptr() + r * max(mx, 1) * 24, off, J, int(kept_all[r, 0]))
+                        ctx.select_replay(merge_all.data_ptr() + r * n_send * 8, off, J, int(kept_all[r, 0]))
                     applied, kept = ctx.select_sync()
                 e1.record(stream)
                 torch.cuda.synchronize()
+                tph.append(time.perf_counter())
                 merge_ms = max_over_ranks(e0.elapsed_time(e1))
+                merge_phases = {k_: round(1e3 * (tph[i + 1] - tph[i]), 3) for i, k_ in enumerate(("counts", "pack", "all_gather", "replay"))}
                 log_entries = int(totals.sum())
                 timed_ms += merge_ms
             barrier()
@@ -475,7 +490,7 @@ def our_arm(args):
             "timed_region_s": job_ms * 1e-3,
             "job": {"rows": rows_total, "seconds": job_ms * 1e-3, "rows_applied_rank0": status_rows[0], "rows_kept_rank0": status_rows[1],
                     "segment_ms": [round(v, 3) for v in seg_ms], "step_ms": [round(v, 3) for v in step_ms], "prefix_ms": prefix_ms,
-                    "merge_ms": merge_ms, "log_entries": log_entries, "selection": sel_stats, "heap_digest": f"{job_digest:016x}",
+                    "merge_ms": merge_ms, "merge_phases_ms_rank0": merge_phases, "log_entries": log_entries, "selection": sel_stats, "heap_digest": f"{job_digest:016x}",
                     "threshold_phenotype0": float(thr_end[0])},
             "steady_state": {"value": R * len(steady) * world / (sum(steady) * 1e-3) if steady else None, "unit": "k-mers/s",
                              "note": "secondary: the second half of the job's steps only (rank 0's device time)"},
@@ -711,6 +726,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--job-rows", type=int, default=2_300_000_000, help="rows per GPU of the timed job (config 2: 2.3e9)")
     ap.add_argument("--hbm-fraction", type=float, default=0.72, help="share of the free HBM the resident batch ring may use")
+    ap.add_argument("--merge-log-cap", type=int, default=1 << 17, help="N > 1: log entries per phenotype the merge buffers hold")
     ap.add_argument("--prefix-rows", type=int, default=1 << 23, help="N > 1: rows of the shared prefix ranks > 0 warm-start from")
     ap.add_argument("--e2e-rows", type=int, default=1 << 23, help="rows per step of the e2e (pinned host memory) leg")
     ap.add_argument("--parity-tile-rows", type=int, default=1 << 23)

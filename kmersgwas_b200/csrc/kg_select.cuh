@@ -250,11 +250,41 @@ __global__ void __launch_bounds__(KG_SEL_THREADS) kg_select_replay_kernel(const 
 #ifdef KG_SEL_PROFILE
 	long long t_loop = 0, t_rep = 0, t_all0 = clock64();
 #endif
+	__shared__ uint32_t s_warp_cnt[KG_SEL_THREADS / 32];
+	__shared__ uint32_t s_m;
+	__shared__ uint32_t s_size_now;
 	for (uint32_t b0 = 0; b0 < n; b0 += KG_SEL_STAGE) {
-		const uint32_t m = min((uint32_t)KG_SEL_STAGE, n - b0);
-		for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
-			stage[i] = cand[(PRESORTED || n == 1) ? b0 + i : order[b0 + i]];
+		const uint32_t m_in = min((uint32_t)KG_SEL_STAGE, n - b0);
+		// Stage the block, dropping IN PARALLEL (order kept) every candidate the sequential loop would reject on its
+		// first comparison anyway: the heap's minimum only rises, so a score that is not above the minimum at the
+		// start of the block (or above the floor) cannot be admitted later in the block either.
+		if (threadIdx.x == 0) { s_m = 0; s_size_now = size; }
 		__syncthreads();
+		const bool full = s_size_now >= K;
+		const double top = full ? hs[0] : 0.0;
+		for (uint32_t c0 = 0; c0 < m_in; c0 += KG_SEL_THREADS) {
+			const uint32_t i = c0 + threadIdx.x;
+			KgCand c;
+			bool keep = false;
+			if (i < m_in) {
+				c = cand[(PRESORTED || n == 1) ? b0 + i : order[b0 + i]];
+				keep = (!full || c.score > top) && !(c.score <= floor_thr);
+			}
+			const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+			if ((threadIdx.x & 31) == 0) s_warp_cnt[threadIdx.x >> 5] = __popc(bal);
+			__syncthreads();
+			uint32_t base = s_m;
+			for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) base += s_warp_cnt[w];
+			if (keep) stage[base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u))] = c;
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				uint32_t t = 0;
+				for (uint32_t w = 0; w < KG_SEL_THREADS / 32; w++) t += s_warp_cnt[w];
+				s_m += t;
+			}
+			__syncthreads();
+		}
+		const uint32_t m = s_m;
 		if (threadIdx.x == 0) {
 #ifdef KG_SEL_PROFILE
 			const long long tl0 = clock64();
