@@ -255,6 +255,10 @@ def our_arm(args):
     ctx = kg.Context.identity(n, device=local, stream=stream.cuda_stream)
     ctx.set_option(kg.OPT_SCAN_ENGINE, args.scan_engine)
     ctx.set_option(kg.OPT_KERNEL_TIMING, 1)
+    if args.max_round:
+        ctx.set_option(kg.OPT_SELECT_MAX_ROUND, args.max_round)
+    if args.growth_permille:
+        ctx.set_option(kg.OPT_SELECT_GROWTH_PERMILLE, args.growth_permille)
     ctx.set_phenotypes(y, mc)
     int8_peak = ctx.probe_int8_peak()
 
@@ -726,6 +730,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--job-rows", type=int, default=2_300_000_000, help="rows per GPU of the timed job (config 2: 2.3e9)")
     ap.add_argument("--hbm-fraction", type=float, default=0.72, help="share of the free HBM the resident batch ring may use")
+    ap.add_argument("--max-round", type=int, default=0, help="longest selection round in rows (0 = library default)")
+    ap.add_argument("--growth-permille", type=int, default=0, help="selection round growth (0 = library default)")
     ap.add_argument("--merge-log-cap", type=int, default=1 << 17, help="N > 1: log entries per phenotype the merge buffers hold")
     ap.add_argument("--prefix-rows", type=int, default=1 << 23, help="N > 1: rows of the shared prefix ranks > 0 warm-start from")
     ap.add_argument("--e2e-rows", type=int, default=1 << 23, help="rows per step of the e2e (pinned host memory) leg")

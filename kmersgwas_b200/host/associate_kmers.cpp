@@ -42,6 +42,10 @@ void run_shard_device(Shard &sh, size_t min_count, size_t batch_size, bool verbo
                       uint64_t first, uint64_t count, uint64_t prefix_rows, bool is_first_shard) {
 	try {
 		MultipleKmersDataBases &db = *sh.db;
+		// Nothing comes back per batch on this path, so --batch_size only bounds memory: the table is streamed in tiles of at
+		// most 256 MB (three pinned buffers: one being read from the file, one in flight to the GPU, one being scanned)
+		const size_t row_bytes = 8 * (1 + db.file_words());
+		batch_size = min<size_t>(batch_size, max<size_t>(65536, (256u << 20) / row_bytes));
 		if (!is_first_shard) {
 			db.restrict_to_rows(0, prefix_rows);
 			while (db.load_kmers(batch_size, min_count)) db.add_loaded_kmers_to_device_heaps();
@@ -149,6 +153,9 @@ int main(int argc, char *argv[]) {
 			throw CliOptions::ParseError("--select must be auto, device or host");
 		const string table = options.str("kmers_table");
 
+		const double t_start = get_time();
+		const bool phase_times = getenv("KMERSGWAS_PHASE_TIMES") != nullptr;
+		auto phase = [&](const char *what) { if (phase_times) cerr << "[phase] " << what << "\t" << get_time() - t_start << " s" << endl; };
 		// phenotypes (reference :81-88)
 		pair<vector<string>, vector<PhenotypeList> > phenotypes_info = load_phenotypes_file(options.str("phenotype_file"));
 		const size_t phenotypes_n = phenotypes_info.first.size();
@@ -173,6 +180,7 @@ int main(int argc, char *argv[]) {
 		KmersSet pa_patterns_counter;
 		const bool count_patterns = options.count("pattern_counter") > 0;
 
+		phase("phenotypes loaded");
 		// ---- pass 1: association scan ----------------------------------------------------------
 		vector<unique_ptr<Shard> > shard_ptrs(n_gpus);
 		for (auto &sp : shard_ptrs) sp.reset(new Shard());
@@ -189,6 +197,7 @@ int main(int argc, char *argv[]) {
 		for (size_t j = 0; j < phenotypes_n; j++) capacities[j] = k_heap[j].capacity();
 
 		// device heaps (kg_select_*) when every capacity fits them (the pipeline's -n 10001 does); else host replay
+		phase("contexts created");
 		bool device_heaps = select_mode != "host";
 		if (device_heaps)
 			for (size_t g = 0; g < n_gpus && device_heaps; g++)
@@ -273,6 +282,7 @@ int main(int argc, char *argv[]) {
 			for (size_t j = 0; j < phenotypes_n; j++) hp[j] = &k_heap[j];
 			kgh_merge_shards(states, hp.data(), hp.size());
 		}
+		phase("pass 1 done (heaps final)");
 		const uint64_t n_patterns = have_device_patterns ? device_patterns : (uint64_t)pa_patterns_counter.size();
 		if (count_patterns) cerr << "Total patterns\t" << n_patterns << endl;
 
@@ -284,20 +294,37 @@ int main(int argc, char *argv[]) {
 			best_kmers.push_back(k_heap[j].get_kmers_for_output(kmer_length));
 			k_heap[j].empty_heap();
 		}
+		phase("heaps read out");
 		MultipleKmersDataBases &db0 = *shards(0).db;
-		for (size_t j = 0; j < phenotypes_n; j++) {
-			const string base = fn_base + "." + std::to_string(j) + "." + phenotypes_info.first[j];
-			BedBimFilesHandle handle(base);
-			write_fam_file(p_list[j], base + ".fam");
-			db0.output_plink_bed_file_selected(handle, best_kmers[j].list);
-			handle.close();
-			cerr << ".";
+		{
+			// the phenotypes' PLINK triples are independent: written concurrently (the reference writes them from one pass 2)
+			const unsigned n_thr = (unsigned)min<size_t>(phenotypes_n, max(1u, kgh_host_threads()));
+			vector<thread> writers;
+			vector<exception_ptr> werr(n_thr);
+			for (unsigned t = 0; t < n_thr; t++)
+				writers.emplace_back([&, t] {
+					try {
+						for (size_t j = t; j < phenotypes_n; j += n_thr) {
+							const string base = fn_base + "." + std::to_string(j) + "." + phenotypes_info.first[j];
+							BedBimFilesHandle handle(base);
+							write_fam_file(p_list[j], base + ".fam");
+							db0.output_plink_bed_file_selected(handle, best_kmers[j].list);
+							handle.close();
+						}
+					} catch (...) {
+						werr[t] = current_exception();
+					}
+				});
+			for (auto &w : writers) w.join();
+			for (auto &e : werr) if (e) rethrow_exception(e);
+			for (size_t j = 0; j < phenotypes_n; j++) cerr << ".";
 		}
 		cerr << endl;
 		if (count_patterns) {
 			ofstream fout(fn_base + ".pattern_counter");
 			fout << n_patterns << endl;
 		}
+		phase("PLINK files written");
 		ofstream fout(fn_base + ".tested_kmers");
 		fout << k_heap[0].number_of_insertion() << endl;
 		fout.close();

@@ -35,8 +35,8 @@ void read_fully(int fd, void *dst, size_t bytes, uint64_t offset, const string &
 // A batch is read by several threads, each pread-ing its own slice: one thread copies ~5 GB/s out of the page cache,
 // the PCIe link behind the pinned buffer takes ~55 GB/s.
 void read_parallel(int fd, void *dst, size_t bytes, uint64_t offset, const string &path) {
-	const size_t kSlice = 64u << 20;
-	unsigned n_thr = (unsigned)std::min<size_t>((bytes + kSlice - 1) / kSlice, 8);
+	const size_t kSlice = 16u << 20;
+	unsigned n_thr = (unsigned)std::min<size_t>((bytes + kSlice - 1) / kSlice, std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
 	if (const char *e = getenv("KMERSGWAS_READ_THREADS")) n_thr = std::max(1, atoi(e));
 	if (n_thr <= 1) { read_fully(fd, dst, bytes, offset, path); return; }
 	std::vector<std::thread> thr;
@@ -392,15 +392,60 @@ size_t MultipleKmersDataBases::output_plink_bed_file(BedBimFilesHandle &f, const
 	return index;
 }
 
-void MultipleKmersDataBases::output_plink_bed_file_selected(BedBimFilesHandle &f, const vector<AssociationOutputInfo> &kmer_list) {
+// The selected rows of one phenotype -> its .bim / .bed pair, without re-streaming the table: each row is read with one
+// pread, squeezed (memcpy when the column map is the identity) and expanded to PLINK's 2 bits per sample with a byte
+// table (8 presence bits -> 2 output bytes); both files are assembled in memory and written once.  Thread-safe
+// (const, pread), so the CLI writes the phenotypes' files concurrently.
+void MultipleKmersDataBases::output_plink_bed_file_selected(BedBimFilesHandle &f, const vector<AssociationOutputInfo> &kmer_list) const {
+	static const struct Lut {
+		uint16_t v[256];
+		Lut() {
+			for (unsigned b = 0; b < 256; b++) {
+				uint16_t o = 0;
+				for (unsigned k = 0; k < 8; k++)
+					if (b & (1u << k)) o = (uint16_t)(o | (3u << (2 * k)));   // 11 = present, 00 = absent (:218-239)
+				v[b] = o;
+			}
+		}
+	} lut;
 	const size_t stride = 1 + m_hash_words_db_file;
+	const size_t n_bytes = (m_accessions + 3) / 4;
+	bool identity = m_accessions == m_accessions_db_file;
+	for (size_t i = 0; identity && i < m_accessions; i++)
+		identity = (size_t)m_map_word_index[i] * WLEN + m_map_bit_index[i] == i;
 	vector<uint64_t> file_row(stride), mem_row;
+	string bed(kmer_list.size() * n_bytes, '\0'), bim;
+	bim.reserve(kmer_list.size() * (m_kmer_len + 24));
+	vector<uint8_t> rec(2 * 8 * m_hash_words + 16);
 	for (size_t i = 0; i < kmer_list.size(); i++) {
 		const uint64_t row = std::get<2>(kmer_list[i]);
 		read_fully(m_fd, file_row.data(), stride * 8, kHeaderBytes + row * stride * 8, m_table_path);
-		squeeze_row(file_row.data(), mem_row);
-		write_PA(bits2kmer31(std::get<0>(kmer_list[i]), m_kmer_len) + "_" + std::to_string(std::get<1>(kmer_list[i])), mem_row, f);
+		const uint64_t *words;
+		if (identity) {
+			words = file_row.data() + 1;
+		} else {
+			squeeze_row(file_row.data(), mem_row);
+			words = mem_row.data();
+		}
+		const size_t n_words = identity ? m_hash_words_db_file : m_hash_words;
+		const uint8_t *src = reinterpret_cast<const uint8_t *>(words);
+		for (size_t b = 0; b < n_words * 8; b++) {
+			const uint16_t o = lut.v[src[b]];
+			rec[2 * b] = (uint8_t)(o & 0xFF);
+			rec[2 * b + 1] = (uint8_t)(o >> 8);
+		}
+		// samples beyond N are absent in the squeezed row; in the raw identity row the file has no such columns either
+		char *dst = &bed[i * n_bytes];
+		memcpy(dst, rec.data(), n_bytes);
+		if (m_accessions % 4) dst[n_bytes - 1] = (char)(dst[n_bytes - 1] & ((1u << (2 * (m_accessions % 4))) - 1u));
+		bim += "0\t";
+		bim += bits2kmer31(std::get<0>(kmer_list[i]), m_kmer_len);
+		bim += '_';
+		bim += std::to_string(std::get<1>(kmer_list[i]));
+		bim += "\t0\t0\t0\t1\n";
 	}
+	f.f_bim.write(bim.data(), (std::streamsize)bim.size());
+	f.f_bed.write(bed.data(), (std::streamsize)bed.size());
 }
 
 // ---- whole-table PLINK conversion (kmers_table_to_bed) ---------------------------------------------

@@ -74,7 +74,7 @@ class MultipleKmersDataBases {
 		std::size_t output_plink_bed_file(BedBimFilesHandle &f, const std::vector<AssociationOutputInfo> &kmer_list,
 		                                  std::size_t index) const;
 		// Same output without re-streaming the table: reads only the selected rows from the file.
-		void output_plink_bed_file_selected(BedBimFilesHandle &f, const std::vector<AssociationOutputInfo> &kmer_list);
+		void output_plink_bed_file_selected(BedBimFilesHandle &f, const std::vector<AssociationOutputInfo> &kmer_list) const;
 
 		void update_presence_absence_pattern_counter(KmersSet &pa_pattern_counter) const;
 		// Device form of the same counter (kg_patterns_*): the hashes of the kept rows go into a device hash set while the
