@@ -252,3 +252,45 @@ def test_build_kmers_table_byte_identical(bins, tmp_path, n_acc, n_all, rng_rows
     assert np.array_equal(rows[:, 0], all_k)
     bits = np.unpackbits(np.ascontiguousarray(rows[:, 1:]).view(np.uint8), axis=1, bitorder="little")[:, :n_acc]
     assert np.array_equal(bits.astype(bool), member)
+
+
+def test_associate_kmers_device_overflow_falls_back_to_host_replay(bins, tmp_path):
+    """scores that rise along the table make every row a candidate: a round overflows its device candidate segment, the
+    CLI notices at the end (DeviceSelectionOverflow) and re-runs pass 1 through the host replay path -- same files"""
+    n_file, n_rows = 64, 300000
+    names = [f"s{i}" for i in range(n_file)]
+    table = S.synth_table(123, n_rows, n_file)
+    y = S.synth_phenotypes(124, n_file, 1)
+    idx = np.arange(n_file)
+    mc = S.min_count_of(n_file, 0.05, 5)
+    keep, scores, kept = S.oracle_scan(table, n_file, idx // 64, idx % 64, y, mc)
+    order = np.argsort(scores[0], kind="stable")          # ascending scores: every kept row beats the heap minimum
+    table = np.ascontiguousarray(table[order])
+    S.write_table(tmp_path / "t", table, n_file, names)
+    S.write_pheno(tmp_path / "p.tsv", names, y)
+    dirs = []
+    for tag, exe in (("ref", S.REF_DIR / "associate_kmers"), ("ours", bins / "associate_kmers")):
+        out = tmp_path / tag
+        out.mkdir()
+        r = _run(exe, ["-p", tmp_path / "p.tsv", "-b", "x", "-o", out, "--kmers_table", tmp_path / "t", "-n", 100, "--kmer_len", 31,
+                       "--k_mers_scores", "--pattern_counter"])
+        assert r.returncode == 0, r.stderr[-2000:]
+        if tag == "ours":
+            assert "re-running pass 1 through the host replay path" in r.stderr
+        dirs.append(out)
+    _same_dir(*dirs)
+
+
+def test_emma_kinship_kmers_two_gpus_allreduce(bins, tmp_path):
+    """--gpus 2: the shards' u64 accumulators are summed by one NCCL all-reduce inside the library
+    (kg_comm_init_all + kg_kinship_allreduce_all); the matrix printed is the reference's.  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g = S.Golden("thaliana_n1135")
+    table, _ = g.write_inputs(tmp_path)
+    args = ["-t", table, "-k", 31, "--maf", 0.05]
+    ref = _run(S.REF_DIR / "emma_kinship_kmers", args)
+    ours = _run(bins / "emma_kinship_kmers", args + ["--gpus", 2])
+    assert ref.returncode == 0 and ours.returncode == 0, ours.stderr[-2000:]
+    assert ours.stdout == ref.stdout
