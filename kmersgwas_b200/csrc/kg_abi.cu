@@ -1392,6 +1392,9 @@ struct KgNccl {
 	std::string err;
 	bool load() {
 		if (lib) return true;
+		// NCCL writes its version banner (NCCL_DEBUG=VERSION or higher) to stdout unless told otherwise; stdout belongs to
+		// the caller (emma_kinship_kmers prints the matrix there)
+		setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
 		for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
 			lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
 			if (lib) break;
@@ -1412,6 +1415,16 @@ struct KgNccl {
 } g_nccl;
 }  // namespace
 
+// NCCL prints its version banner with the NCCL_DEBUG=VERSION level straight to stdout (NCCL_DEBUG_FILE only applies to
+// higher levels); stdout belongs to the caller (emma_kinship_kmers prints the matrix there), so fd 1 points at stderr
+// while a communicator is being created.
+#include <unistd.h>
+struct KgStdoutToStderr {
+	int saved;
+	KgStdoutToStderr() { fflush(stdout); saved = dup(1); if (saved >= 0) dup2(2, 1); }
+	~KgStdoutToStderr() { fflush(stdout); if (saved >= 0) { dup2(saved, 1); close(saved); } }
+};
+
 #define KG_NCCL(ctx, expr)                                                                         \
 	do {                                                                                           \
 		ncclResult_t r_ = (expr);                                                                  \
@@ -1428,6 +1441,7 @@ extern "C" kg_status kg_comm_unique_id(void *id128) {
 	if (!g_nccl.load()) { g_create_error = g_nccl.err; return KG_ERR_CUDA; }
 	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
 	ncclUniqueId id;
+	KgStdoutToStderr quiet;
 	if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return KG_ERR_CUDA; }
 	memcpy(id128, &id, sizeof id);
 	return KG_OK;
@@ -1441,6 +1455,7 @@ extern "C" kg_status kg_comm_init_rank(kg_ctx *c, const void *id128, int n_ranks
 	ncclUniqueId id;
 	memcpy(&id, id128, sizeof id);
 	ncclComm_t comm = nullptr;
+	KgStdoutToStderr quiet;
 	KG_NCCL(c, g_nccl.CommInitRank(&comm, n_ranks, id, rank));
 	c->nccl_comm = comm;
 	return KG_OK;
@@ -1453,6 +1468,7 @@ extern "C" kg_status kg_comm_init_all(kg_ctx *const *ctxs, int n) {
 	std::vector<int> devs(n);
 	for (int i = 0; i < n; i++) { devs[i] = ctxs[i]->device; kg_comm_destroy(ctxs[i]); }
 	std::vector<ncclComm_t> comms(n, nullptr);
+	KgStdoutToStderr quiet;
 	KG_NCCL(c0, g_nccl.CommInitAll(comms.data(), n, devs.data()));
 	for (int i = 0; i < n; i++) ctxs[i]->nccl_comm = comms[i];
 	return KG_OK;
