@@ -147,6 +147,19 @@ __device__ __forceinline__ float kg_filter_group_threshold(const KgFilterGroupCo
 	return __fsub_rd(__fmaf_rd(gc.alpha, g, -gc.kappa), slack);
 }
 
+// max |v[j]| over 16 int32 accumulators: two reduction trees of 3-input max / min (8 + 8 operations, depth 3)
+__device__ __forceinline__ int kg_absmax16(const uint32_t (&v)[16]) {
+	const int a0 = __vimax3_s32((int)v[0], (int)v[1], (int)v[2]), a1 = __vimax3_s32((int)v[3], (int)v[4], (int)v[5]);
+	const int a2 = __vimax3_s32((int)v[6], (int)v[7], (int)v[8]), a3 = __vimax3_s32((int)v[9], (int)v[10], (int)v[11]);
+	const int a4 = __vimax3_s32((int)v[12], (int)v[13], (int)v[14]);
+	const int b0 = __vimin3_s32((int)v[0], (int)v[1], (int)v[2]), b1 = __vimin3_s32((int)v[3], (int)v[4], (int)v[5]);
+	const int b2 = __vimin3_s32((int)v[6], (int)v[7], (int)v[8]), b3 = __vimin3_s32((int)v[9], (int)v[10], (int)v[11]);
+	const int b4 = __vimin3_s32((int)v[12], (int)v[13], (int)v[14]);
+	const int mx = __vimax3_s32(__vimax3_s32(a0, a1, a2), __vimax3_s32(a3, a4, (int)v[15]), 0);
+	const int mn = __vimin3_s32(__vimin3_s32(b0, b1, b2), __vimin3_s32(b3, b4, (int)v[15]), 0);
+	return max(mx, -mn);
+}
+
 template <int MODE>  // 0 = list candidate rows, 1 = debug: dump accumulators
 __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const KgFilterParams prm) {
 	extern __shared__ uint8_t kg_f_smem_raw[];
@@ -387,23 +400,13 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 						hm = fminf(n1f, n0f);                              // m = size of the smaller group
 						g = __fmul_rd(__fsqrt_rd(n1f * n0f), 0.999999f);   // <= sqrt(den); den is exact in fp32 (< 2^24)
 					}
-					{
-						int mx = 0, mn = 0;
-#pragma unroll
-						for (int j = 0; j < 16; j += 2) {
-							mx = __vimax3_s32(mx, (int)v[j], (int)v[j + 1]);
-							mn = __vimin3_s32(mn, (int)v[j], (int)v[j + 1]);
-						}
-						if (!((float)max(mx, -mn) < kg_filter_group_threshold(sConst[c0 >> 4], g, hm))) gmask |= 1u << (c0 >> 4);
-					}
+					// max |accumulator| of each group: 3-input min / max TREES (depth 3 instead of a chain of 8: the epilogue
+					// warps are bound by dependent-issue latency, profiles/r02_scan_filter_ncu.md), both groups interleaved
+					const int amax_v = kg_absmax16(v);
+					if (!((float)amax_v < kg_filter_group_threshold(sConst[c0 >> 4], g, hm))) gmask |= 1u << (c0 >> 4);
 					if (second) {
-						int mx = 0, mn = 0;
-#pragma unroll
-						for (int j = 0; j < 16; j += 2) {
-							mx = __vimax3_s32(mx, (int)u[j], (int)u[j + 1]);
-							mn = __vimin3_s32(mn, (int)u[j], (int)u[j + 1]);
-						}
-						if (!((float)max(mx, -mn) < kg_filter_group_threshold(sConst[(c0 >> 4) + 1], g, hm)))
+						const int amax_u = kg_absmax16(u);
+						if (!((float)amax_u < kg_filter_group_threshold(sConst[(c0 >> 4) + 1], g, hm)))
 							gmask |= 1u << ((c0 >> 4) + 1);
 					}
 				}
