@@ -260,6 +260,7 @@ def our_arm(args):
     if args.growth_permille:
         ctx.set_option(kg.OPT_SELECT_GROWTH_PERMILLE, args.growth_permille)
     ctx.set_phenotypes(y, mc)
+    fshape = ctx.filter_shape()
     int8_peak = ctx.probe_int8_peak()
 
     # ---- batch ring: as many steps resident in HBM as fit; the job runs in segments of that many steps, each segment
@@ -442,13 +443,14 @@ def our_arm(args):
                 traffic = tr[dom]["dram_bytes_per_row"] * dom_rows / max(dom_launches, 1)
         except Exception:
             pass
-        k_pad = 128 * ((64 * w_file + 127) // 128)
-        p_pad = 16 * ((p + 1 + 15) // 16)
-        f_ms, f_launches, f_rows = kt["scan_filter"]
+        k_pad = fshape["k_pad"] or 128 * ((64 * w_file + 127) // 128)
+        p_pad = fshape["p_pad"] or 16 * ((p + 1 + 15) // 16)              # accumulator columns of ONE pass
+        n_pass = max(fshape["n_pass"], 1)
+        f_ms, f_launches, f_rows = kt["scan_filter"]                       # rows summed over launches: every pass counts its rows
         tensor_ops = 2.0 * k_pad * p_pad * f_rows                          # int8 multiply-adds x 2 the filter issues
         tensor_tops = tensor_ops / (f_ms * 1e-3) / 1e12 if f_ms > 0 else 0.0
         t_hbm_row = row_bytes / (hbm_peak * 1e9)
-        t_tensor_row = 2.0 * k_pad * p_pad / (int8_peak * 1e12) if int8_peak > 0 else 0.0
+        t_tensor_row = 2.0 * k_pad * p_pad * n_pass / (int8_peak * 1e12) if int8_peak > 0 else 0.0
         tensor_binds = dom == "scan_filter" and t_tensor_row > t_hbm_row
         steady = step_ms[len(step_ms) // 2:]
         roofline = {
@@ -464,13 +466,13 @@ def our_arm(args):
                     "algorithmic_bytes_per_row": row_bytes},
             "tensor": {"achieved_int8_tops": tensor_tops, "measured_int8_peak_tops": int8_peak, "nominal_dense_int8_tops": 4500.0,
                        "frac_of_measured": tensor_tops / int8_peak if int8_peak > 0 else None,
-                       "mma_shape_per_128_rows": f"M=128 N={p_pad} K={k_pad}",
+                       "mma_shape_per_128_rows": f"M=128 N={p_pad} K={k_pad} x {n_pass} pass(es)",
                        "per_row_bounds_ps": {"hbm": t_hbm_row * 1e12, "tensor_int8": t_tensor_row * 1e12}},
             "launches": dom_launches, "avg_launch_ms": dom_ms / max(dom_launches, 1),
             "kernel_ms_share_of_job": {k_: v[0] / job_ms for k_, v in kt.items() if v[1]},
             "kernels": {k_: {"ms_total": v[0], "launches": v[1], "rows": v[2]} for k_, v in kt.items() if v[1]},
             "note": (f"achieved = algorithmic work of the dominant kernel's launches / their CUDA-event time on the launching stream; HBM: "
-                     f"{row_bytes} B/row; tensor: 2 x K_pad x P_pad int8 ops/row.  At P={p} the int8 tensor pipe binds the scan "
+                     f"{row_bytes} B/row; tensor: 2 x K_pad x P_pad int8 ops per row and pass.  At P={p} the int8 tensor pipe binds the scan "
                      f"(SURVEY 7 hard part 2), so frac is against the live-measured int8 peak; the hbm block gives the GB/s view"),
         }
         line = {

@@ -159,6 +159,11 @@ kg_status kg_mac_filter(kg_ctx *ctx, const uint64_t *rows, uint64_t n_rows, uint
 kg_status kg_scan_scores_dense(kg_ctx *ctx, const uint64_t *rows, uint64_t n_rows,
                                uint8_t *keep, double *scores);
 
+/* Geometry of scan engine 2 for the phenotypes set (all 0 when the engine is unavailable for the shape): passes over a
+ * tile, accumulator columns per pass (UMMA N), contraction length (UMMA K total), raw row-block stages.  The tensor work
+ * of one filter launch over R rows is 2 * k_pad * p_pad * R int8 operations (bench.py's roofline). */
+kg_status kg_scan_filter_shape(kg_ctx *ctx, uint32_t *n_pass, uint32_t *p_pad, uint32_t *k_pad, uint32_t *raw_stages);
+
 /* Testing aid for scan engine 2 (int8 tensor-core filter): the filter's exact integer sums
  * q[r * n_pheno + p] = sum over the set presence bits of row r of the int8-quantised, centred phenotype p,
  * and (optional, may be NULL) the quantised values yq[p * 64 * W_file + file_column].  Host outputs.

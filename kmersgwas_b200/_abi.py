@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "kg_select_digest", "kg_select_thresholds", "kg_select_log_reset", "kg_select_log_counts", "kg_select_log_export",
     "kg_select_replay", "kg_select_set_floor", "kg_select_export_scores", "kg_select_kmax", "kg_probe_int8_peak", "kg_select_stats",
     "kg_comm_unique_id", "kg_comm_init_rank", "kg_comm_init_all", "kg_kinship_allreduce", "kg_kinship_allreduce_all",
-    "kg_stream_mark", "kg_stream_wait", "kg_snps_scores", "kg_table_build",
+    "kg_stream_mark", "kg_stream_wait", "kg_snps_scores", "kg_table_build", "kg_scan_filter_shape",
     "kg_patterns_begin", "kg_patterns_attach", "kg_patterns_submit", "kg_patterns_count", "kg_patterns_export", "kg_patterns_insert",
 ]
 
@@ -128,6 +128,7 @@ def load():
     lib.kg_patterns_insert.argtypes = [vp, vp, u64]
     lib.kg_snps_scores.argtypes = [C.c_int, vp, u64, C.c_uint32, vp, vp, C.c_uint32, vp, C.c_uint32, C.c_double, vp]
     lib.kg_table_build.argtypes = [C.c_int, vp, u64, C.c_uint32, vp, vp, vp]
+    lib.kg_scan_filter_shape.argtypes = [vp, u32p, u32p, u32p, u32p]
     lib.kg_stream_mark.argtypes = [vp, u64p]
     lib.kg_stream_wait.argtypes = [vp, u64]
     lib.kg_select_kmax.argtypes = [vp]
@@ -284,6 +285,11 @@ class Context:
         self._chk(self._lib.kg_mac_filter(self._h, _rows_ptr(rows), int(n_rows), int(min_count),
                                           keep.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(kept)))
         return keep.astype(bool), int(kept.value)
+
+    def filter_shape(self) -> dict:
+        a, b, c_, d = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        self._chk(self._lib.kg_scan_filter_shape(self._h, C.byref(a), C.byref(b), C.byref(c_), C.byref(d)))
+        return dict(n_pass=a.value, p_pad=b.value, k_pad=c_.value, raw_stages=d.value)
 
     def filter_sums(self, rows, n_rows: int):
         """-> (q[n_rows, P] int32 exact sums of the tensor-core filter, yq[P, 64*W_file] int8 quantised phenotypes)"""

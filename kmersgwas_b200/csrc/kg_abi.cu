@@ -1051,6 +1051,17 @@ extern "C" kg_status kg_scan_scores_dense(kg_ctx *c, const uint64_t *rows, uint6
 	return KG_OK;
 }
 
+extern "C" kg_status kg_scan_filter_shape(kg_ctx *c, uint32_t *n_pass, uint32_t *p_pad, uint32_t *k_pad, uint32_t *raw_stages) {
+	if (!c) return KG_ERR_INVALID;
+	if (!c->d_y_lane) KG_FAIL(c, KG_ERR_STATE, "kg_scan_filter_shape: call kg_scan_set_phenotypes first");
+	const bool ok = c->tc.scan_ready;
+	if (n_pass) *n_pass = ok ? c->tc.n_pass : 0;
+	if (p_pad) *p_pad = ok ? c->tc.p_pad : 0;
+	if (k_pad) *k_pad = ok ? 128 * ((c->w_file + 1) / 2) : 0;
+	if (raw_stages) *raw_stages = ok ? c->tc.raw_stages : 0;
+	return KG_OK;
+}
+
 extern "C" kg_status kg_scan_filter_sums(kg_ctx *c, const uint64_t *rows, uint64_t n_rows, int32_t *q, int8_t *yq) {
 	if (!c) return KG_ERR_INVALID;
 	if (!c->d_y_lane) KG_FAIL(c, KG_ERR_STATE, "kg_scan_filter_sums: call kg_scan_set_phenotypes first");

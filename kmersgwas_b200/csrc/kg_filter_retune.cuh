@@ -27,6 +27,7 @@ struct KgRetuneParams {
 	int8_t *yq_image;            // [n_pass][b_bytes] out (on reorder)
 	int32_t *tile_pheno;         // [n_pass][p_pad] out (on reorder)
 	KgFilterGroupConst *gconst;  // [n_pass][16] group slots
+	int32_t *thr_tab;            // [n_pass][p_pad / 16][n_used + 1] group bound per row popcount (KgFilterParams::thr_tab)
 	float *alpha_out, *kappa_out;   // [P] per-phenotype constants of the per-column test
 	unsigned long long *status;  // KG_SEL_ST_* (reorder counter) or NULL
 	uint32_t force;              // 1: rebuild regardless of the tightness test
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(256) kg_filter_retune_kernel(const KgRetunePar
 	prm.yq_image += (size_t)pass * prm.b_bytes;
 	prm.tile_pheno += (size_t)pass * prm.p_pad;
 	prm.gconst += (size_t)pass * 16;
+	prm.thr_tab += (size_t)pass * kg_filter_tab_floats(prm.p_pad, prm.n_used);
 	__shared__ float s_alpha[128], s_kappa[128];
 	__shared__ uint32_t s_col_new[128], s_col_cur[128];
 	__shared__ float s_amin[2][16];
@@ -51,6 +53,7 @@ __global__ void __launch_bounds__(256) kg_filter_retune_kernel(const KgRetunePar
 	__shared__ int s_reorder;
 	__shared__ float s_red[256];
 	__shared__ float s_slope;
+	__shared__ KgFilterGroupConst s_gc[16];
 	const uint32_t P0 = pass * prm.cols_per_pass, PC = min(prm.cols_per_pass, prm.n_pheno - P0), N = prm.n_used;
 	const uint32_t n_groups = prm.p_pad / 16;
 	const uint32_t tid = threadIdx.x;
@@ -186,5 +189,12 @@ __global__ void __launch_bounds__(256) kg_filter_retune_kernel(const KgRetunePar
 		}
 		gc.pad_[0] = gc.pad_[1] = 0.0f;
 		prm.gconst[tid] = gc;
+		s_gc[tid] = gc;
+	}
+	__syncthreads();
+	// 6. the groups' bounds as a table over the row popcount: the filter's epilogue looks them up
+	for (uint32_t e = tid; e < n_groups * (N + 1); e += blockDim.x) {
+		const uint32_t g = e / (N + 1), n1 = e - g * (N + 1);
+		prm.thr_tab[e] = kg_filter_bound_to_int(kg_filter_group_threshold_n1(s_gc[g], n1, N));
 	}
 }

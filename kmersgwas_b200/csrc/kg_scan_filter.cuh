@@ -95,7 +95,13 @@ struct KgFilterParams {
 	const int8_t *yq_image;    // B operand in its shared-memory byte order, b_bytes long
 	uint32_t b_bytes;          // (p_pad / 8) * sbo_b
 	uint32_t sbo_b;            // ceil(w_file / 2) * 1024: K_pad = 128 * ceil(w_file / 2) columns
-	const KgFilterGroupConst *gconst;   // [p_pad / 16]; groups without phenotype columns hold alpha = +inf
+	const KgFilterGroupConst *gconst;   // [p_pad / 16]; groups without phenotype columns hold alpha = +inf (kept for diagnostics)
+	const int32_t *thr_tab;    // [p_pad / 16][n_used + 1]: the group's bound as a function of the row popcount n1,
+	                           //   alpha * sqrt(n1 (N - n1)) - kappa - slack(min(n1, N - n1)), every step rounded down, as the
+	                           //   smallest INTEGER max|Q| that is not ruled out (kg_filter_bound_to_int) -- written by
+	                           //   kg_filter_retune_kernel, copied to shared memory at kernel start: the epilogue then pays one
+	                           //   load and one integer compare per (row, group) instead of ~15 dependent ALU operations (its
+	                           //   warps are bound by dependent-issue latency)
 	uint32_t n_used, min_count;
 	uint32_t *row_list;        // out: rows of the tile (index inside the tile) that could not be ruled out, any order
 	unsigned long long *n_listed;   // device counter for row_list (zeroed before the launch); capacity = n_rows
@@ -113,8 +119,11 @@ struct KgFilterParams {
 };
 
 __host__ __device__ inline uint32_t kg_filter_raw_stage_bytes(uint32_t w_file) { return KG_F_ROWS * 8u * (w_file + 1); }
-__host__ __device__ inline size_t kg_filter_smem_bytes(uint32_t w_file, uint32_t b_bytes, uint32_t p_pad, uint32_t raw_stages) {
-	return 1024 /*alignment slack*/ + (size_t)b_bytes + (size_t)raw_stages * kg_filter_raw_stage_bytes(w_file) + (size_t)(p_pad / 16) * sizeof(KgFilterGroupConst) + 320;
+// per-group threshold table: thr_tab[g][n1], n1 = 0 .. n_used (see KgFilterParams::thr_tab)
+__host__ __device__ inline size_t kg_filter_tab_floats(uint32_t p_pad, uint32_t n_used) { return (size_t)(p_pad / 16) * ((size_t)n_used + 1); }
+__host__ __device__ inline size_t kg_filter_smem_bytes(uint32_t w_file, uint32_t b_bytes, uint32_t p_pad, uint32_t raw_stages, uint32_t n_used) {
+	return 1024 /*alignment slack*/ + (size_t)b_bytes + (size_t)raw_stages * kg_filter_raw_stage_bytes(w_file) +
+	       ((kg_filter_tab_floats(p_pad, n_used) * sizeof(float) + 15) & ~(size_t)15) + 320;
 }
 // K index (byte inside the A / B operands) of file column `col`.  The expander (below) turns 16 presence bits into
 // 4 registers with 4 PRMTs: register b holds the samples 4 n + b (n = byte inside the register), i.e. inside every
@@ -160,6 +169,26 @@ __device__ __forceinline__ int kg_absmax16(const uint32_t (&v)[16]) {
 	return max(mx, -mn);
 }
 
+// the group's bound for a row with n1 set presence bits (what thr_tab[g][n1] holds)
+__device__ __forceinline__ float kg_filter_group_threshold_n1(const KgFilterGroupConst &gc, uint32_t n1, uint32_t n_used) {
+	const float n1f = (float)n1, n0f = (float)n_used - n1f;
+	const float hm = fminf(n1f, n0f);                                                      // m = size of the smaller group
+	// <= sqrt(den): the product is rounded down, the root is rounded down, and 0.999999 covers the rest (for N > 4096 the
+	// product is no longer exact in fp32; its rounding error is 2^-24, far inside the 1e-6 margin)
+	const float g = __fmul_rd(__fsqrt_rd(__fmul_rd(n1f, n0f)), 0.999999f);
+	return kg_filter_group_threshold(gc, g, hm);
+}
+
+// "a row is ruled out iff (float)max|Q| < thr" as an integer test: listed iff max|Q| >= the value returned.
+// max|Q| is an integer below 2^24 (exact in fp32), so (float)q >= thr <=> q >= ceil(thr); NaN (0 * inf: rows with an empty
+// group, dropped by the MAC filter anyway) lists the row like the float test did, +inf (group without phenotypes) never does.
+__device__ __forceinline__ int32_t kg_filter_bound_to_int(float thr) {
+	if (thr != thr) return 0;
+	if (!(thr > 0.0f)) return 0;
+	if (thr >= 2147483520.0f) return INT32_MAX;
+	return (int32_t)ceilf(thr);
+}
+
 template <int MODE>  // 0 = list candidate rows, 1 = debug: dump accumulators
 __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const KgFilterParams prm) {
 	extern __shared__ uint8_t kg_f_smem_raw[];
@@ -168,8 +197,9 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 	uint8_t *sB = base;
 	const uint32_t raw_stage_bytes = kg_filter_raw_stage_bytes(prm.w_file);
 	uint8_t *sRaw = sB + prm.b_bytes;
-	KgFilterGroupConst *sConst = reinterpret_cast<KgFilterGroupConst *>(sRaw + prm.raw_stages * raw_stage_bytes);
-	uint64_t *bars = reinterpret_cast<uint64_t *>(sConst + prm.p_pad / 16);
+	int32_t *sTab = reinterpret_cast<int32_t *>(sRaw + prm.raw_stages * raw_stage_bytes);
+	const uint32_t tab_floats = (uint32_t)kg_filter_tab_floats(prm.p_pad, prm.n_used);
+	uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(sTab) + ((tab_floats * sizeof(float) + 15) & ~(size_t)15));
 	uint64_t *raw_full = bars, *raw_empty = bars + KG_F_RAW_STAGES;
 	uint64_t *a_full = bars + 2 * KG_F_RAW_STAGES, *a_empty = a_full + KG_F_MAX_A_STAGES;
 	uint64_t *tm_full = a_empty + KG_F_MAX_A_STAGES, *tm_empty = tm_full + 2;
@@ -190,7 +220,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 		kg_mbar_init(b_full, 1);
 		kg_fence_mbar_init();
 	}
-	for (uint32_t i = threadIdx.x; i < prm.p_pad / 16; i += blockDim.x) sConst[i] = prm.gconst[i];
+	for (uint32_t i = threadIdx.x; i < tab_floats; i += blockDim.x) sTab[i] = prm.thr_tab[i];
 	if (warp == KG_F_MMA_WARP0) kg_tmem_alloc(tmem_slot, KG_F_TMEM_COLS);
 	kg_tc_fence_before();
 	__syncthreads();
@@ -362,7 +392,6 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 		const uint32_t q4 = warp & 3;                       // TMEM lane quarter this warp may access
 		const uint32_t r = q4 * 32 + lane;                  // row of the block = TMEM lane
 		const uint32_t eset = (warp - KG_F_EPI_WARP0) >> 2; // this warp's set: it handles the blocks of accumulator buffer eset
-		const float Nf = (float)prm.n_used;
 		unsigned long long kept_local = 0;
 		for (uint32_t it = eset; (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x < n_blocks; it += 2) {
 			const uint32_t blk = blockIdx.x + it * gridDim.x;
@@ -384,7 +413,8 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 			} else {
 				// row popcount (column 0), then per 16-column group: max |accumulator| against the group's loosest bound
 				uint32_t n1 = 0;
-				float g = 0.f, hm = 0.f;
+				const int32_t *tab = sTab;   // -> thr_tab[.][n1] once the row popcount is known
+				const uint32_t tab_stride = prm.n_used + 1;
 				uint32_t gmask = 0;   // bit k: group k could not be ruled out for this row
 				// (dbg 256: perf experiment, only the first 32 accumulator columns are read back)
 				for (uint32_t c0 = 0; c0 < (KG_F_DBG(prm, 2) ? 0u : (KG_F_DBG(prm, 256) ? 32u : prm.p_pad)); c0 += 32) {
@@ -396,18 +426,15 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 					if (c0 == 0) {
 						n1 = v[0] / KG_F_ONE;
 						v[0] = 0;
-						const float n1f = (float)n1, n0f = Nf - n1f;
-						hm = fminf(n1f, n0f);                              // m = size of the smaller group
-						g = __fmul_rd(__fsqrt_rd(n1f * n0f), 0.999999f);   // <= sqrt(den); den is exact in fp32 (< 2^24)
+						tab = sTab + min(n1, prm.n_used);
 					}
 					// max |accumulator| of each group: 3-input min / max TREES (depth 3 instead of a chain of 8: the epilogue
 					// warps are bound by dependent-issue latency, profiles/r02_scan_filter_ncu.md), both groups interleaved
 					const int amax_v = kg_absmax16(v);
-					if (!((float)amax_v < kg_filter_group_threshold(sConst[c0 >> 4], g, hm))) gmask |= 1u << (c0 >> 4);
+					if (amax_v >= tab[(c0 >> 4) * tab_stride]) gmask |= 1u << (c0 >> 4);
 					if (second) {
 						const int amax_u = kg_absmax16(u);
-						if (!((float)amax_u < kg_filter_group_threshold(sConst[(c0 >> 4) + 1], g, hm)))
-							gmask |= 1u << ((c0 >> 4) + 1);
+						if (amax_u >= tab[((c0 >> 4) + 1) * tab_stride]) gmask |= 1u << ((c0 >> 4) + 1);
 					}
 				}
 				// load_kmers :121  (popcnt >= mac) && (popcnt <= N - mac)
@@ -544,7 +571,7 @@ __global__ void __launch_bounds__(256) kg_pair_select_kernel(const KgPairSelectP
 		const bool untested = q[0] == KG_F_NO_Q;
 		const float n1f = (float)n1, n0f = Nf - n1f;
 		const uint32_t m = (uint32_t)fminf(n1f, n0f);
-		const float g = __fmul_rd(__fsqrt_rd(n1f * n0f), 0.999999f);   // as in the filter epilogue
+		const float g = __fmul_rd(__fsqrt_rd(__fmul_rd(n1f, n0f)), 0.999999f);   // as kg_filter_group_threshold_n1
 #pragma unroll
 		for (int j = 0; j < 16; j++) {
 			const int32_t ph = prm.tile_pheno[16 * k + j];

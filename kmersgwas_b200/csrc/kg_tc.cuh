@@ -18,7 +18,8 @@ static void kg_tc_free(KgTcState *tc) {
 	tc->aligned_cap = 0;
 	tc->row_list_cap = 0;
 	cudaFree(tc->d_scale); cudaFree(tc->d_kappa0); cudaFree(tc->d_degenerate); cudaFree(tc->d_q); cudaFree(tc->d_kidx);
-	cudaFree(tc->d_col_of); cudaFree(tc->d_group_lines);
+	cudaFree(tc->d_col_of); cudaFree(tc->d_group_lines); cudaFree(tc->d_thr_tab);
+	tc->d_thr_tab = nullptr;
 	tc->d_scale = nullptr; tc->d_kappa0 = nullptr; tc->d_degenerate = nullptr; tc->d_q = nullptr; tc->d_kidx = nullptr;
 	tc->d_col_of = nullptr; tc->d_group_lines = nullptr;
 }
@@ -73,6 +74,7 @@ static kg_status kg_tc_retune(kg_ctx *c, bool force) {
 	r.yq_image = tc.d_yq;
 	r.tile_pheno = tc.d_tile_pheno;
 	r.gconst = tc.d_gconst;
+	r.thr_tab = tc.d_thr_tab;
 	r.alpha_out = reinterpret_cast<float *>(tc.d_gconst + 16 * (size_t)tc.n_pass);
 	r.kappa_out = r.alpha_out + c->n_pheno;
 	r.status = c->sel.active ? c->sel.d_status : nullptr;
@@ -95,7 +97,8 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	tc.row_list_cap = 0;
 	tc.qcap = 0;
 	cudaFree(tc.d_scale); cudaFree(tc.d_kappa0); cudaFree(tc.d_degenerate); cudaFree(tc.d_q); cudaFree(tc.d_kidx);
-	cudaFree(tc.d_col_of); cudaFree(tc.d_group_lines);
+	cudaFree(tc.d_col_of); cudaFree(tc.d_group_lines); cudaFree(tc.d_thr_tab);
+	tc.d_thr_tab = nullptr;
 	tc.d_scale = nullptr; tc.d_kappa0 = nullptr; tc.d_degenerate = nullptr; tc.d_q = nullptr; tc.d_kidx = nullptr;
 	tc.d_col_of = nullptr; tc.d_group_lines = nullptr;
 	const uint32_t P = c->n_pheno, N = (uint32_t)c->n_used;
@@ -109,7 +112,7 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	uint32_t best_pp = 0, best_rs = 0;
 	for (uint32_t rs = KG_F_RAW_STAGES; rs >= 2; rs--)
 		for (uint32_t pp = pp_want; pp >= 16; pp -= 16)
-			if (kg_filter_smem_bytes(c->w_file, (pp / 8) * tc.sbo_b, pp, rs) <= 227u * 1024) {
+			if (kg_filter_smem_bytes(c->w_file, (pp / 8) * tc.sbo_b, pp, rs, N) <= 227u * 1024) {
 				if (pp > best_pp) { best_pp = pp; best_rs = rs; }
 				break;
 			}
@@ -134,7 +137,7 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 		tc.a_stages = std::max(2u, std::min<uint32_t>(KG_F_MAX_A_STAGES, a_cols / (16 * tc.a_words)));
 		tc.nc = (c->w_file + tc.a_words - 1) / tc.a_words;
 	}
-	const size_t smem = kg_filter_smem_bytes(c->w_file, tc.b_bytes, tc.p_pad, tc.raw_stages);
+	const size_t smem = kg_filter_smem_bytes(c->w_file, tc.b_bytes, tc.p_pad, tc.raw_stages, N);
 	tc.smem_bytes = smem;
 
 	// quantise: centred, symmetric int8 per phenotype
@@ -227,6 +230,7 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 		KG_CUDA(c, dev_alloc_copy(&tc.d_kidx, kidx));
 		KG_CUDA(c, dev_alloc_copy(&tc.d_col_of, zero_cols));
 		KG_CUDA(c, dev_alloc_copy(&tc.d_group_lines, zero_lines));
+		KG_CUDA(c, cudaMalloc((void **)&tc.d_thr_tab, (size_t)tc.n_pass * kg_filter_tab_floats(tc.p_pad, N) * sizeof(float)));
 	}
 	tc.use_pairs = true;
 	tc.dbg_flags = 0u;
@@ -283,6 +287,7 @@ static KgFilterParams kg_tc_filter_params(kg_ctx *c, const uint64_t *dev, uint64
 	f.b_bytes = tc.b_bytes;
 	f.sbo_b = tc.sbo_b;
 	f.gconst = tc.d_gconst + (size_t)pass * 16;
+	f.thr_tab = tc.d_thr_tab + (size_t)pass * kg_filter_tab_floats(tc.p_pad, (uint32_t)c->n_used);
 	f.n_used = (uint32_t)c->n_used;
 	f.min_count = (uint32_t)std::min<uint64_t>(c->min_count, 0xFFFFFFFFull);
 	f.row_list = tc.d_row_list;

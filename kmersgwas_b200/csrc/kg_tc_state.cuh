@@ -57,6 +57,7 @@ struct KgTcState {
 	uint32_t *d_kidx = nullptr;            // [n_used] operand K index of memory column i
 	uint32_t *d_col_of = nullptr;          // [P] column assignment the device image was built with
 	float *d_group_lines = nullptr;        // [16][8]
+	int32_t *d_thr_tab = nullptr;            // [n_pass][p_pad / 16][n_used + 1] group bounds per row popcount
 };
 
 // Device-resident BestAssociationsHeap set (kg_select.cuh); owned by kg_ctx.
