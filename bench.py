@@ -224,6 +224,8 @@ def our_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
+    # this rank's threads and the pinned row buffers it allocates below live on its GPU's NUMA node
+    numa_node, numa_cpus = (-1, 0) if args.no_numa_bind else kg._abi.bind_host_to_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout for the one JSON line
@@ -492,6 +494,7 @@ def our_arm(args):
                 "parallelism": (f"k-mer-block shards x{world} (weak: {J} rows per GPU), no data-path collective in the scan; ranks > 0 warm-start from a "
                                 f"{args.prefix_rows}-row shared prefix; logs all-gathered and replayed on rank 0 (exact merge)"),
                 "selection": "device-resident BestAssociationsHeap set (kg_select_*): no host in the scan loop",
+                "host_placement": {"numa_node": numa_node, "cpus": numa_cpus, "how": "kg_bind_host_to_device (rank 0 shown; -1 = not bound)"},
             },
             "timed_region_s": job_ms * 1e-3,
             "job": {"rows": rows_total, "seconds": job_ms * 1e-3, "rows_applied_rank0": status_rows[0], "rows_kept_rank0": status_rows[1],
@@ -747,6 +750,7 @@ def main():
     ap.add_argument("--kinship-engine", type=int, default=0)
     ap.add_argument("--kinship-rows", type=int, default=1 << 20)
     ap.add_argument("--e2e-buffers", type=int, default=3)
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--cpu-rows", type=int, default=400000, help="rows of the cpu_baseline sample")
     ap.add_argument("--kinship-cpu-rows", type=int, default=15000, help="rows of the kinship cpu_baseline sample")
     ap.add_argument("--ref-rows", type=int, default=200000, help="rows per step of --impl reference")

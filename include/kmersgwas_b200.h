@@ -326,6 +326,16 @@ kg_status kg_kernel_time_reset(kg_ctx *ctx);
  * on every SM, timed with CUDA events (the roofline denominator bench.py reports for the tcgen05 kernels). */
 kg_status kg_probe_int8_peak(kg_ctx *ctx, double *tops);
 
+/* Host placement for the pinned tile loader (the reference's reader, kmers_multiple_databases.cpp:103-146, has no
+ * such notion: it reads into pageable memory on whatever core runs it).  Restricts the CALLING thread (and the threads
+ * it creates afterwards) to the CPUs of the NUMA node the device's PCIe slot hangs off, and makes that node the
+ * preferred one for the memory the thread allocates from now on -- call it before allocating the pinned row buffers
+ * (cudaHostAlloc / kg-owned staging) and before starting reader threads.  With 4+ GPUs streaming 55 GB/s each, buffers
+ * on the wrong socket are limited by the inter-socket link.  Returns the node, or -1 when nothing was changed (one
+ * node, no sysfs entry, KMERSGWAS_NUMA_BIND=0, or the node's CPUs are outside the process's cpuset).  n_cpus (may be
+ * NULL) receives the number of CPUs the thread may now run on. */
+int kg_bind_host_to_device(int device, int *n_cpus);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,7 @@ ABI_SYMBOLS = [
     "kg_select_replay", "kg_select_set_floor", "kg_select_export_scores", "kg_select_kmax", "kg_probe_int8_peak", "kg_select_stats",
     "kg_comm_unique_id", "kg_comm_init_rank", "kg_comm_init_all", "kg_kinship_allreduce", "kg_kinship_allreduce_all",
     "kg_stream_mark", "kg_stream_wait", "kg_snps_scores", "kg_table_build", "kg_scan_filter_shape",
+    "kg_bind_host_to_device",
     "kg_patterns_begin", "kg_patterns_attach", "kg_patterns_submit", "kg_patterns_count", "kg_patterns_export", "kg_patterns_insert",
 ]
 
@@ -114,6 +115,8 @@ def load():
     lib.kg_select_set_floor.argtypes = [vp, vp, C.c_uint32]
     lib.kg_select_export_scores.argtypes = [vp, u64, vp]
     lib.kg_probe_int8_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.kg_bind_host_to_device.argtypes = [C.c_int, C.POINTER(C.c_int)]
+    lib.kg_bind_host_to_device.restype = C.c_int
     lib.kg_select_stats.argtypes = [vp, u64p, u64p, u64p, u64p]
     lib.kg_comm_unique_id.argtypes = [vp]
     lib.kg_comm_init_rank.argtypes = [vp, vp, C.c_int, C.c_int]
@@ -135,6 +138,13 @@ def load():
     lib.kg_select_kmax.restype = C.c_uint32
     _lib = lib
     return lib
+
+
+def bind_host_to_device(device: int):
+    """kg_bind_host_to_device: (numa node or -1, cpus the calling thread may now use)."""
+    n = C.c_int(0)
+    node = load().kg_bind_host_to_device(int(device), C.byref(n))
+    return int(node), int(n.value)
 
 
 def comm_unique_id() -> bytes:

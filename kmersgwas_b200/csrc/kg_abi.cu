@@ -1,5 +1,9 @@
 // kg_abi.cu -- implementation of include/kmersgwas_b200.h (the C ABI) on top of the sm_100a kernels.
 // No CPU fallback: every entry point needs a CUDA device.
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+#include <cctype>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -87,6 +91,9 @@ struct kg_ctx {
 	// squeeze scratch
 	uint64_t *d_squeezed = nullptr;
 	size_t squeezed_cap = 0;
+	// kg_scan_scores_dense output scratch
+	void *d_dense = nullptr;
+	size_t dense_cap = 0;
 
 	// kinship
 	unsigned long long *d_accum = nullptr;
@@ -229,6 +236,53 @@ extern "C" const char *kg_last_error(const kg_ctx *ctx) {
 
 extern "C" uint64_t kg_launch_count(const kg_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+// ------------------------------------------------------------------------------------------ host placement
+static bool kg_read_small_file(const char *path, char *buf, size_t cap) {
+	FILE *f = fopen(path, "r");
+	if (!f) return false;
+	const size_t n = fread(buf, 1, cap - 1, f);
+	fclose(f);
+	buf[n] = 0;
+	return n > 0;
+}
+
+extern "C" int kg_bind_host_to_device(int device, int *n_cpus) {
+	if (n_cpus) *n_cpus = 0;
+	if (const char *e = getenv("KMERSGWAS_NUMA_BIND"))
+		if (atoi(e) == 0) return -1;
+	char bus[32] = {0}, path[128], text[4096];
+	if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+	for (char *q = bus; *q; q++) *q = (char)tolower((unsigned char)*q);
+	snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+	if (!kg_read_small_file(path, text, sizeof text)) return -1;
+	const int node = atoi(text);
+	if (node < 0 || node >= 1024) return -1;
+	snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+	if (!kg_read_small_file(path, text, sizeof text)) return -1;
+	// "0-31,64-95" -> the part of it inside the thread's current affinity mask (a container's cpuset)
+	cpu_set_t now, want;
+	CPU_ZERO(&want);
+	if (sched_getaffinity(0, sizeof now, &now) != 0) return -1;
+	for (const char *q = text; *q && *q != '\n';) {
+		char *end;
+		long a = strtol(q, &end, 10), b = a;
+		if (end == q) break;
+		if (*end == '-') { q = end + 1; b = strtol(q, &end, 10); }
+		for (long cpu = a; cpu <= b && cpu < CPU_SETSIZE; cpu++)
+			if (CPU_ISSET(cpu, &now)) CPU_SET(cpu, &want);
+		q = (*end == ',') ? end + 1 : end;
+	}
+	const int cpus = CPU_COUNT(&want);
+	if (cpus == 0 || sched_setaffinity(0, sizeof want, &want) != 0) return -1;
+	if (n_cpus) *n_cpus = cpus;
+	// set_mempolicy(MPOL_PREFERRED, {node}): memory the thread faults in (and the pages the driver pins for it) comes
+	// from the device's node while it has room; no libnuma in the image, so the raw system call
+	unsigned long mask[1024 / (8 * sizeof(unsigned long))] = {0};
+	mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+	(void)syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, (unsigned long)(sizeof mask * 8));
+	return node;
+}
+
 static kg_status ctx_init(kg_ctx *c, int device, const kg_shape *shape, void *stream) {
 	if (!shape || !shape->map_word || !shape->map_bit || shape->n_used == 0 || shape->n_file == 0)
 		KG_FAIL(c, KG_ERR_INVALID, "kg_ctx_create: empty shape");
@@ -337,7 +391,7 @@ extern "C" void kg_ctx_destroy(kg_ctx *c) {
 		if (c->thr_stage[i].ev) cudaEventDestroy(c->thr_stage[i].ev);
 	}
 	if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
-	cudaFree(c->d_squeezed); cudaFree(c->d_keep_bits);
+	cudaFree(c->d_squeezed); cudaFree(c->d_keep_bits); cudaFree(c->d_dense);
 	cudaFree(c->d_ibs);
 	if (c->own_accum) cudaFree(c->d_accum);
 	kg_tc_free(&c->tc);
@@ -1030,13 +1084,22 @@ extern "C" kg_status kg_scan_scores_dense(kg_ctx *c, const uint64_t *rows, uint6
 	KgRowView view;
 	st = memory_view(c, dev, n_rows, &view);
 	if (st != KG_OK) return st;
-	uint8_t *d_keep = nullptr;
-	double *d_scores = nullptr;
-	KG_CUDA(c, cudaMalloc((void **)&d_keep, n_rows));
-	cudaError_t me = cudaMalloc((void **)&d_scores, (size_t)c->n_pheno * n_rows * sizeof(double));
-	if (me != cudaSuccess) { cudaFree(d_keep); KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc dense scores: %s", cudaGetErrorString(me)); }
+	// context-owned output scratch, grown on demand: [n_pheno][n_rows] doubles, then n_rows keep flags
+	const size_t need = (size_t)c->n_pheno * n_rows * sizeof(double) + n_rows;
+	if (c->dense_cap < need) {
+		KG_CUDA(c, cudaStreamSynchronize(c->stream));
+		cudaFree(c->d_dense);
+		c->d_dense = nullptr;
+		c->dense_cap = 0;
+		cudaError_t me = cudaMalloc((void **)&c->d_dense, need);
+		if (me != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc dense scores (%zu bytes): %s", need, cudaGetErrorString(me));
+		c->dense_cap = need;
+	}
+	double *d_scores = reinterpret_cast<double *>(c->d_dense);
+	uint8_t *d_keep = reinterpret_cast<uint8_t *>(c->d_dense) + (size_t)c->n_pheno * n_rows * sizeof(double);
 	cudaMemsetAsync(d_scores, 0, (size_t)c->n_pheno * n_rows * sizeof(double), c->stream);
 	KgScanParams prm = scan_params(c, view, 0);
+	prm.cand = nullptr;   // dense mode writes scores, never candidates
 	prm.keep_out = d_keep;
 	prm.scores_out = d_scores;
 	st = launch_exact_pt<1>(c, prm);
@@ -1044,8 +1107,6 @@ extern "C" kg_status kg_scan_scores_dense(kg_ctx *c, const uint64_t *rows, uint6
 	cudaError_t e1 = cudaStreamSynchronize(c->stream);
 	cudaError_t e2 = cudaMemcpy(keep, d_keep, n_rows, cudaMemcpyDeviceToHost);
 	cudaError_t e3 = cudaMemcpy(scores, d_scores, (size_t)c->n_pheno * n_rows * sizeof(double), cudaMemcpyDeviceToHost);
-	cudaFree(d_keep);
-	cudaFree(d_scores);
 	if (st != KG_OK) return st;
 	KG_CUDA(c, e1); KG_CUDA(c, e2); KG_CUDA(c, e3);
 	return KG_OK;

@@ -42,6 +42,8 @@ void run_shard_device(Shard &sh, size_t min_count, size_t batch_size, bool verbo
                       uint64_t first, uint64_t count, uint64_t prefix_rows, bool is_first_shard) {
 	try {
 		MultipleKmersDataBases &db = *sh.db;
+		// this thread, its reader threads and the pinned tiles they fill live on the GPU's NUMA node (no-op on one node)
+		kg_bind_host_to_device(db.device(), nullptr);
 		// Nothing comes back per batch on this path, so --batch_size only bounds memory: the table is streamed in tiles of at
 		// most 256 MB (three pinned buffers: one being read from the file, one in flight to the GPU, one being scanned)
 		const size_t row_bytes = 8 * (1 + db.file_words());
