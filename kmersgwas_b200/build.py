@@ -68,7 +68,8 @@ def build_cuda(force=False, verbose=False) -> Path:
     out = cuda_lib_path()
     srcs = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "kmersgwas_b200.h"]
     if force or _stale(out, srcs):
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-o", out] + sorted(CSRC.glob("*.cu"))
+        extra = os.environ.get("KMERSGWAS_NVCC_EXTRA", "").split()   # e.g. -DKG_PERF_SWITCHES for profiling experiments
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-shared", "-o", out] + sorted(CSRC.glob("*.cu"))
         _run(cmd, verbose)
     return out
 

@@ -24,6 +24,7 @@ struct KgCand {      // one candidate association: what add_kmers_to_heap hands 
 };
 
 #define KG_SEL_THREADS 256
+#define KG_SEL_RING 64            // admission records in flight between the sequential thread and the slot warp
 #define KG_SEL_STAGE 1024          // candidates staged in shared memory per replay block (24 KB)
 
 // device-resident status words of a selection (kg_ctx::sel.d_status)
@@ -79,36 +80,109 @@ __host__ __device__ __forceinline__ long long kg_dbits(double x) {
 	return r;
 #endif
 }
-#ifdef KG_SEL_INTCMP
-#define KG_GT(a, b) (kg_dbits(a) > kg_dbits(b))
-#else
 #define KG_GT(a, b) ((a) > (b))
-#endif
 // ---- libstdc++ heap algorithms on (score, slot) pairs; cmp_second(l, r) = l.score > r.score (min-heap) ------------
-// hs has its element 1 on a 16-byte boundary, so the two children 2h+1, 2h+2 of a node are one 128-bit load.
-__host__ __device__ __forceinline__ void kg_heap_push_up(double *hs, uint32_t *hl, int32_t hole, double v, uint32_t vs) {
-	// __push_heap(first, hole, top = 0, value): while (hole > top && comp(first[parent], value)) move the parent down.
-	// A newly admitted score is just above the heap's minimum, so it climbs almost to the root: the ancestors of a
-	// position are known in advance, and four levels of them are loaded per shared-memory round trip (nothing written
-	// in between touches an ancestor).
-	while (hole > 0) {
-		const int32_t p1 = (hole - 1) >> 1;
-		const int32_t p2 = p1 > 0 ? (p1 - 1) >> 1 : 0;
-		const int32_t p3 = p2 > 0 ? (p2 - 1) >> 1 : 0;
-		const int32_t p4 = p3 > 0 ? (p3 - 1) >> 1 : 0;
-		const double s1 = hs[p1], s2 = hs[p2], s3 = hs[p3], s4 = hs[p4];
-		const uint32_t l1 = hl[p1], l2 = hl[p2], l3 = hl[p3], l4 = hl[p4];
-		if (!KG_GT(s1, v)) break;
-		hs[hole] = s1; hl[hole] = l1; hole = p1;
-		if (hole == 0 || !KG_GT(s2, v)) break;
-		hs[hole] = s2; hl[hole] = l2; hole = p2;
-		if (hole == 0 || !KG_GT(s3, v)) break;
-		hs[hole] = s3; hl[hole] = l3; hole = p3;
-		if (hole == 0 || !KG_GT(s4, v)) break;
-		hs[hole] = s4; hl[hole] = l4; hole = p4;
+// The heap is two arrays, scores hs[] and slots hl[], with hs[1] on a 16-byte boundary and hl[1] / hl[3] on 8- / 16-byte
+// ones, so the two children 2h+1, 2h+2 of a node (and its four grandchildren 4h+3 .. 4h+6) are single vector loads.
+// The algorithms are written once over a memory policy:
+//   KgHeapPtr     plain pointers (tests/heap_host_check.cu runs them on the host against the oracle's priority_queue)
+//   KgHeapShared  32-bit shared-window addresses + ld/st.shared: what the replay kernel uses.  With generic pointers into
+//                 dynamic shared memory the compiler re-derives the window base (S2R SR_CgaCtaId, ~30 cycles each) several
+//                 times per admission, inside the one dependent chain that bounds the kernel.
+struct KgHeapPtr {
+	double *hs;
+	uint32_t *hl;
+	__host__ __device__ __forceinline__ double lds(int32_t i) const { return hs[i]; }
+	__host__ __device__ __forceinline__ uint32_t ldl(int32_t i) const { return hl[i]; }
+	__host__ __device__ __forceinline__ double2 lds2(int32_t i) const { return *reinterpret_cast<const double2 *>(hs + i); }
+	__host__ __device__ __forceinline__ uint2 ldl2(int32_t i) const { return *reinterpret_cast<const uint2 *>(hl + i); }
+	__host__ __device__ __forceinline__ uint4 ldl4(int32_t i) const { return *reinterpret_cast<const uint4 *>(hl + i); }
+	__host__ __device__ __forceinline__ void sts(int32_t i, double v) const { hs[i] = v; }
+	__host__ __device__ __forceinline__ void stl(int32_t i, uint32_t v) const { hl[i] = v; }
+};
+#ifdef __CUDACC__
+struct KgHeapShared {
+	uint32_t hs_a, hl_a;   // shared-window byte addresses of hs[0], hl[0]
+	__device__ __forceinline__ KgHeapShared(const double *hs, const uint32_t *hl) {
+		hs_a = (uint32_t)__cvta_generic_to_shared(hs);
+		hl_a = (uint32_t)__cvta_generic_to_shared(hl);
+		asm volatile("" : "+r"(hs_a), "+r"(hl_a));   // opaque: kept in registers, never re-derived
 	}
-	hs[hole] = v;
-	hl[hole] = vs;
+	__device__ __forceinline__ double lds(int32_t i) const {
+		double v;
+		asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(hs_a + 8u * (uint32_t)i));
+		return v;
+	}
+	__device__ __forceinline__ uint32_t ldl(int32_t i) const {
+		uint32_t v;
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(hl_a + 4u * (uint32_t)i));
+		return v;
+	}
+	__device__ __forceinline__ double2 lds2(int32_t i) const {
+		double2 v;
+		asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(hs_a + 8u * (uint32_t)i));
+		return v;
+	}
+	__device__ __forceinline__ uint2 ldl2(int32_t i) const {
+		uint2 v;
+		asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(hl_a + 4u * (uint32_t)i));
+		return v;
+	}
+	__device__ __forceinline__ uint4 ldl4(int32_t i) const {
+		uint4 v;
+		asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(hl_a + 4u * (uint32_t)i));
+		return v;
+	}
+	__device__ __forceinline__ void sts(int32_t i, double v) const {
+		asm volatile("st.shared.f64 [%0], %1;" ::"r"(hs_a + 8u * (uint32_t)i), "d"(v));
+	}
+	__device__ __forceinline__ void stl(int32_t i, uint32_t v) const {
+		asm volatile("st.shared.u32 [%0], %1;" ::"r"(hl_a + 4u * (uint32_t)i), "r"(v));
+	}
+};
+#endif
+
+#ifdef __CUDA_ARCH__
+#define KG_HEAP_UNROLL _Pragma("unroll")
+#else
+#define KG_HEAP_UNROLL
+#endif
+// __push_heap(first, hole, top = 0, value): while (hole > top && comp(first[parent], value)) move the parent down.
+// The ancestors of a position are known in advance (j-th ancestor of 1-based position i: i >> j), so CLIMB levels of them
+// are loaded back to back in one shared-memory round trip (nothing written in between touches an ancestor), compared
+// independently, and moved down while every comparison below them said "above v".  A newly admitted score is just above
+// the heap's minimum and climbs almost to the root (~log2 K levels): CLIMB = 16 covers that in one trip.  Pushes that
+// rarely climb (the fill phase, the re-inserted leaf of a pop) use CLIMB = 4.
+template <int CLIMB, class M>
+__host__ __device__ __forceinline__ void kg_heap_push_up(const M m, int32_t hole, double v, uint32_t vs) {
+	while (hole > 0) {
+		const uint32_t i1 = (uint32_t)hole + 1u;
+		int32_t q[CLIMB];
+		double s[CLIMB];
+		uint32_t l[CLIMB];
+		KG_HEAP_UNROLL
+		for (int j = 0; j < CLIMB; j++) {
+			const uint32_t a = i1 >> (j + 1);
+			q[j] = a ? (int32_t)a - 1 : 0;
+		}
+		KG_HEAP_UNROLL
+		for (int j = 0; j < CLIMB; j++) s[j] = m.lds(q[j]);
+		KG_HEAP_UNROLL
+		for (int j = 0; j < CLIMB; j++) l[j] = m.ldl(q[j]);
+		bool go = true;
+		KG_HEAP_UNROLL
+		for (int j = 0; j < CLIMB; j++) {
+			go = go && (i1 >> (j + 1)) != 0u && KG_GT(s[j], v);
+			if (go) {
+				m.sts(hole, s[j]);
+				m.stl(hole, l[j]);
+				hole = q[j];
+			}
+		}
+		if (!go) break;
+	}
+	m.sts(hole, v);
+	m.stl(hole, vs);
 }
 
 // pop_heap + pop_back on a heap of `len` entries, then push_back + push_heap of (v_new, slot_new): the reference's
@@ -117,51 +191,298 @@ __host__ __device__ __forceinline__ void kg_heap_push_up(double *hs, uint32_t *h
 // One thread runs this, so the cost is the chain of dependent shared-memory round trips.  __adjust_heap always walks the
 // hole down to a leaf choosing the smaller child (ties: the right one), independent of the value that is re-inserted, so
 // TWO levels are resolved per round trip: the children (2h+1, 2h+2) and the grandchildren (4h+3 .. 4h+6) of the hole
-// are contiguous, and with &hs[1] / &hs[3] on 16-byte and &hl[1] / &hl[3] on 8- / 16-byte boundaries they are five
-// vector loads issued back to back (scores and slots together, so the slot moves never wait on their own loads).
+// are contiguous: five vector loads issued back to back (scores and slots together, so the slot moves never wait on
+// their own loads).  The re-inserted value (the old last leaf) then climbs from the leaf the hole reached: its first
+// comparison is against the entry just moved into the hole's parent, which is still in a register -- usually the climb
+// ends there without another round trip.
 // `cap` = entries that may be READ (>= len; reads past the heap's end are clamped to it and their values unused).
-__host__ __device__ __forceinline__ void kg_heap_replace_top(double *hs, uint32_t *hl, int32_t len, int32_t cap, double v_new, uint32_t slot_new) {
+template <class M>
+__host__ __device__ __forceinline__ void kg_heap_replace_top(const M m, int32_t len, int32_t cap, double v_new, uint32_t slot_new) {
 	if (len > 1) {
 		// __pop_heap: value = last element, *last = *first (discarded by pop_back), __adjust_heap(first, 0, len - 1, value)
-		const double v = hs[len - 1];
-		const uint32_t vs = hl[len - 1];
+		const double v = m.lds(len - 1);
+		const uint32_t vs = m.ldl(len - 1);
 		const int32_t n = len - 1;
 		const int32_t lim = (n - 1) / 2;      // nodes below lim have both children inside [0, n)
 		const int32_t g_max = cap - 4;        // last index a 4-entry grandchild load may start at (cap >= 8, odd start kept below)
 		int32_t hole = 0;
+		double moved = 0.0;                   // score now at the hole's parent (valid once hole > 0)
 		while (hole < lim) {
 			const int32_t l = 2 * hole + 1;                           // children l, l + 1
 			int32_t g = 2 * l + 1;                                    // grandchildren g .. g + 3 (g = 3 mod 4)
 			g = g > g_max ? 3 : g;                                    // out of range: any valid aligned index (values unused)
-			const double2 s12 = *reinterpret_cast<const double2 *>(hs + l);
-			const uint2 l12 = *reinterpret_cast<const uint2 *>(hl + l);
-			const double2 s34 = *reinterpret_cast<const double2 *>(hs + g);
-			const double2 s56 = *reinterpret_cast<const double2 *>(hs + g + 2);
-			const uint4 l36 = *reinterpret_cast<const uint4 *>(hl + g);
+			const double2 s12 = m.lds2(l);
+			const uint2 l12 = m.ldl2(l);
+			const double2 s34 = m.lds2(g);
+			const double2 s56 = m.lds2(g + 2);
+			const uint4 l36 = m.ldl4(g);
 			// comp(first[right], first[left]) = right.score > left.score: take the left child, else (ties too) the right one
 			const bool left = KG_GT(s12.y, s12.x);
 			const int32_t c = left ? l : l + 1;
-			hs[hole] = left ? s12.x : s12.y;
-			hl[hole] = left ? l12.x : l12.y;
+			moved = left ? s12.x : s12.y;
+			m.sts(hole, moved);
+			m.stl(hole, left ? l12.x : l12.y);
 			hole = c;
 			if (!(c < lim)) break;
 			const double a = left ? s34.x : s56.x, b = left ? s34.y : s56.y;
 			const uint32_t la = left ? l36.x : l36.z, lb = left ? l36.y : l36.w;
 			const bool left2 = KG_GT(b, a);
-			hs[c] = left2 ? a : b;
-			hl[c] = left2 ? la : lb;
+			moved = left2 ? a : b;
+			m.sts(c, moved);
+			m.stl(c, left2 ? la : lb);
 			hole = 2 * c + (left2 ? 1 : 2);
 		}
 		if ((n & 1) == 0 && hole == (n - 2) / 2) {   // the last inner node has a left child only
 			const int32_t ch = 2 * hole + 1;
-			hs[hole] = hs[ch];
-			hl[hole] = hl[ch];
+			moved = m.lds(ch);
+			m.sts(hole, moved);
+			m.stl(hole, m.ldl(ch));
 			hole = ch;
 		}
-		kg_heap_push_up(hs, hl, hole, v, vs);
+		if (hole > 0 && !KG_GT(moved, v)) {          // __push_heap stops at once: the parent is not above v
+			m.sts(hole, v);
+			m.stl(hole, vs);
+		} else {
+			kg_heap_push_up<2>(m, hole, v, vs);
+		}
 	}
 	// push_back at position len - 1, push_heap
-	kg_heap_push_up(hs, hl, len - 1, v_new, slot_new);
+	kg_heap_push_up<2>(m, len - 1, v_new, slot_new);
+}
+
+// ---- the same algorithms split in two, for the replay kernel --------------------------------------------------------
+// Only the SCORES decide where entries move; the slots (and the payload behind them) just follow.  The kernel's one
+// sequential thread therefore runs the score half and writes a 16-byte record of what it did; a second warp applies the
+// records to the slot array, all levels of a path at once, and stores the payload.  The sequential thread is bound by
+// the number of instructions on its dependent chain (~3.3 cycles each, profiles/r02_select_replay_ncu.md), and the slot
+// half was ~40 % of them.
+struct KgHeapRec {
+	uint32_t cand;   // index of the admitted candidate in the staged block
+	uint32_t leaf;   // pop: the leaf the hole reached (its ancestors are the sift path)
+	uint32_t info;   // bits 0-7 c1: levels the re-inserted last entry climbed from the leaf; 8-15 c2: levels the new entry
+	                 // climbed from `pos`; bits 16-17 KG_REC_*; bit 18: the pop sifted (heap had more than one entry)
+	uint32_t pos;    // position the new entry was pushed at (len - 1 after a pop, the old size in the fill phase)
+};
+#define KG_REC_POP 0u
+#define KG_REC_PUSH 1u
+#define KG_REC_END 2u
+#define KG_REC_SIFTED (1u << 18)
+
+// __push_heap on the scores alone; returns the number of levels climbed
+template <class M>
+__host__ __device__ __forceinline__ uint32_t kg_heap_push_up_scores(const M m, int32_t hole, double v) {
+	uint32_t climbed = 0;
+	while (hole > 0) {
+		const int32_t p1 = (hole - 1) >> 1;
+		const int32_t p2 = p1 > 0 ? (p1 - 1) >> 1 : 0;
+		const double s1 = m.lds(p1), s2 = m.lds(p2);
+		if (!KG_GT(s1, v)) break;
+		m.sts(hole, s1); hole = p1; climbed++;
+		if (hole == 0 || !KG_GT(s2, v)) break;
+		m.sts(hole, s2); hole = p2; climbed++;
+	}
+	m.sts(hole, v);
+	return climbed;
+}
+
+// pop + push of kg_heap_replace_top on the scores alone; fills leaf / info of the record
+template <class M>
+__host__ __device__ __forceinline__ void kg_heap_replace_top_scores(const M m, int32_t len, int32_t cap, double v_new, KgHeapRec &rec) {
+	uint32_t c1 = 0, sifted = 0;
+	rec.leaf = 0;
+	if (len > 1) {
+		const double v = m.lds(len - 1);
+		const int32_t n = len - 1;
+		const int32_t lim = (n - 1) / 2;
+		const int32_t g_max = cap - 4;
+		int32_t hole = 0;
+		double moved = 0.0;
+		while (hole < lim) {
+			const int32_t l = 2 * hole + 1;
+			int32_t g = 2 * l + 1;
+			g = g > g_max ? 3 : g;
+			const double2 s12 = m.lds2(l);
+			const double2 s34 = m.lds2(g);
+			const double2 s56 = m.lds2(g + 2);
+			const bool left = KG_GT(s12.y, s12.x);
+			const int32_t c = left ? l : l + 1;
+			moved = left ? s12.x : s12.y;
+			m.sts(hole, moved);
+			hole = c;
+			if (!(c < lim)) break;
+			const double a = left ? s34.x : s56.x, b = left ? s34.y : s56.y;
+			const bool left2 = KG_GT(b, a);
+			moved = left2 ? a : b;
+			m.sts(c, moved);
+			hole = 2 * c + (left2 ? 1 : 2);
+		}
+		if ((n & 1) == 0 && hole == (n - 2) / 2) {
+			const int32_t ch = 2 * hole + 1;
+			moved = m.lds(ch);
+			m.sts(hole, moved);
+			hole = ch;
+		}
+		rec.leaf = (uint32_t)hole;
+		sifted = KG_REC_SIFTED;
+		if (hole > 0 && !KG_GT(moved, v)) m.sts(hole, v);
+		else c1 = kg_heap_push_up_scores(m, hole, v);
+	}
+	const uint32_t c2 = kg_heap_push_up_scores(m, len - 1, v_new);
+	rec.pos = (uint32_t)(len - 1);
+	rec.info = c1 | (c2 << 8) | (KG_REC_POP << 16) | sifted;
+}
+
+#ifdef __CUDACC__
+// kg_heap_replace_top_scores for the replay kernel.  Same moves; the sift's dependent chain is cut to
+//     ld.shared (children) -> compare -> select -> compare -> select -> ld.shared
+// per TWO levels (profiles/r02_select_replay_ncu.md: the generic loop spent half its time on the two data-dependent
+// bounds branches and on index -> address arithmetic between the last compare and the next load):
+//  - every entry above the last two levels has both children and all four grandchildren, so the first
+//    (depth of the last entry - 1) / 2 double steps run in a counted loop with no bounds test at all;
+//  - the loop carries the shared-memory ADDRESS of the hole's children pair, A = hs + 8 + 16 h; both candidates for the
+//    next A are formed while the second compare is in flight, and the loads take A as it is.
+struct KgHeapShape {   // what the sift needs to know about a heap of `len` entries (the same for every admission once it is full)
+	int32_t len, lim, iters, edge;
+};
+__device__ __forceinline__ KgHeapShape kg_heap_shape(int32_t len) {
+	KgHeapShape sh;
+	const int32_t n = len - 1;                                   // entries during the sift of a pop
+	sh.len = len;
+	sh.lim = (n - 1) / 2;                                        // entries below lim have both children inside [0, n)
+	sh.iters = n >= 1 ? (31 - __clz(n) - 1) >> 1 : 0;            // depth of entry n - 1 is floor(log2 n)
+	sh.edge = (n >= 2 && (n & 1) == 0) ? (n - 2) / 2 : -1;       // the last inner entry when it has a left child only
+	return sh;
+}
+__device__ __forceinline__ void kg_heap_replace_top_scores(const KgHeapShared m, const KgHeapShape sh, int32_t cap, double v_new, KgHeapRec &rec) {
+	uint32_t c1 = 0, sifted = 0;
+	rec.leaf = 0;
+	const int32_t len = sh.len;
+	if (len > 1) {
+		const double v = m.lds(len - 1);
+		const int32_t lim = sh.lim;
+		const int32_t g_max = cap - 4;
+		double moved = 0.0;
+		const int32_t iters = sh.iters;
+		uint32_t A = m.hs_a + 8u;
+		const uint32_t C = 24u - 3u * m.hs_a;
+		for (int32_t it = 0; it < iters; it++) {
+			const uint32_t G = 2u * A - m.hs_a + 8u;      // hs + 24 + 32 h: grandchildren 4h+3 .. 4h+6
+			double2 s12, s34, s56;
+			asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(s12.x), "=d"(s12.y) : "r"(A));
+			asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(s34.x), "=d"(s34.y) : "r"(G));
+			asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(s56.x), "=d"(s56.y) : "r"(G + 16u));
+			const bool left = KG_GT(s12.y, s12.x);
+			const double m1 = left ? s12.x : s12.y;
+			const double a = left ? s34.x : s56.x, b = left ? s34.y : s56.y;
+			const bool left2 = KG_GT(b, a);
+			moved = left2 ? a : b;
+			const uint32_t pre = 4u * A + C + (left ? 0u : 32u);
+			asm volatile("st.shared.f64 [%0], %1;" ::"r"((A + m.hs_a - 8u) >> 1), "d"(m1));      // hs[h]
+			asm volatile("st.shared.f64 [%0], %1;" ::"r"(A + (left ? 0u : 8u)), "d"(moved));      // hs[2h + 1 + !left]
+			A = left2 ? pre : pre + 16u;
+		}
+		int32_t hole = (int32_t)((A - m.hs_a - 8u) >> 4);
+		while (hole < lim) {                                  // the last level or two, with the bounds tests
+			const int32_t l = 2 * hole + 1;
+			int32_t g = 2 * l + 1;
+			g = g > g_max ? 3 : g;
+			const double2 s12 = m.lds2(l);
+			const double2 s34 = m.lds2(g);
+			const double2 s56 = m.lds2(g + 2);
+			const bool left = KG_GT(s12.y, s12.x);
+			const int32_t c = left ? l : l + 1;
+			moved = left ? s12.x : s12.y;
+			m.sts(hole, moved);
+			hole = c;
+			if (!(c < lim)) break;
+			const double a = left ? s34.x : s56.x, b = left ? s34.y : s56.y;
+			const bool left2 = KG_GT(b, a);
+			moved = left2 ? a : b;
+			m.sts(c, moved);
+			hole = 2 * c + (left2 ? 1 : 2);
+		}
+		if (hole == sh.edge) {                                // the last inner entry has a left child only
+			const int32_t ch = 2 * hole + 1;
+			moved = m.lds(ch);
+			m.sts(hole, moved);
+			hole = ch;
+		}
+		rec.leaf = (uint32_t)hole;
+		sifted = KG_REC_SIFTED;
+		if (hole > 0 && !KG_GT(moved, v)) m.sts(hole, v);
+		else c1 = kg_heap_push_up_scores(m, hole, v);
+	}
+	const uint32_t c2 = kg_heap_push_up_scores(m, len - 1, v_new);
+	rec.pos = (uint32_t)(len - 1);
+	rec.info = c1 | (c2 << 8) | (KG_REC_POP << 16) | sifted;
+}
+#endif
+
+__host__ __device__ __forceinline__ uint32_t kg_heap_depth(uint32_t i) {   // level of position i (root = 0)
+#ifdef __CUDA_ARCH__
+	return 31u - (uint32_t)__clz((int)(i + 1u));
+#else
+	uint32_t d = 0;
+	while (((i + 1u) >> (d + 1)) != 0u) d++;
+	return d;
+#endif
+}
+
+// What a record does to the slot array, one move after the other (the definition; tests/heap_host_check.cu runs it
+// against the oracle).  Net effect of the sift + the re-inserted entry's climb of c1 levels on the path node(0) = root ..
+// node(d) = leaf: entries above level d - c1 move up one level, level d - c1 takes the old last entry, the levels below
+// it end up unchanged.  Then the new entry's climb of c2 levels along the ancestors of `pos`.  Returns the new entry's slot.
+__host__ __device__ inline uint32_t kg_heap_apply_slots_seq(uint32_t *hl, const KgHeapRec &rec) {
+	const uint32_t c1 = rec.info & 0xffu, c2 = (rec.info >> 8) & 0xffu, type = (rec.info >> 16) & 3u;
+	uint32_t slot = rec.pos;                              // fill phase: slot = position at admission
+	if (type == KG_REC_POP) {
+		slot = hl[0];                                     // the evicted entry's slot is reused
+		if (rec.info & KG_REC_SIFTED) {
+			const uint32_t last = hl[rec.pos];
+			const uint32_t d = kg_heap_depth(rec.leaf), i1 = rec.leaf + 1u;
+			for (uint32_t j = 0; j + c1 < d; j++) hl[(i1 >> (d - j)) - 1u] = hl[(i1 >> (d - j - 1)) - 1u];
+			hl[(i1 >> c1) - 1u] = last;
+		}
+	}
+	const uint32_t q1 = rec.pos + 1u;
+	for (uint32_t t = 0; t < c2; t++) hl[(q1 >> t) - 1u] = hl[(q1 >> (t + 1)) - 1u];
+	hl[(q1 >> c2) - 1u] = slot;
+	return slot;
+}
+
+#ifdef __CUDACC__
+// The same, by one warp: every level of the path (then of the climb) is one lane.
+__device__ __forceinline__ uint32_t kg_heap_apply_slots_warp(uint32_t *hl, const KgHeapRec &rec, uint32_t lane) {
+	const uint32_t c1 = rec.info & 0xffu, c2 = (rec.info >> 8) & 0xffu, type = (rec.info >> 16) & 3u;
+	uint32_t slot = rec.pos, val = 0;
+	if (type == KG_REC_POP) {
+		slot = hl[0];
+		if (rec.info & KG_REC_SIFTED) {
+			const uint32_t last = hl[rec.pos];
+			const uint32_t d = kg_heap_depth(rec.leaf), i1 = rec.leaf + 1u, nmove = d - c1;
+			if (lane < nmove) val = hl[(i1 >> (d - lane - 1)) - 1u];
+			__syncwarp();
+			if (lane < nmove) hl[(i1 >> (d - lane)) - 1u] = val;
+			else if (lane == nmove) hl[(i1 >> c1) - 1u] = last;
+		}
+		__syncwarp();
+	}
+	const uint32_t q1 = rec.pos + 1u;
+	if (lane < c2) val = hl[(q1 >> (lane + 1)) - 1u];
+	__syncwarp();
+	if (lane < c2) hl[(q1 >> lane) - 1u] = val;
+	else if (lane == c2) hl[(q1 >> c2) - 1u] = slot;
+	__syncwarp();
+	return slot;
+}
+#endif
+
+// pointer forms (host check)
+__host__ __device__ __forceinline__ void kg_heap_push_up(double *hs, uint32_t *hl, int32_t hole, double v, uint32_t vs) {
+	kg_heap_push_up<4>(KgHeapPtr{hs, hl}, hole, v, vs);
+}
+__host__ __device__ __forceinline__ void kg_heap_replace_top(double *hs, uint32_t *hl, int32_t len, int32_t cap, double v_new, uint32_t slot_new) {
+	kg_heap_replace_top(KgHeapPtr{hs, hl}, len, cap, v_new, slot_new);
 }
 
 __device__ __forceinline__ void kg_bitonic_sort_u64(unsigned long long *buf, uint32_t n2) {
@@ -242,17 +563,24 @@ __global__ void __launch_bounds__(KG_SEL_THREADS) kg_select_replay_kernel(const 
 
 	// ---- replay: thread 0 runs add_association over the candidates, block by block
 	KgCand *stage = reinterpret_cast<KgCand *>(scratch);
+	const KgHeapShared heap(hs, hl);
 	uint64_t *pk = prm.pay_kmer + (size_t)p * prm.kmax, *pr = prm.pay_row + (size_t)p * prm.kmax;
 	KgCand *log = prm.log ? prm.log + (size_t)p * prm.log_cap : nullptr;
 	uint32_t n_log = log ? prm.log_count[p] : 0;
 	const double floor_thr = prm.floor_thr ? prm.floor_thr[p] : -1.0;
 	unsigned long long pushes = 0, pops = 0;
-#ifdef KG_SEL_PROFILE
-	long long t_loop = 0, t_rep = 0, t_all0 = clock64();
-#endif
 	__shared__ uint32_t s_warp_cnt[KG_SEL_THREADS / 32];
 	__shared__ uint32_t s_m;
 	__shared__ uint32_t s_size_now;
+	// record ring between the sequential thread (warp 0, lane 0) and the slot warp (warp 1); positions only grow
+	__shared__ __align__(16) KgHeapRec s_ring[KG_SEL_RING];
+	__shared__ uint32_t s_head, s_tail, s_nlog;
+	uint32_t a_ring = (uint32_t)__cvta_generic_to_shared(s_ring), a_head = (uint32_t)__cvta_generic_to_shared(&s_head),
+	         a_tail = (uint32_t)__cvta_generic_to_shared(&s_tail);
+	asm volatile("" : "+r"(a_ring), "+r"(a_head), "+r"(a_tail));   // kept in registers (see KgHeapShared)
+	if (threadIdx.x == 0) { s_head = 0; s_tail = 0; s_nlog = n_log; }
+	uint32_t ring_pos = 0;                                 // producer: records written; consumer: records applied
+	uint32_t tail_seen = 0;                                // producer: the slot warp's position when last read
 	for (uint32_t b0 = 0; b0 < n; b0 += KG_SEL_STAGE) {
 		const uint32_t m_in = min((uint32_t)KG_SEL_STAGE, n - b0);
 		// Stage the block, dropping IN PARALLEL (order kept) every candidate the sequential loop would reject on its
@@ -286,51 +614,72 @@ __global__ void __launch_bounds__(KG_SEL_THREADS) kg_select_replay_kernel(const 
 		}
 		const uint32_t m = s_m;
 		if (threadIdx.x == 0) {
-#ifdef KG_SEL_PROFILE
-			const long long tl0 = clock64();
-#endif
-			for (uint32_t i = 0; i < m; i++) {
-				const double s = stage[i].score;
-				uint32_t slot;
-				if (size < K) {                                  // :45-48 heap not full: push
-					if (s <= floor_thr) continue;                // (only in multi-GPU shards > 0; never while exactness matters)
-					slot = size;
-					kg_heap_push_up(hs, hl, (int32_t)size, s, slot);
-					size++;
+			// ---- the sequential half: add_association on the scores, one record per admission
+			const KgHeapShape shape = kg_heap_shape((int32_t)K);   // used once size == K
+			double s_next = m ? stage[0].score : 0.0;            // the next candidate's score is fetched one admission ahead
+			for (uint32_t i = 0; i <= m; i++) {
+				KgHeapRec rec;
+				if (i < m) {
+					const double s = s_next;
+					s_next = stage[i + 1 < m ? i + 1 : i].score;
+					if (size < K) {                                  // :45-48 heap not full: push
+						if (s <= floor_thr) continue;                // (only in multi-GPU shards > 0; never while exactness matters)
+						rec.leaf = 0;
+						rec.pos = size;
+						rec.info = (kg_heap_push_up_scores(heap, (int32_t)size, s) << 8) | (KG_REC_PUSH << 16);
+						size++;
+					} else {
+						if (!(s > heap.lds(0)) || s <= floor_thr) continue;   // :50 strict '>' against lowest_score = top
+						kg_heap_replace_top_scores(heap, shape, kpad, s, rec);
+						pops++;
+					}
+					pushes++;
+					rec.cand = i;
 				} else {
-					if (!(s > hs[0]) || s <= floor_thr) continue;   // :50 strict '>' against lowest_score = top
-					slot = hl[0];
-#ifdef KG_SEL_PROFILE
-					const long long tr0 = clock64();
-#endif
-					kg_heap_replace_top(hs, hl, (int32_t)size, kpad, s, slot);
-#ifdef KG_SEL_PROFILE
-					t_rep += clock64() - tr0;
-#endif
-					pops++;
+					rec.cand = rec.leaf = rec.pos = 0;
+					rec.info = KG_REC_END << 16;                     // the slot warp leaves its loop for this block
 				}
-				pushes++;
-				pk[slot] = stage[i].kmer;
-				pr[slot] = stage[i].row;
-				if (log) {
-					if (n_log < prm.log_cap) log[n_log] = stage[i];
-					n_log++;
-				}
+				while (ring_pos - tail_seen >= KG_SEL_RING)          // ring full as far as known: look at the slot warp's position
+					asm volatile("ld.relaxed.cta.shared.u32 %0, [%1];" : "=r"(tail_seen) : "r"(a_tail));
+				asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_ring + 16u * (ring_pos % KG_SEL_RING)), "r"(rec.cand),
+				             "r"(rec.leaf), "r"(rec.info), "r"(rec.pos));
+				ring_pos++;
+				asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a_head), "r"(ring_pos) : "memory");
 			}
-#ifdef KG_SEL_PROFILE
-			t_loop += clock64() - tl0;
-#endif
+		} else if ((threadIdx.x >> 5) == 1) {
+			// ---- the slot half: apply the records to hl[], store the payload and the admission log
+			const uint32_t lane = threadIdx.x & 31;
+			uint32_t nl = s_nlog;
+			for (bool open = true; open;) {
+				uint32_t h;
+				do {   // lane 0 polls, the warp stays converged on one value
+					h = 0;
+					if (lane == 0) asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(h) : "r"(a_head) : "memory");
+					h = __shfl_sync(0xffffffffu, h, 0);
+					if (h == ring_pos) __nanosleep(32);
+				} while (h == ring_pos);
+				for (; ring_pos != h; ring_pos++) {
+					const uint4 r4 = *reinterpret_cast<const uint4 *>(&s_ring[ring_pos % KG_SEL_RING]);
+					KgHeapRec rec;
+					rec.cand = r4.x; rec.leaf = r4.y; rec.info = r4.z; rec.pos = r4.w;
+					if (((rec.info >> 16) & 3u) == KG_REC_END) { open = false; ring_pos++; break; }
+					const uint32_t slot = kg_heap_apply_slots_warp(hl, rec, lane);
+					if (lane == 0) {
+						pk[slot] = stage[rec.cand].kmer;
+						pr[slot] = stage[rec.cand].row;
+					} else if (lane == 1 && log) {
+						if (nl < prm.log_cap) log[nl] = stage[rec.cand];
+					}
+					nl++;
+				}
+				__syncwarp();
+				if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a_tail), "r"(ring_pos) : "memory");
+			}
+			if (lane == 0) s_nlog = nl;
 		}
 		__syncthreads();
 	}
-#ifdef KG_SEL_PROFILE
-	if (threadIdx.x == 0 && p == 0) {
-		atomicAdd(prm.status + 10, (unsigned long long)t_loop);
-		atomicAdd(prm.status + 11, (unsigned long long)t_rep);
-		atomicAdd(prm.status + 12, (unsigned long long)(clock64() - t_all0));
-		atomicAdd(prm.status + 13, pops);
-	}
-#endif
+	n_log = s_nlog;
 
 	// ---- heap: shared -> global; threshold for the scan kernels (only thread 0 knows the new size)
 	__shared__ uint32_t s_size;

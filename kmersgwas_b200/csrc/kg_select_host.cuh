@@ -259,10 +259,6 @@ extern "C" kg_status kg_select_stats(kg_ctx *c, uint64_t *rounds, uint64_t *cand
 	if (rounds) *rounds = s.h_status[KG_SEL_ST_ROUNDS];
 	if (candidates) *candidates = s.h_status[KG_SEL_ST_CANDS];
 	if (reorders) *reorders = s.h_status[KG_SEL_ST_REORDERS];
-#ifdef KG_SEL_PROFILE
-	fprintf(stderr, "[kg select profile, phenotype 0] cycles: replay loop %llu, replace_top %llu, kernel after sort %llu; pops %llu\n",
-	        s.h_status[10], s.h_status[11], s.h_status[12], s.h_status[13]);
-#endif
 	if (admitted) {
 		std::vector<unsigned long long> hs(2 * (size_t)s.n_pheno);
 		KG_CUDA(c, cudaMemcpy(hs.data(), s.d_hstat, hs.size() * 8, cudaMemcpyDeviceToHost));

@@ -15,16 +15,29 @@ int main() {
 		struct { uint32_t *p; uint32_t *data() { return p; } uint32_t &operator[](size_t i) { return p[i]; } } hl{hlp};
 		std::vector<uint64_t> pk(K), pr(K);
 		uint32_t size = 0;
+		// second copy driven by the split form (scores by the sequential half, slots from the records)
+		void *raw3 = aligned_alloc(16, kpad * 8 + 32); double *hs2 = (double *)((char *)raw3 + 8);
+		std::vector<uint32_t> hl2(kpad + 8);
 		kgo_heap *o = kgo_heap_new(K);
 		for (int i = 0; i < n; i++) {
 			const double s = (double)(rand() % 97);   // many ties
 			const uint64_t kmer = 1000 + i, row = i;
 			kgo_heap_add(o, kmer, s, row);
 			uint32_t slot;
+			{
+				const KgHeapPtr m2{hs2, hl2.data()};
+				KgHeapRec rec; rec.cand = 0; bool admit = true;
+				if (size < K) { rec.leaf = 0; rec.pos = size; rec.info = (kg_heap_push_up_scores(m2, (int32_t)size, s) << 8) | (KG_REC_PUSH << 16); }
+				else if (s > hs2[0]) kg_heap_replace_top_scores(m2, (int32_t)size, (int32_t)kpad, s, rec);
+				else admit = false;
+				if (admit) kg_heap_apply_slots_seq(hl2.data(), rec);
+			}
 			if (size < K) { slot = size; kg_heap_push_up(hs, hl.data(), (int32_t)size, s, slot); size++; }
 			else { if (!(s > hs[0])) continue; slot = hl[0]; kg_heap_replace_top(hs, hl.data(), (int32_t)size, (int32_t)kpad, s, slot); }
 			pk[slot] = kmer; pr[slot] = row;
 		}
+		for (uint32_t i = 0; i < size; i++) if (hs2[i] != hs[i] || hl2[i] != hl[i]) { printf("trial %d: split form differs at %u\n", trial, i); return 1; }
+		free(raw3);
 		// compare by popping copies: push layout into a fresh oracle heap
 		kgo_heap *d = kgo_heap_new(K ? K : 1);
 		for (uint32_t i = 0; i < size; i++) kgo_heap_add(d, pk[hl[i]], hs[i], pr[hl[i]]);
