@@ -20,7 +20,8 @@
 // The phenotype columns are sorted by alpha and tested 16 at a time: max |Q| of the group against the group's
 // smallest alpha and largest kappa.  A row with no surviving group is ruled out for every phenotype.
 //
-// Kernel: persistent, one CTA per SM, 128-row blocks, warp-specialised (23 warps):
+// Kernel: persistent, one CTA per SM, 128-row blocks, warp-specialised (23 warps; the numbers below are the split for
+// tables wider than 4 presence words, narrow tables trade expander warps for epilogue sets: kg_filter_split_*):
 //   warp 0        bulk-async-copies raw 128-row blocks (contiguous 128 * 8(1+W) bytes) into a 4-stage ring
 //   warps 1-12    expanders: presence bits -> s8 {0, -1} with 8 PRMTs per 32 bits (byte-permute against constant
 //                 tables, ALU pipe only), stored with tcgen05.st straight into TENSOR MEMORY (A operand from TMEM: lane =
@@ -47,18 +48,25 @@
 #define KG_F_TMEM_COLS 512       //   2 x p_pad accumulator columns + a_stages x 16 a_words columns <= 512
 #define KG_F_RAW_STAGES 4         // most raw row-block stages (KgFilterParams::raw_stages of them are used: 4, fewer for wide tables)
 #define KG_F_EXPAND_WARP0 1
-#ifndef KG_F_EXPAND_WARPS
-#define KG_F_EXPAND_WARPS 12        // KG_F_EXPAND_WARPS / 4 per TMEM lane quarter share a stage's words
-#endif
-#define KG_F_NSUB (KG_F_EXPAND_WARPS / 4)
-#define KG_F_MAX_WPT 3           // presence words per expander thread and stage: a_words <= KG_F_MAX_WPT * KG_F_NSUB
-#define KG_F_EPI_WARP0 (KG_F_EXPAND_WARP0 + KG_F_EXPAND_WARPS)
-#define KG_F_EPI_WARPS 8         // two sets of 4 (one warp per TMEM lane quarter); set s owns accumulator buffer s
-#define KG_F_MMA_WARP0 (KG_F_EPI_WARP0 + KG_F_EPI_WARPS)
+// Role split = template parameters <NEXP expander warps, NACC accumulator buffers = epilogue sets of 4 warps>, always
+// 1 + NEXP + 4 NACC + KG_F_MMA_WARPS = 23 warps.  The epilogue's work per row block does not shrink with the table's width
+// (P_pad accumulators per row whatever W is) while the expansion's does, so narrow tables trade expander warps for
+// epilogue sets (measured, filter ms per 1.2e9 rows at N = 241: <12,2> 65.5, <8,3> 50.7, <4,4> 61.5; per 2e9 rows at
+// N = 64: 93.3 / 70.7 / 59.5):
+//   split 0  <12, 2>  W > 4 presence words: the expansion of 128 x 64 W presence bits is the larger job
+//   split 1  < 8, 3>  W <= 4
+//   split 2  < 4, 4>  W <= 2
+// as long as NACC x P_pad accumulator columns + two A stages fit the 512 tensor-memory columns.
+#define KG_F_SPLITS 3
+__host__ __device__ constexpr int kg_filter_split_nexp(int split) { return split == 0 ? 12 : split == 1 ? 8 : 4; }
+__host__ __device__ constexpr int kg_filter_split_nacc(int split) { return split == 0 ? 2 : split == 1 ? 3 : 4; }
+__host__ __device__ constexpr int kg_filter_split_max_w(int split) { return split == 0 ? 1 << 30 : split == 1 ? 4 : 2; }
+#define KG_F_MAX_ACC 4           // barrier slots for the accumulator buffers
+#define KG_F_MAX_WPT 3           // presence words per expander thread and stage: a_words <= KG_F_MAX_WPT * (NEXP / 4)
 #ifndef KG_F_MMA_WARPS
 #define KG_F_MMA_WARPS 2         // issuers that take turns with the A-stage batches of the MMA stream (see the MMA role below)
 #endif
-#define KG_F_THREADS ((KG_F_MMA_WARP0 + KG_F_MMA_WARPS) * 32)
+#define KG_F_THREADS ((KG_F_EXPAND_WARP0 + 12 + 4 * 2 + KG_F_MMA_WARPS) * 32)
 #define KG_F_NO_Q INT32_MIN      // ent_q marker: this (row, group) entry has no recorded accumulators
 #define KG_F_ONE 1               // accumulator units per presence bit: A holds -1 (0xFF, s8), B holds the NEGATED phenotype column
 // perf-experiment switches (KgFilterParams::dbg) exist only in builds with -DKG_PERF_SWITCHES; a production build
@@ -189,8 +197,11 @@ __device__ __forceinline__ int32_t kg_filter_bound_to_int(float thr) {
 	return (int32_t)ceilf(thr);
 }
 
-template <int MODE>  // 0 = list candidate rows, 1 = debug: dump accumulators
+template <int MODE, int NEXP, int NACC>  // MODE 0 = list candidate rows, 1 = debug: dump accumulators; role split (above)
 __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const KgFilterParams prm) {
+	constexpr uint32_t KG_F_EXPAND_WARPS = NEXP, KG_F_NSUB = NEXP / 4;
+	constexpr uint32_t KG_F_EPI_WARP0 = KG_F_EXPAND_WARP0 + NEXP, KG_F_MMA_WARP0 = KG_F_EPI_WARP0 + 4 * NACC;
+	static_assert(NEXP % 4 == 0 && NACC >= 2 && NACC <= KG_F_MAX_ACC && (KG_F_MMA_WARP0 + KG_F_MMA_WARPS) * 32 == KG_F_THREADS, "role split");
 	extern __shared__ uint8_t kg_f_smem_raw[];
 	// carve shared memory (1024-byte aligned base)
 	uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)kg_f_smem_raw + 1023) & ~(uintptr_t)1023);
@@ -202,8 +213,8 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 	uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(sTab) + ((tab_floats * sizeof(float) + 15) & ~(size_t)15));
 	uint64_t *raw_full = bars, *raw_empty = bars + KG_F_RAW_STAGES;
 	uint64_t *a_full = bars + 2 * KG_F_RAW_STAGES, *a_empty = a_full + KG_F_MAX_A_STAGES;
-	uint64_t *tm_full = a_empty + KG_F_MAX_A_STAGES, *tm_empty = tm_full + 2;
-	uint64_t *b_full = tm_empty + 2;
+	uint64_t *tm_full = a_empty + KG_F_MAX_A_STAGES, *tm_empty = tm_full + KG_F_MAX_ACC;
+	uint64_t *b_full = tm_empty + KG_F_MAX_ACC;
 	uint64_t *turn = b_full + 1;   // [KG_F_MMA_WARPS] issue-order token passed round the MMA issuers
 	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(turn + KG_F_MMA_WARPS);
 
@@ -215,7 +226,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 		for (int i = 0; i < KG_F_RAW_STAGES; i++) { kg_mbar_init(&raw_full[i], 1); kg_mbar_init(&raw_empty[i], KG_F_EXPAND_WARPS); }
 		for (int i = 0; i < KG_F_MAX_A_STAGES; i++) { kg_mbar_init(&a_full[i], KG_F_EXPAND_WARPS); kg_mbar_init(&a_empty[i], 1); }
 		// tm_full: one tcgen05.commit from each issuer that has MMAs in the block (a commit tracks the issuing thread only)
-		for (int i = 0; i < 2; i++) { kg_mbar_init(&tm_full[i], min(prm.nc, prm.n_issuers)); kg_mbar_init(&tm_empty[i], 4); }
+		for (int i = 0; i < NACC; i++) { kg_mbar_init(&tm_full[i], min(prm.nc, prm.n_issuers)); kg_mbar_init(&tm_empty[i], 4); }
 		for (int i = 0; i < KG_F_MMA_WARPS; i++) kg_mbar_init(&turn[i], 1);
 		kg_mbar_init(b_full, 1);
 		kg_fence_mbar_init();
@@ -263,7 +274,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 		// run the loop (descriptors in uniform registers); one elected lane issues.
 		const uint32_t k = warp - KG_F_MMA_WARP0;
 		const uint32_t idesc = kg_umma_idesc_i8(KG_F_ROWS, prm.p_pad, true, true, false, false);
-		const uint32_t a_tmem0 = tmem_base + 2 * prm.tcols;                             // A stage 0, K offset 0
+		const uint32_t a_tmem0 = tmem_base + NACC * prm.tcols;                          // A stage 0, K offset 0
 		const uint32_t a_stage_cols = 16 * prm.a_words;
 		const uint64_t b_desc0 = kg_umma_smem_desc(kg_smem_u32(sB), 128, prm.sbo_b);   // column chunk 0
 		kg_mbar_wait(b_full, 0);
@@ -276,7 +287,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 		uint32_t turn_par = 0;
 		bool first = k == 0;
 		while (it < n_it) {
-			const uint32_t buf = it & 1;
+			const uint32_t buf = it % NACC;
 			const uint32_t d_tmem = tmem_base + buf * prm.tcols;
 			// The token comes FIRST: once every earlier batch has been issued, the previous user of this A stage (and of
 			// this accumulator buffer) has passed its own wait, so the barriers below are in the phase this batch waits
@@ -287,7 +298,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 			}
 			first = false;
 			if (c == 0) {
-				kg_mbar_wait(&tm_empty[buf], ((it >> 1) & 1) ^ 1);
+				kg_mbar_wait(&tm_empty[buf], ((it / NACC) & 1) ^ 1);
 				kg_tc_fence_after();
 			}
 			kg_mbar_wait(&a_full[st], st_par);
@@ -333,7 +344,7 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 		// my words [lo, hi) of a full stage / of the last (possibly shorter) stage of a row block
 		const uint32_t per_f = (prm.a_words + KG_F_NSUB - 1) / KG_F_NSUB, lo_f = min(sub * per_f, prm.a_words), hi_f = min(lo_f + per_f, prm.a_words);
 		const uint32_t per_l = (words_last + KG_F_NSUB - 1) / KG_F_NSUB, lo_l = min(sub * per_l, words_last), hi_l = min(lo_l + per_l, words_last);
-		const uint32_t a_taddr0 = tmem_base + 2 * prm.tcols + ((q4 * 32u) << 16);
+		const uint32_t a_taddr0 = tmem_base + NACC * prm.tcols + ((q4 * 32u) << 16);
 		uint32_t it = 0, st = 0, st_par = 1;                            // a_empty parity: the first pass finds every stage free
 		uint32_t rst = 0, r_par = 0;
 		for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, it++) {
@@ -393,11 +404,11 @@ __global__ void __launch_bounds__(KG_F_THREADS, 1) kg_scan_filter_kernel(const K
 		const uint32_t r = q4 * 32 + lane;                  // row of the block = TMEM lane
 		const uint32_t eset = (warp - KG_F_EPI_WARP0) >> 2; // this warp's set: it handles the blocks of accumulator buffer eset
 		unsigned long long kept_local = 0;
-		for (uint32_t it = eset; (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x < n_blocks; it += 2) {
+		for (uint32_t it = eset; (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x < n_blocks; it += NACC) {
 			const uint32_t blk = blockIdx.x + it * gridDim.x;
 			const uint64_t grow = (uint64_t)blk * KG_F_ROWS + r;
 			const uint32_t buf = eset;
-			kg_mbar_wait(&tm_full[buf], (it >> 1) & 1);
+			kg_mbar_wait(&tm_full[buf], (it / NACC) & 1);
 			kg_tc_fence_after();
 			const uint32_t taddr = tmem_base + buf * prm.tcols + ((q4 * 32u) << 16);
 			if (MODE == 1) {

@@ -84,6 +84,17 @@ static kg_status kg_tc_retune(kg_ctx *c, bool force) {
 	return KG_OK;
 }
 
+// the filter kernel instance for a role split / mode (kg_scan_filter.cuh)
+typedef void (*KgFilterKernel)(const KgFilterParams);
+template <int SPLIT>
+static KgFilterKernel kg_filter_kernel_pick(int mode) {
+	constexpr int E = kg_filter_split_nexp(SPLIT), A = kg_filter_split_nacc(SPLIT);
+	return mode ? kg_scan_filter_kernel<1, E, A> : kg_scan_filter_kernel<0, E, A>;
+}
+static KgFilterKernel kg_filter_kernel_of(int split, int mode) {
+	return split == 2 ? kg_filter_kernel_pick<2>(mode) : split == 1 ? kg_filter_kernel_pick<1>(mode) : kg_filter_kernel_pick<0>(mode);
+}
+
 static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	KgTcState &tc = c->tc;
 	tc.scan_ready = false;
@@ -123,9 +134,18 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	tc.raw_stages = best_rs;
 	tc.b_bytes = (tc.p_pad / 8) * tc.sbo_b;
 	tc.tcols = tc.p_pad;
-	// tensor memory: 2 accumulator buffers + the A stages (16 columns per presence word); as few, as large stages as fit
+	// role split of the kernel (kg_scan_filter.cuh): the narrower the table, the more accumulator buffers / epilogue sets
+	tc.split = 0;
+	for (int sp = KG_F_SPLITS - 1; sp > 0; sp--)
+		if ((int)c->w_file <= kg_filter_split_max_w(sp) &&
+		    kg_filter_split_nacc(sp) * tc.p_pad + 2 * 16 * std::min<uint32_t>(c->w_file, 2) <= KG_F_TMEM_COLS) { tc.split = sp; break; }
+#ifdef KG_PERF_SWITCHES
+	if (const char *e = getenv("KG_FILTER_SPLIT")) tc.split = std::max(0, std::min(KG_F_SPLITS - 1, atoi(e)));
+#endif
+	// tensor memory: the accumulator buffers + the A stages (16 columns per presence word); as few, as large stages as fit
 	{
-		const uint32_t a_cols = KG_F_TMEM_COLS - 2 * tc.p_pad;
+		const uint32_t KG_F_NSUB = (uint32_t)kg_filter_split_nexp(tc.split) / 4;
+		const uint32_t a_cols = KG_F_TMEM_COLS - (uint32_t)kg_filter_split_nacc(tc.split) * tc.p_pad;
 		tc.a_words = std::max(1u, std::min<uint32_t>(c->w_file, a_cols / 32));           // at least two stages (few large stages measured best)
 		tc.a_words = std::min<uint32_t>(tc.a_words, KG_F_MAX_WPT * KG_F_NSUB);            // register budget of the expanders
 #ifdef KG_PERF_SWITCHES   // perf experiments only (profiles/filter_dbg_sweep.sh builds with -DKG_PERF_SWITCHES)
@@ -242,8 +262,8 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	tc.n_issuers = getenv("KG_FILTER_ISSUERS") ? (uint32_t)std::max(1, std::min(KG_F_MMA_WARPS, atoi(getenv("KG_FILTER_ISSUERS")))) : 0u;
 	tc.print_stats = getenv("KG_FILTER_STATS") != nullptr;
 #endif
-	KG_CUDA(c, cudaFuncSetAttribute(kg_scan_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	KG_CUDA(c, cudaFuncSetAttribute(kg_scan_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	KG_CUDA(c, cudaFuncSetAttribute(kg_filter_kernel_of(tc.split, 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	KG_CUDA(c, cudaFuncSetAttribute(kg_filter_kernel_of(tc.split, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	tc.scan_ready = true;
 	tc.why_unavailable.clear();
 	// first images: every threshold is -1 (d_thr as kg_scan_set_phenotypes left it) -> alpha = 0, every kept row listed
@@ -372,7 +392,7 @@ static kg_status kg_tc_scan_tile(kg_ctx *c, const uint64_t *dev_in, uint64_t n_r
 		// by kg_tile_end_kernel / kg_select_round_end_kernel after every pass
 		KgFilterParams f = kg_tc_filter_params(c, dev, n_rows, pass);
 		timing_begin(c, KG_KERNEL_SCAN_FILTER, n_rows);
-		kg_scan_filter_kernel<0><<<grid, KG_F_THREADS, tc.smem_bytes, c->stream>>>(f);
+		kg_filter_kernel_of(tc.split, 0)<<<grid, KG_F_THREADS, tc.smem_bytes, c->stream>>>(f);
 		timing_end(c);
 		KG_LAUNCH_CHECK(c);
 
@@ -474,7 +494,7 @@ static kg_status kg_tc_filter_debug(kg_ctx *c, const uint64_t *dev_in, uint64_t 
 		KgFilterParams f = kg_tc_filter_params(c, dev, n_rows, pass);
 		f.q_out = d_q;
 		f.kept_count = c->d_counters + 4;  // scratch counter: the debug pass must not change rows_kept
-		kg_scan_filter_kernel<1><<<grid, KG_F_THREADS, tc.smem_bytes, c->stream>>>(f);
+		kg_filter_kernel_of(tc.split, 1)<<<grid, KG_F_THREADS, tc.smem_bytes, c->stream>>>(f);
 		c->launches++;
 		e1 = cudaGetLastError();
 		if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(c->stream);

@@ -36,6 +36,7 @@ struct KgTcState {
 	std::vector<float> kappa;              // [P]
 	std::vector<uint8_t> degenerate;       // [P] phenotype column the bound cannot handle: always a candidate
 	uint32_t p_pad = 0, nc = 0, sbo_b = 0, b_bytes = 0, tcols = 0, a_words = 0, a_stages = 0;
+	int split = 0;                         // role split of the filter kernel (kg_filter_split_*): 0 wide, 1 / 2 narrow tables
 	uint32_t n_pass = 1, cols_per_pass = 0, raw_stages = 4;   // phenotype columns are scanned in passes of <= 127 (P_pad <= 128)
 	size_t smem_bytes = 0;
 	uint64_t *d_aligned = nullptr;         // realigned copy of a tile whose device pointer is not 16-byte aligned
