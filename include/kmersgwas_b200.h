@@ -78,7 +78,7 @@ enum {
 	/* device-side selection (kg_select_*): set before kg_select_begin */
 	KG_OPT_SELECT_GROWTH_PERMILLE = 6, /* round length = growth x rows scanned so far, in 1/1000 (default 500); the expected
 	                              number of candidates per phenotype and round is growth x K */
-	KG_OPT_SELECT_MAX_ROUND = 7,  /* longest round in rows (default 1 << 23) */
+	KG_OPT_SELECT_MAX_ROUND = 7,  /* longest round in rows (default 1 << 24) */
 	KG_OPT_SELECT_CAND_CAP = 8,   /* candidates a phenotype's segment holds per round (default max(4 K, 65536)) */
 	KG_OPT_SELECT_LOG_CAP = 9     /* admission-log entries per phenotype (default 32 K + 65536); KG_SELECT_LOG only */
 };
