@@ -46,7 +46,9 @@
 #define KG_F_ROWS 128            // rows per block = UMMA M
 #define KG_F_MAX_A_STAGES 8      // A stages live in tensor memory next to the two accumulator buffers:
 #define KG_F_TMEM_COLS 512       //   2 x p_pad accumulator columns + a_stages x 16 a_words columns <= 512
-#define KG_F_RAW_STAGES 4         // most raw row-block stages (KgFilterParams::raw_stages of them are used: 4, fewer for wide tables)
+#define KG_F_RAW_STAGES 16        // most raw row-block stages (as many as fit next to the B image are used).  Narrow rows need MANY:
+                                 // a stage is 128 x 8(1+W) bytes (2 KB at W = 1) and ~40 KB per SM must be in flight to cover the
+                                 // HBM latency at full bandwidth (4 stages: N = 64 ran at 0.11 of the HBM peak)
 #define KG_F_EXPAND_WARP0 1
 // Role split = template parameters <NEXP expander warps, NACC accumulator buffers = epilogue sets of 4 warps>, always
 // 1 + NEXP + 4 NACC + KG_F_MMA_WARPS = 23 warps.  The epilogue's work per row block does not shrink with the table's width
@@ -131,7 +133,7 @@ __host__ __device__ inline uint32_t kg_filter_raw_stage_bytes(uint32_t w_file) {
 __host__ __device__ inline size_t kg_filter_tab_floats(uint32_t p_pad, uint32_t n_used) { return (size_t)(p_pad / 16) * ((size_t)n_used + 1); }
 __host__ __device__ inline size_t kg_filter_smem_bytes(uint32_t w_file, uint32_t b_bytes, uint32_t p_pad, uint32_t raw_stages, uint32_t n_used) {
 	return 1024 /*alignment slack*/ + (size_t)b_bytes + (size_t)raw_stages * kg_filter_raw_stage_bytes(w_file) +
-	       ((kg_filter_tab_floats(p_pad, n_used) * sizeof(float) + 15) & ~(size_t)15) + 320;
+	       ((kg_filter_tab_floats(p_pad, n_used) * sizeof(float) + 15) & ~(size_t)15) + 640;
 }
 // K index (byte inside the A / B operands) of file column `col`.  The expander (below) turns 16 presence bits into
 // 4 registers with 4 PRMTs: register b holds the samples 4 n + b (n = byte inside the register), i.e. inside every

@@ -174,6 +174,11 @@ static uint64_t kg_sel_next_round(const KgSelState &s, uint64_t left) {
 	uint64_t len;
 	if (s.rows_submitted < s.fill_rows) len = std::min<uint64_t>(s.fill_rows - s.rows_submitted, s.cand_cap);   // every kept row is a candidate
 	else len = std::min<uint64_t>(std::max<uint64_t>((uint64_t)(s.growth * (double)s.rows_submitted), s.min_round), s.max_round);
+	// Whole 128-row blocks (unless a cap forbids it): a round that starts at an odd row of a table with an odd number of
+	// words per row is not 16-byte aligned, and the filter then scans a device-to-device COPY of the round
+	// (kg_tc_aligned_tile) -- half of the cold phase's rounds did
+	const uint64_t up = (len + 127) & ~(uint64_t)127;
+	if (up <= s.max_round && (s.rows_submitted >= s.fill_rows || up <= s.cand_cap)) len = up;
 	return std::max<uint64_t>(1, std::min(len, left));
 }
 

@@ -102,11 +102,8 @@ static kg_status kg_tc_prepare_scan(kg_ctx *c) {
 	cudaFree(tc.d_yq); cudaFree(tc.d_gconst);
 	tc.d_yq = nullptr; tc.d_gconst = nullptr;
 	// the filter's list buffers are sized for the phenotype count they were allocated with ([p_pad / 16][capacity]):
-	// a new phenotype set starts from scratch (kg_tc_ensure_row_list reallocates on the next tile)
-	cudaFree(tc.d_row_list); cudaFree(tc.d_group_list); cudaFree(tc.d_ent_q); cudaFree(tc.d_ent_n1); cudaFree(tc.d_pairs);
-	tc.d_row_list = nullptr; tc.d_group_list = nullptr; tc.d_ent_q = nullptr; tc.d_ent_n1 = nullptr; tc.d_pairs = nullptr;
-	tc.row_list_cap = 0;
-	tc.qcap = 0;
+	// The list buffers ([groups][capacity]) survive a new phenotype set: kg_tc_ensure_row_list reallocates them when the
+	// new set needs more 16-column groups than they were sized for (tc.row_list_groups), or a longer tile arrives.
 	cudaFree(tc.d_scale); cudaFree(tc.d_kappa0); cudaFree(tc.d_degenerate); cudaFree(tc.d_q); cudaFree(tc.d_kidx);
 	cudaFree(tc.d_col_of); cudaFree(tc.d_group_lines); cudaFree(tc.d_thr_tab);
 	tc.d_thr_tab = nullptr;
@@ -327,17 +324,23 @@ static KgFilterParams kg_tc_filter_params(kg_ctx *c, const uint64_t *dev, uint64
 
 static kg_status kg_tc_ensure_row_list(kg_ctx *c, uint64_t n_rows) {
 	KgTcState &tc = c->tc;
-	if (tc.row_list_cap >= n_rows) return KG_OK;
+	const uint32_t n_groups_now = tc.p_pad / 16;
+	if (tc.row_list_cap >= n_rows && tc.row_list_groups >= n_groups_now) return KG_OK;
 	KG_CUDA(c, cudaStreamSynchronize(c->stream));
 	cudaFree(tc.d_row_list);
 	cudaFree(tc.d_group_list);
 	tc.d_row_list = nullptr;
 	tc.d_group_list = nullptr;
+	// Capacity grows by doubling: the device selection submits rounds that grow 1.5x each in the cold phase, and a
+	// reallocation (stream sync + cudaFree + cudaMalloc) per round was part of every job's first 10^8 rows
+	uint64_t want = std::max<uint64_t>({n_rows, tc.row_list_cap, (uint64_t)1 << 20});
+	if (n_rows > tc.row_list_cap && tc.row_list_cap) want = std::max<uint64_t>(want, 2 * tc.row_list_cap);
 	tc.row_list_cap = 0;
-	const uint64_t cap = std::max<uint64_t>(n_rows, 1u << 20);
+	tc.row_list_groups = std::max(tc.row_list_groups, n_groups_now);
+	const uint64_t cap = want;
 	cudaError_t e = cudaMalloc((void **)&tc.d_row_list, cap * sizeof(uint32_t));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc filter row list: %s", cudaGetErrorString(e));
-	e = cudaMalloc((void **)&tc.d_group_list, (size_t)(tc.p_pad / 16) * cap * sizeof(uint32_t));
+	e = cudaMalloc((void **)&tc.d_group_list, (size_t)tc.row_list_groups * cap * sizeof(uint32_t));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc filter group lists: %s", cudaGetErrorString(e));
 	tc.row_list_cap = cap;
 	// entries that carry their accumulators: the first qcap of every group list (longer lists stay in list mode)
@@ -346,7 +349,7 @@ static kg_status kg_tc_ensure_row_list(kg_ctx *c, uint64_t n_rows) {
 	// measured (B200, P = 101): a pair costs ~1.3 ns, a list-mode entry ~3.9 ns, and the per-column test leaves about
 	// one pair per entry, so pair mode wins for every list that is not most of the tile
 	tc.qcap = std::max<uint64_t>(4096, cap / 16);
-	const size_t n_groups = tc.p_pad / 16;
+	const size_t n_groups = tc.row_list_groups;
 	e = cudaMalloc((void **)&tc.d_ent_q, n_groups * tc.qcap * 16 * sizeof(int32_t));
 	if (e != cudaSuccess) KG_FAIL(c, KG_ERR_NOMEM, "cudaMalloc filter entry sums: %s", cudaGetErrorString(e));
 	e = cudaMalloc((void **)&tc.d_ent_n1, n_groups * tc.qcap * sizeof(uint32_t));

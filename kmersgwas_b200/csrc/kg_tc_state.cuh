@@ -12,6 +12,7 @@ struct KgTcState {
 	std::string why_unavailable = "tensor-core engine not initialised";
 	uint32_t *d_row_list = nullptr;        // rows of the current tile the filter could not rule out
 	uint64_t row_list_cap = 0;
+	uint32_t row_list_groups = 0;          // 16-column groups the list buffers below were sized for
 	uint32_t *d_group_list = nullptr;      // [p_pad / 16][row_list_cap] positions in d_row_list, per 16-column group
 	unsigned long long *d_group_count = nullptr;   // [16]
 	int32_t *d_tile_pheno = nullptr;       // [p_pad] phenotype of every filter column (-1: none)
