@@ -63,6 +63,50 @@ def test_full_tile_filter_engine_equals_exact_engine_at_warm_thresholds(kg):
     assert res[0][1] == 4 * TILE and res[0][0] != 0
 
 
+@pytest.mark.parametrize("n,p", [(241, 101), (64, 101), (128, 30)])
+def test_narrow_table_role_splits_equal_exact_engine_at_scale(kg, n, p):
+    """The narrow-table role splits of the filter kernel (<8,3> for W <= 4 presence words, <4,4> for W <= 2) on a full
+    2^22-row tile at warm thresholds: same device heaps as the exact engine."""
+    import torch
+    y = np.ascontiguousarray(np.random.default_rng(4300 + n).standard_normal((p, n)).astype(np.float32))
+    mc = S.min_count_of(n, 0.05, 5)
+    stride = (n + 63) // 64 + 1
+    tile = 1 << 22
+
+    def ctx(engine):
+        c = kg.Context.identity(n)
+        c.set_option(kg.OPT_SCAN_ENGINE, engine)
+        c.set_phenotypes(y, mc)
+        c.select_begin(K, 0)
+        return c
+
+    warm = ctx(0)
+    buf = torch.empty(tile * stride, dtype=torch.int64, device="cuda")
+    for t in range(3):
+        warm.synth_rows_device(79, t * tile, tile, buf.data_ptr())
+        warm.scan_submit(buf.data_ptr(), tile, t * tile)
+    applied, kept = warm.select_sync()
+    assert applied == 3 * tile
+    state = torch.empty(warm.select_state_len(), dtype=torch.int64, device="cuda")
+    warm.select_export(dev_ptr=state.data_ptr())
+    warm.synth_rows_device(79, 3 * tile, tile, buf.data_ptr())
+    res = []
+    for engine in (2, 1):
+        c = ctx(engine)
+        c.set_option(kg.OPT_KERNEL_TIMING, 1)
+        c.select_import(state.data_ptr(), applied, kept)
+        c.scan_submit(buf.data_ptr(), tile, 3 * tile)
+        a2, k2 = c.select_sync()
+        kt = c.kernel_times()
+        if engine == 2:
+            assert kt["scan_filter"][2] == tile and kt["scan_exact"][2] == 0
+        res.append((c.select_digest(), a2, k2, c.select_stats()["admitted"]))
+        c.close()
+    warm.close()
+    assert res[0] == res[1]
+    assert res[0][1] == 4 * tile and res[0][0] != 0
+
+
 def test_shard_protocol_equals_sequential_scan_at_scale(kg):
     import torch
     y = np.ascontiguousarray(np.random.default_rng(4243).standard_normal((P, N)).astype(np.float32))

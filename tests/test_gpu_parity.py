@@ -487,3 +487,22 @@ def test_pattern_counter_on_device(kg, subset):
     assert ctx.patterns_count()[0] == len(np.unique(np.concatenate([want, want2])))
     ctx.close()
     other.close()
+
+
+def test_bind_host_to_device_reports_a_node_or_nothing(gpu_device):
+    """kg_bind_host_to_device: -1 (nothing changed: single-node box, no sysfs entry) or the NUMA node of the GPU's PCIe
+    slot with at least one CPU left to run on; the library keeps working afterwards either way."""
+    import os
+    import kmersgwas_b200 as kg
+    before = os.sched_getaffinity(0)
+    node, cpus = kg._abi.bind_host_to_device(0)
+    after = os.sched_getaffinity(0)
+    try:
+        if node < 0:
+            assert cpus == 0 and after == before
+        else:
+            assert 1 <= cpus == len(after) and after <= before
+        c = kg.Context.identity(64)
+        c.close()
+    finally:
+        os.sched_setaffinity(0, before)
