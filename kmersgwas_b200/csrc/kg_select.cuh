@@ -8,8 +8,9 @@
 // exact replacement has to perform the same sequence of push_heap / pop_heap element moves.  This file does that on
 // the GPU: one CTA per phenotype holds the heap (score + payload slot per position, 12 bytes) in SHARED memory and one
 // thread replays the round's candidates in row order with libstdc++'s __push_heap / __adjust_heap (bits/stl_heap.h,
-// restated like oracle/oracle.c does for the CPU); the other threads sort the candidates by row (bitonic, shared or
-// global memory), stage them, and move the heap between shared and global memory.  The scan kernels feed it through
+// restated like oracle/oracle.c does for the CPU) -- on the SCORES; a second warp applies the same moves to the slot
+// array from the records that thread writes (kg_heap_apply_slots_warp) and stores the payload; the other threads sort
+// the candidates by row (bitonic, shared or global memory), stage them, and move the heap between shared and global memory.  The scan kernels feed it through
 // per-phenotype candidate segments; thresholds, the tensor filter's bound constants and its column order are
 // recomputed on the device after every round (kg_filter_retune_kernel), so the host is not in the scan loop at all.
 #pragma once
@@ -561,7 +562,7 @@ __global__ void __launch_bounds__(KG_SEL_THREADS) kg_select_replay_kernel(const 
 	}
 	__syncthreads();
 
-	// ---- replay: thread 0 runs add_association over the candidates, block by block
+	// ---- replay: add_association over the candidates, block by block (thread 0: scores; warp 1: slots + payload)
 	KgCand *stage = reinterpret_cast<KgCand *>(scratch);
 	const KgHeapShared heap(hs, hl);
 	uint64_t *pk = prm.pay_kmer + (size_t)p * prm.kmax, *pr = prm.pay_row + (size_t)p * prm.kmax;
