@@ -152,3 +152,31 @@ def test_topk_golden_through_filter_engine(kg, name, pair_limit):
         assert np.array_equal(k, g.z["top_kmers"][j])
         assert np.array_equal(_bits(s), _bits(g.z["top_scores"][j]))
     sess.close()
+
+
+def test_one_context_reused_with_more_phenotype_groups(kg):
+    """kg_scan_set_phenotypes may be called again on one context (MultipleKmersDataBases::ensure_phenotypes does): going
+    from 5 to 101 phenotypes needs seven 16-column groups where one was enough, so the filter's list buffers must be
+    re-sized for the new group count; then back to 3 phenotypes (the larger buffers are kept)."""
+    n_file, n_rows = 1135, 20000
+    table = S.synth_table(911, n_rows, n_file)
+    mc = S.min_count_of(n_file, 0.05, 5)
+    idx = np.arange(n_file)
+    ctx = kg.Context.identity(n_file)
+    ctx.set_option(kg.OPT_SCAN_ENGINE, 2)
+    for n_pheno in (5, 101, 3):
+        y = S.synth_phenotypes(920 + n_pheno, n_file, n_pheno)
+        keep_o, scores_o, kept_o = S.oracle_scan(table, n_file, idx // 64, idx % 64, y, mc)
+        thr = np.array([np.quantile(scores_o[j][keep_o], 0.99) for j in range(n_pheno)])
+        ctx.set_phenotypes(y, mc)
+        ctx.set_thresholds(thr)
+        ctx.scan_submit(table, n_rows, 0)
+        hits, seen, kept = ctx.scan_fetch()
+        assert seen == n_rows and kept == kept_o
+        for j in range(n_pheno):
+            sel = keep_o & (scores_o[j] > thr[j])
+            got = hits[hits["pheno"] == j]
+            order = np.argsort(got["row"], kind="stable")
+            assert np.array_equal(got["row"][order], np.nonzero(sel)[0])
+            assert np.array_equal(_bits(got["score"][order]), _bits(scores_o[j][sel]))
+    ctx.close()
