@@ -132,6 +132,24 @@ def test_select_per_phenotype_capacity_and_underfull(kg):
     ctx.close()
 
 
+@pytest.mark.parametrize("tie_patterns", [0, 53])
+def test_select_tiny_and_odd_capacities(kg, tie_patterns):
+    """Heap capacities 1 .. 33 around the powers of two: the sift's counted double steps, its bounded tail, the
+    single-left-child case and the record / slot-warp hand-off at every small heap shape; with tie_patterns the table
+    has 53 distinct presence patterns only, so most scores tie and the layout decides what is evicted."""
+    caps = [1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 31, 32, 33]
+    n_file, n_pheno, n_rows = 96, len(caps), 5000
+    table, y, mc, keep, scores, kept = _case(n_file, n_pheno, n_rows, 77, tie_patterns=tie_patterns)
+    kbest = np.array(caps, dtype=np.uint64)
+    want = _oracle_heaps(table, keep, scores, kbest)
+    for engine in (1, 2):
+        ctx, ka = _run_select(kg, table, y, mc, kbest, engine, n_file, [1500, 3500], growth=400)
+        applied, dkept = ctx.select_sync()
+        assert applied == n_rows and dkept == kept
+        _assert_heaps_equal(ctx.select_heaps(), want)
+        ctx.close()
+
+
 def test_select_overflow_recovery(kg):
     """a candidate segment that is too small poisons the round; sync reports how far the heaps got and the caller
     resubmits the rest (the library shortens its rounds)"""
