@@ -659,6 +659,7 @@ __global__ void __launch_bounds__(KG_SEL_THREADS) kg_select_replay_kernel(const 
 					h = __shfl_sync(0xffffffffu, h, 0);
 					if (h == ring_pos) __nanosleep(32);
 				} while (h == ring_pos);
+				__syncwarp();   // lane 0's acquire orders the other lanes' reads of the records as well
 				for (; ring_pos != h; ring_pos++) {
 					const uint4 r4 = *reinterpret_cast<const uint4 *>(&s_ring[ring_pos % KG_SEL_RING]);
 					KgHeapRec rec;
