@@ -576,12 +576,14 @@ __global__ void __launch_bounds__(256) kg_pair_select_kernel(const KgPairSelectP
 		const uint32_t n1 = prm.ent_n1[(size_t)k * prm.qcap + idx];
 		const int4 *qp = reinterpret_cast<const int4 *>(prm.ent_q + ((size_t)k * prm.qcap + idx) * 16);
 		int32_t q[16];
+		const int4 t0 = qp[0];
+		const bool untested = t0.x == KG_F_NO_Q;   // only the first 16 bytes of such an entry were written
+		q[0] = t0.x; q[1] = t0.y; q[2] = t0.z; q[3] = t0.w;
 #pragma unroll
-		for (int j = 0; j < 4; j++) {
-			const int4 t = qp[j];
+		for (int j = 1; j < 4; j++) {
+			const int4 t = untested ? make_int4(0, 0, 0, 0) : qp[j];
 			q[4 * j] = t.x; q[4 * j + 1] = t.y; q[4 * j + 2] = t.z; q[4 * j + 3] = t.w;
 		}
-		const bool untested = q[0] == KG_F_NO_Q;
 		const float n1f = (float)n1, n0f = Nf - n1f;
 		const uint32_t m = (uint32_t)fminf(n1f, n0f);
 		const float g = __fmul_rd(__fsqrt_rd(__fmul_rd(n1f, n0f)), 0.999999f);   // as kg_filter_group_threshold_n1
